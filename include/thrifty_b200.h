@@ -1,0 +1,159 @@
+/*
+ * thrifty_b200.h -- C ABI of the B200-native Thrifty `detect` hot path.
+ *
+ * One shared object (libthrifty_b200.so, built by nvcc for sm_100a) exposes the
+ * per-block detect chain of swkrueger/Thrifty:
+ *
+ *   uint8 IQ -> complex64 -> FFT -> windowed spectral-peak carrier detect ->
+ *   Dirichlet sub-bin fit -> time-domain mix -> FFT -> x conj(FFT(template)) ->
+ *   IFFT -> |corr| windowed peak + threshold -> Gaussian sub-sample offset -> SoA
+ *
+ * fused into a single persistent CUDA kernel (one launch per batch of blocks).
+ * No torch / numpy / cuFFT types cross this boundary: plain pointers and sizes.
+ *
+ * Reference interfaces this ABI replaces (paths inside the reference checkout):
+ *   - thrifty/detect.py:34-91        class Detector (ctor + detect())         -> thr_create / thr_detect_batch*
+ *   - thrifty/carrier_sync.py:82-118 DefaultSynchronizer                      -> fused (carrier stage of the kernel)
+ *   - thrifty/soa_estimator.py:42-124 SoaEstimator                            -> fused (correlation stage of the kernel)
+ *   - fastdet/corr_detector.h:24-45  CorrDetector(template, block_len, history_len, thresh...) / detect()
+ *   - fastcard/fastcard.h:46-53      fastcard_new / fastcard_process / fastcard_free (handle + int status model)
+ *
+ * Conventions (mirroring fastcard.h): opaque handle, int status (0 ok, <0 error),
+ * no exceptions, caller owns input/output buffers, the handle owns device scratch
+ * and the template spectra, one handle = one host thread + one CUDA stream.
+ */
+#ifndef THRIFTY_B200_H
+#define THRIFTY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define THR_ABI_VERSION 1
+
+/* status codes */
+#define THR_OK             0
+#define THR_ERR_INVALID   -1   /* bad argument / unsupported configuration   */
+#define THR_ERR_CUDA      -2   /* CUDA runtime error (see thr_last_error)    */
+#define THR_ERR_NOMEM     -3
+#define THR_ERR_NO_DEVICE -4   /* no usable sm_100 device                    */
+
+/* thr_record.flags */
+#define THR_FLAG_CARRIER_DETECTED 1u   /* carrier peak above threshold (carrier_sync.py:69)      */
+#define THR_FLAG_CORR_DETECTED    2u   /* correlation peak above threshold (soa_estimator.py:85) */
+
+typedef struct thr_detector thr_detector;
+
+/*
+ * Detector configuration == thrifty/detect.py:24-31 DetectorSettings plus
+ * launch geometry.  `templates` is borrowed only for the duration of thr_create.
+ */
+typedef struct thr_config {
+    int32_t block_len;        /* N, power of two, 1024..32768                            */
+    int32_t history_len;      /* H, samples repeated from the previous block             */
+    int32_t template_len;     /* L, samples per template; L <= N and H >= L-1            */
+    int32_t n_templates;      /* T >= 1 templates, stored back to back [T][L]            */
+    const double *templates;  /* real template samples (numpy .npy float64 layout)       */
+    int32_t carrier_len;      /* W of the Dirichlet kernel (detect.py:207: len(template))*/
+    int32_t window_start;     /* carrier window, signed bins, CLOSED interval            */
+    int32_t window_stop;      /*   (carrier_detect.py:17-58; 0,-1 = whole spectrum)      */
+    double carrier_thresh[3]; /* (constant, snr, stddev) -- setting_parsers.py:141-185   */
+    double corr_thresh[3];    /* (constant, snr, stddev)                                 */
+    int32_t device;           /* CUDA device ordinal                                     */
+    int32_t max_batch;        /* max blocks per launch (device staging is sized for it)  */
+    uint32_t flags;           /* reserved, must be 0                                     */
+    int32_t reserved;
+} thr_config;
+
+/*
+ * One record per (block, template): the fields of thrifty/toads_data.py:8-45
+ * (DetectionResult / CarrierSyncInfo / CorrDetectionInfo) as a 64-byte POD.
+ * timestamp / rxid stay on the host.  If the carrier is not detected the corr_*
+ * fields are: corr_sample = -1, others NaN, soa = NaN.
+ */
+typedef struct thr_record {
+    int64_t block_idx;        /* echo of the input block index                           */
+    double  soa;              /* (N-H)*block_idx + corr_sample + corr_offset (detect.py:67) */
+    int32_t carrier_bin;      /* FFT index of the carrier peak                           */
+    float   carrier_offset;   /* Dirichlet-fit sub-bin offset (0 if no carrier)          */
+    float   carrier_energy;   /* |X[bin]| (magnitude, as in the .toad column)            */
+    float   carrier_noise;    /* carrier noise rms estimate                              */
+    int32_t corr_sample;      /* correlation peak lag                                    */
+    float   corr_offset;      /* Gaussian sub-sample offset, clipped to +-0.6            */
+    float   corr_energy;      /* |corr[sample]|                                          */
+    float   corr_noise;       /* correlation noise rms estimate (may be NaN)             */
+    uint32_t flags;           /* THR_FLAG_*                                              */
+    int32_t template_idx;     /* which template this record belongs to                   */
+    float   signal_energy;    /* mean |X'|^2 == sum |x|^2 (soa_estimator.py:111)         */
+    float   reserved;
+} thr_record;
+
+typedef struct thr_info {
+    int32_t abi_version;
+    int32_t device;
+    int32_t sm_count;
+    int32_t grid;             /* CTAs per launch (persistent)                            */
+    int32_t threads;          /* threads per CTA                                         */
+    int32_t smem_bytes;       /* dynamic shared memory per CTA                           */
+    int32_t ctas_per_sm;
+    int32_t buffer_in_smem;   /* 1: FFT working set in shared memory; 0: global scratch  */
+    int64_t launches;         /* detect-kernel launches issued by this handle so far     */
+    char    device_name[64];
+    char    kernel[64];
+} thr_info;
+
+/* ---- lifecycle (cf. fastcard_new / fastcard_free) ---- */
+int  thr_create(const thr_config *cfg, thr_detector **out);
+void thr_destroy(thr_detector *det);
+/* Message for the last error on `det`, or for the last failed thr_create if det == NULL. */
+const char *thr_last_error(const thr_detector *det);
+int  thr_get_info(const thr_detector *det, thr_info *info);
+int  thr_device_count(void);
+
+/* ---- detection, host buffers (copies included; the reference-facing call) ----
+ * raw:       n_blocks * 2N uint8, interleaved I,Q (the payload of a .card line,
+ *            block_data.py:129-131 / fastcard/card_reader.c:69-75)
+ * block_idx: n_blocks int64 block indices (NULL -> 0,1,2,...)
+ * out:       n_blocks * n_templates records
+ * n_blocks may exceed max_batch; the call chunks and overlaps copies with compute. */
+int thr_detect_batch(thr_detector *det, const uint8_t *raw, const int64_t *block_idx,
+                     int64_t n_blocks, thr_record *out);
+/* Same, complex64 samples (interleaved re,im float32), n_blocks * N * 8 bytes:
+ * the type the Python seam passes (detect.py:60-62). */
+int thr_detect_batch_c64(thr_detector *det, const float *iq, const int64_t *block_idx,
+                         int64_t n_blocks, thr_record *out);
+
+/* ---- detection, device-resident buffers (async on the handle's stream) ----
+ * n_blocks <= max_batch.  Pointers are device pointers. */
+int thr_detect_batch_device(thr_detector *det, const uint8_t *d_raw, const int64_t *d_block_idx,
+                            int32_t n_blocks, thr_record *d_out);
+int thr_detect_batch_device_c64(thr_detector *det, const float *d_iq, const int64_t *d_block_idx,
+                                int32_t n_blocks, thr_record *d_out);
+
+/* One block with the intermediate arrays of Detector(yield_data=True) (detect.py:75-76):
+ * shifted_fft: N complex64 (may be NULL), corr: (N-L+1) complex64 (may be NULL),
+ * fft_mag: N float32 |FFT(block)| (may be NULL).  Host pointers; template 0. */
+int thr_detect_block_data(thr_detector *det, const uint8_t *raw, const float *iq, int64_t block_idx,
+                          thr_record *out, float *shifted_fft, float *corr, float *fft_mag);
+
+/* ---- stream / timing plumbing ---- */
+int thr_set_stream(thr_detector *det, void *cuda_stream);   /* NULL -> handle's own stream */
+int thr_synchronize(thr_detector *det);
+int thr_timer_start(thr_detector *det);                     /* CUDA event on the handle's stream */
+int thr_timer_stop(thr_detector *det, float *elapsed_ms);   /* records, synchronises, returns ms  */
+
+/* ---- memory helpers (so callers need no CUDA binding of their own) ---- */
+void *thr_host_alloc(size_t bytes);                         /* pinned host memory */
+void  thr_host_free(void *p);
+void *thr_device_alloc(int device, size_t bytes);
+void  thr_device_free(int device, void *p);
+int   thr_memcpy_h2d(int device, void *dst, const void *src, size_t bytes);
+int   thr_memcpy_d2h(int device, void *dst, const void *src, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* THRIFTY_B200_H */

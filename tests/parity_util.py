@@ -1,0 +1,98 @@
+"""Shared parity helpers: golden-config loading and record comparison.
+
+Parity definition (BASELINE.json north_star): flags equal; carrier bin and
+correlation peak sample bit-exact; magnitudes / noise within 1e-4 relative; sub-sample
+offsets within 1e-4 absolute; SoA within 1e-4 samples.  Blocks whose reference
+|peak/threshold - 1| < 1e-3 are 'marginal' (float32-vs-float64 rounding may flip the
+verdict) and are excluded from flag equality -- none of the committed goldens has one.
+"""
+import os
+import zlib
+
+import numpy as np
+
+from thrifty_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+RTOL_MAG = 1e-4
+ATOL_OFFSET = 1e-4
+
+
+def template_by_id(tid):
+    if tid == "example":
+        return np.load(os.path.join(GOLDEN, "template_example.npy"))
+    assert tid.startswith("gold")
+    bits, idx = tid[4:].split("_")
+    return synth.gold_template(int(bits), int(idx))
+
+
+def load_golden(name):
+    g = np.load(os.path.join(GOLDEN, "detect_%s.npz" % name))
+    cfg = dict(
+        name=name, block_len=int(g["block_len"]), history_len=int(g["history_len"]),
+        template=template_by_id(str(g["template_id"])), window=tuple(int(v) for v in g["window"]),
+        n_blocks=int(g["n_blocks"]), p_signal=float(g["p_signal"]),
+        bin_range=tuple(float(v) for v in g["bin_range"]),
+        cthresh=tuple(float(v) for v in g["cthresh"]), kthresh=tuple(float(v) for v in g["kthresh"]),
+        seed=int(g["seed"]))
+    gen_id = str(g["gen_template_id"])
+    gen_tpl = np.ones(len(cfg["template"])) if gen_id == "ones" else template_by_id(gen_id)
+    raw, _ = synth.make_blocks(cfg["n_blocks"], cfg["block_len"], cfg["history_len"], gen_tpl,
+                               cfg["p_signal"], seed=cfg["seed"], bin_range=cfg["bin_range"])
+    assert np.uint32(zlib.crc32(raw.tobytes())) == g["raw_crc32"], "synthetic generator drifted"
+    block_idx = 10 + 3 * np.arange(cfg["n_blocks"], dtype=np.int64)
+    return cfg, raw, block_idx, g["records"], [str(s) for s in g["toad_lines"]]
+
+
+GOLDEN_NAMES = ["n16384_example", "n8192_gold10", "n4096_gold9", "n4096_gold9_wrapwin_std",
+                "n4096_gold9_tone", "n32768_example"]
+
+
+def compare_records(got, ref, what=""):
+    """got: thr_record array [B] (one template); ref: oracle RECORD_DTYPE array [B]."""
+    assert len(got) == len(ref)
+    stats = dict(n=len(ref), carrier=0, detected=0, marginal=0, max_rel_corr_energy=0.0,
+                 max_abs_corr_offset=0.0, max_abs_carrier_offset=0.0, max_abs_soa=0.0)
+    for i in range(len(ref)):
+        r, g = ref[i], got[i]
+        tag = "%s block %d" % (what, i)
+        g_car = bool(g["flags"] & 1)
+        g_det = bool(g["flags"] & 2)
+        cm, km = r["carrier_margin"], r["corr_margin"]
+        marg_c = np.isfinite(cm) and abs(cm - 1) < 1e-3
+        marg_k = np.isfinite(km) and abs(km - 1) < 1e-3
+        if marg_c or marg_k:
+            stats["marginal"] += 1
+        assert g["block_idx"] == r["block_idx"], tag
+        if not marg_c:
+            assert g_car == bool(r["carrier_detected"]), tag + " carrier flag"
+        if not r["carrier_detected"] or not g_car:
+            continue
+        stats["carrier"] += 1
+        assert g["carrier_bin"] == r["carrier_bin"], tag + " carrier bin"
+        np.testing.assert_allclose(g["carrier_energy"], r["carrier_energy"], rtol=RTOL_MAG, err_msg=tag)
+        np.testing.assert_allclose(g["carrier_noise"], r["carrier_noise"], rtol=RTOL_MAG, err_msg=tag)
+        np.testing.assert_allclose(g["carrier_offset"], r["carrier_offset"], atol=ATOL_OFFSET, err_msg=tag)
+        stats["max_abs_carrier_offset"] = max(stats["max_abs_carrier_offset"],
+                                              abs(float(g["carrier_offset"]) - r["carrier_offset"]))
+        if not marg_k:
+            assert g_det == bool(r["corr_detected"]), tag + " corr flag"
+        assert g["corr_sample"] == r["corr_sample"], tag + " corr sample"
+        np.testing.assert_allclose(g["corr_energy"], r["corr_energy"], rtol=RTOL_MAG, err_msg=tag)
+        if np.isnan(r["corr_noise"]):
+            assert np.isnan(g["corr_noise"]), tag
+        else:
+            np.testing.assert_allclose(g["corr_noise"], r["corr_noise"], rtol=RTOL_MAG, err_msg=tag)
+        stats["max_rel_corr_energy"] = max(stats["max_rel_corr_energy"],
+                                           abs(float(g["corr_energy"]) / r["corr_energy"] - 1))
+        if g_det and r["corr_detected"]:
+            stats["detected"] += 1
+            np.testing.assert_allclose(g["corr_offset"], r["corr_offset"], atol=ATOL_OFFSET, err_msg=tag)
+            stats["max_abs_corr_offset"] = max(stats["max_abs_corr_offset"],
+                                               abs(float(g["corr_offset"]) - r["corr_offset"]))
+        if g_det == bool(r["corr_detected"]):
+            np.testing.assert_allclose(g["soa"], r["soa"], rtol=0, atol=ATOL_OFFSET, err_msg=tag + " soa")
+            stats["max_abs_soa"] = max(stats["max_abs_soa"], abs(float(g["soa"]) - r["soa"]))
+    return stats

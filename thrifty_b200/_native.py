@@ -1,0 +1,282 @@
+"""ctypes binding of libthrifty_b200.so (the C ABI in include/thrifty_b200.h).
+
+There is deliberately no fallback: if the shared object is missing or no sm_100
+device is usable, constructing a detector raises.  Build the library with
+``python -c "import __graft_entry__ as g; g.build()"`` or ``make -C thrifty_b200/csrc``.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import (POINTER, Structure, byref, c_char, c_char_p, c_double, c_float, c_int,
+                    c_int32, c_int64, c_size_t, c_uint32, c_void_p)
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libthrifty_b200.so")
+
+THR_OK = 0
+FLAG_CARRIER = 1
+FLAG_CORR = 2
+
+
+class NativeError(RuntimeError):
+    """A thr_* call returned a negative status."""
+
+
+class ThrConfig(Structure):
+    _fields_ = [
+        ("block_len", c_int32), ("history_len", c_int32), ("template_len", c_int32),
+        ("n_templates", c_int32), ("templates", POINTER(c_double)), ("carrier_len", c_int32),
+        ("window_start", c_int32), ("window_stop", c_int32),
+        ("carrier_thresh", c_double * 3), ("corr_thresh", c_double * 3),
+        ("device", c_int32), ("max_batch", c_int32), ("flags", c_uint32), ("reserved", c_int32),
+    ]
+
+
+class ThrInfo(Structure):
+    _fields_ = [
+        ("abi_version", c_int32), ("device", c_int32), ("sm_count", c_int32), ("grid", c_int32),
+        ("threads", c_int32), ("smem_bytes", c_int32), ("ctas_per_sm", c_int32),
+        ("buffer_in_smem", c_int32), ("launches", c_int64),
+        ("device_name", c_char * 64), ("kernel", c_char * 64),
+    ]
+
+
+# numpy view of thr_record (64 bytes)
+RECORD_DTYPE = np.dtype([
+    ("block_idx", "<i8"), ("soa", "<f8"),
+    ("carrier_bin", "<i4"), ("carrier_offset", "<f4"), ("carrier_energy", "<f4"), ("carrier_noise", "<f4"),
+    ("corr_sample", "<i4"), ("corr_offset", "<f4"), ("corr_energy", "<f4"), ("corr_noise", "<f4"),
+    ("flags", "<u4"), ("template_idx", "<i4"), ("signal_energy", "<f4"), ("reserved", "<f4"),
+])
+assert RECORD_DTYPE.itemsize == 64
+
+EXPORTS = [
+    "thr_create", "thr_destroy", "thr_last_error", "thr_get_info", "thr_device_count",
+    "thr_detect_batch", "thr_detect_batch_c64", "thr_detect_batch_device",
+    "thr_detect_batch_device_c64", "thr_detect_block_data", "thr_set_stream", "thr_synchronize",
+    "thr_timer_start", "thr_timer_stop", "thr_host_alloc", "thr_host_free", "thr_device_alloc",
+    "thr_device_free", "thr_memcpy_h2d", "thr_memcpy_d2h",
+]
+
+_lib = None
+
+
+def load_library(path=None):
+    """dlopen the shared object and declare prototypes.  Raises if it is missing."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise NativeError(
+            "libthrifty_b200.so not found at %s: build it (python -c 'import __graft_entry__ as g; "
+            "g.build()'); there is no CPU fallback for the detect path" % path)
+    lib = ctypes.CDLL(path)
+    lib.thr_create.argtypes = [POINTER(ThrConfig), POINTER(c_void_p)]
+    lib.thr_create.restype = c_int
+    lib.thr_destroy.argtypes = [c_void_p]
+    lib.thr_destroy.restype = None
+    lib.thr_last_error.argtypes = [c_void_p]
+    lib.thr_last_error.restype = c_char_p
+    lib.thr_get_info.argtypes = [c_void_p, POINTER(ThrInfo)]
+    lib.thr_get_info.restype = c_int
+    lib.thr_device_count.argtypes = []
+    lib.thr_device_count.restype = c_int
+    lib.thr_detect_batch.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]
+    lib.thr_detect_batch.restype = c_int
+    lib.thr_detect_batch_c64.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]
+    lib.thr_detect_batch_c64.restype = c_int
+    lib.thr_detect_batch_device.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_void_p]
+    lib.thr_detect_batch_device.restype = c_int
+    lib.thr_detect_batch_device_c64.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_void_p]
+    lib.thr_detect_batch_device_c64.restype = c_int
+    lib.thr_detect_block_data.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
+                                          c_void_p, c_void_p, c_void_p]
+    lib.thr_detect_block_data.restype = c_int
+    lib.thr_set_stream.argtypes = [c_void_p, c_void_p]
+    lib.thr_set_stream.restype = c_int
+    lib.thr_synchronize.argtypes = [c_void_p]
+    lib.thr_synchronize.restype = c_int
+    lib.thr_timer_start.argtypes = [c_void_p]
+    lib.thr_timer_start.restype = c_int
+    lib.thr_timer_stop.argtypes = [c_void_p, POINTER(c_float)]
+    lib.thr_timer_stop.restype = c_int
+    lib.thr_host_alloc.argtypes = [c_size_t]
+    lib.thr_host_alloc.restype = c_void_p
+    lib.thr_host_free.argtypes = [c_void_p]
+    lib.thr_host_free.restype = None
+    lib.thr_device_alloc.argtypes = [c_int, c_size_t]
+    lib.thr_device_alloc.restype = c_void_p
+    lib.thr_device_free.argtypes = [c_int, c_void_p]
+    lib.thr_device_free.restype = None
+    lib.thr_memcpy_h2d.argtypes = [c_int, c_void_p, c_void_p, c_size_t]
+    lib.thr_memcpy_h2d.restype = c_int
+    lib.thr_memcpy_d2h.argtypes = [c_int, c_void_p, c_void_p, c_size_t]
+    lib.thr_memcpy_d2h.restype = c_int
+    if path == LIB_PATH:
+        _lib = lib
+    return lib
+
+
+class PinnedBuffer(object):
+    """Page-locked host memory exposed as a numpy uint8 array (thr_host_alloc)."""
+
+    def __init__(self, nbytes):
+        self._lib = load_library()
+        self.ptr = self._lib.thr_host_alloc(nbytes)
+        if not self.ptr:
+            raise NativeError("thr_host_alloc(%d) failed" % nbytes)
+        self.nbytes = nbytes
+        self.array = np.ctypeslib.as_array((ctypes.c_uint8 * nbytes).from_address(self.ptr))
+
+    def close(self):
+        if self.ptr:
+            self.array = None
+            self._lib.thr_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class NativeDetector(object):
+    """Thin owner of a thr_detector handle."""
+
+    def __init__(self, block_len, history_len, templates, carrier_len, carrier_window,
+                 carrier_thresh, corr_thresh, device=0, max_batch=4096):
+        self._lib = load_library()
+        self._h = c_void_p()
+        tpl = np.ascontiguousarray(np.atleast_2d(np.asarray(templates, dtype=np.float64)))
+        self.n_templates, self.template_len = tpl.shape
+        self.block_len = int(block_len)
+        self.history_len = int(history_len)
+        self.max_batch = int(max_batch)
+        self.device = int(device)
+        cfg = ThrConfig()
+        cfg.block_len = self.block_len
+        cfg.history_len = self.history_len
+        cfg.template_len = self.template_len
+        cfg.n_templates = self.n_templates
+        cfg.templates = tpl.ctypes.data_as(POINTER(c_double))
+        cfg.carrier_len = int(carrier_len)
+        win = (0, -1) if carrier_window is None else carrier_window
+        cfg.window_start, cfg.window_stop = int(win[0]), int(win[1])
+        cfg.carrier_thresh = (c_double * 3)(*[float(v) for v in carrier_thresh])
+        cfg.corr_thresh = (c_double * 3)(*[float(v) for v in corr_thresh])
+        cfg.device = self.device
+        cfg.max_batch = self.max_batch
+        cfg.flags = 0
+        rc = self._lib.thr_create(byref(cfg), byref(self._h))
+        if rc != THR_OK:
+            msg = self._lib.thr_last_error(None).decode()
+            self._h = c_void_p()
+            if "out of range" in msg and "window" in msg:
+                raise ValueError(msg)            # carrier_detect.py:47-49 raises ValueError
+            raise NativeError("thr_create failed (%d): %s" % (rc, msg))
+
+    # -- helpers
+    def _check(self, rc):
+        if rc != THR_OK:
+            raise NativeError("thrifty_b200 call failed (%d): %s"
+                              % (rc, self._lib.thr_last_error(self._h).decode()))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def info(self):
+        info = ThrInfo()
+        self._check(self._lib.thr_get_info(self._h, byref(info)))
+        return {k: (getattr(info, k).decode() if isinstance(getattr(info, k), bytes) else getattr(info, k))
+                for k, _ in ThrInfo._fields_}
+
+    def close(self):
+        if self._h:
+            self._lib.thr_destroy(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- host-buffer API
+    def detect_raw(self, raw, block_idx=None):
+        """raw: uint8 [B, 2N] (C-contiguous).  Returns records [B, n_templates]."""
+        raw = np.ascontiguousarray(raw, dtype=np.uint8)
+        if raw.ndim != 2 or raw.shape[1] != 2 * self.block_len:
+            raise ValueError("raw must have shape [B, %d]" % (2 * self.block_len))
+        nblk = raw.shape[0]
+        out = np.zeros((nblk, self.n_templates), dtype=RECORD_DTYPE)
+        idx_ptr = None
+        if block_idx is not None:
+            idx = np.ascontiguousarray(block_idx, dtype=np.int64)
+            assert idx.shape == (nblk,)
+            idx_ptr = idx.ctypes.data
+        self._check(self._lib.thr_detect_batch(self._h, raw.ctypes.data, idx_ptr, nblk, out.ctypes.data))
+        return out
+
+    def detect_c64(self, iq, block_idx=None):
+        """iq: complex64 [B, N].  Returns records [B, n_templates]."""
+        iq = np.ascontiguousarray(iq, dtype=np.complex64)
+        if iq.ndim != 2 or iq.shape[1] != self.block_len:
+            raise ValueError("iq must have shape [B, %d]" % self.block_len)
+        nblk = iq.shape[0]
+        out = np.zeros((nblk, self.n_templates), dtype=RECORD_DTYPE)
+        idx_ptr = None
+        if block_idx is not None:
+            idx = np.ascontiguousarray(block_idx, dtype=np.int64)
+            assert idx.shape == (nblk,)
+            idx_ptr = idx.ctypes.data
+        self._check(self._lib.thr_detect_batch_c64(self._h, iq.ctypes.data, idx_ptr, nblk, out.ctypes.data))
+        return out
+
+    def detect_block_data(self, raw=None, iq=None, block_idx=0):
+        """One block with intermediates -> (record[n_templates], shifted_fft, corr, fft_mag)."""
+        n = self.block_len
+        corr_len = n - self.template_len + 1
+        out = np.zeros(self.n_templates, dtype=RECORD_DTYPE)
+        sfft = np.zeros(n, dtype=np.complex64)
+        corr = np.zeros(corr_len, dtype=np.complex64)
+        mag = np.zeros(n, dtype=np.float32)
+        raw_ptr = iq_ptr = None
+        if raw is not None:
+            raw = np.ascontiguousarray(raw, dtype=np.uint8)
+            assert raw.shape == (2 * n,)
+            raw_ptr = raw.ctypes.data
+        else:
+            iq = np.ascontiguousarray(iq, dtype=np.complex64)
+            assert iq.shape == (n,)
+            iq_ptr = iq.ctypes.data
+        self._check(self._lib.thr_detect_block_data(self._h, raw_ptr, iq_ptr, int(block_idx), out.ctypes.data,
+                                                    sfft.ctypes.data, corr.ctypes.data, mag.ctypes.data))
+        return out, sfft, corr, mag
+
+    # -- device-buffer API (pointers are integers, e.g. torch.Tensor.data_ptr())
+    def detect_device(self, d_raw, d_block_idx, n_blocks, d_out):
+        self._check(self._lib.thr_detect_batch_device(self._h, d_raw, d_block_idx, int(n_blocks), d_out))
+
+    def detect_device_c64(self, d_iq, d_block_idx, n_blocks, d_out):
+        self._check(self._lib.thr_detect_batch_device_c64(self._h, d_iq, d_block_idx, int(n_blocks), d_out))
+
+    def set_stream(self, cuda_stream):
+        self._check(self._lib.thr_set_stream(self._h, cuda_stream))
+
+    def synchronize(self):
+        self._check(self._lib.thr_synchronize(self._h))
+
+    def timer_start(self):
+        self._check(self._lib.thr_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = c_float()
+        self._check(self._lib.thr_timer_stop(self._h, byref(ms)))
+        return ms.value

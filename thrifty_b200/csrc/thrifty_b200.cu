@@ -1,0 +1,539 @@
+// thrifty_b200.cu -- C ABI (include/thrifty_b200.h) over the fused detect kernel.
+//
+// Host-side duties: validate the DetectorSettings (same checks as the reference:
+// carrier_detect.py:47-49 window range, soa_estimator.py:33 history >= template-1),
+// build conj(FFT(template || 0))/N in float64 (soa_estimator.py:63-76) and lay it out in
+// the kernel's digit-reversed order, own device scratch/staging, launch.
+//
+// The product path has no CPU fallback: every entry point fails with THR_ERR_* if the
+// device or the kernel is unavailable.
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <complex>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/thrifty_b200.h"
+#include "detect_kernel.cuh"
+
+using thr::DetectParams;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Variant {
+    int log2n;
+    int threads;
+    bool gmem;
+    int r2, r3, i3;
+    size_t smem;
+    const void *fn;
+    const char *name;
+};
+
+template <int LOG2N, int T, bool GMEM>
+Variant make_variant(const char *name) {
+    using C = thr::Cfg<LOG2N, T, GMEM>;
+    Variant v;
+    v.log2n = LOG2N;
+    v.threads = T;
+    v.gmem = GMEM;
+    v.r2 = C::R2;
+    v.r3 = C::R3;
+    v.i3 = C::I3;
+    v.smem = C::smem_bytes();
+    v.fn = (const void *)&thr::detect_kernel<LOG2N, T, GMEM>;
+    v.name = name;
+    return v;
+}
+
+bool pick_variant(int n, Variant *out) {
+    switch (n) {
+        case 1024:  *out = make_variant<10, 32, false>("detect_kernel<N=1024,T=32,smem>"); return true;
+        case 2048:  *out = make_variant<11, 64, false>("detect_kernel<N=2048,T=64,smem>"); return true;
+        case 4096:  *out = make_variant<12, 128, false>("detect_kernel<N=4096,T=128,smem>"); return true;
+        case 8192:  *out = make_variant<13, 256, false>("detect_kernel<N=8192,T=256,smem>"); return true;
+        case 16384: *out = make_variant<14, 512, false>("detect_kernel<N=16384,T=512,smem>"); return true;
+        case 32768: *out = make_variant<15, 512, true>("detect_kernel<N=32768,T=512,gmem>"); return true;
+        default: return false;
+    }
+}
+
+struct Slot {                 // one in-flight chunk of the host-buffer API
+    cudaStream_t stream = nullptr;
+    uint8_t *d_in = nullptr;  // raw u8 staging (max_batch * 2N)
+    int64_t *d_idx = nullptr;
+    thr_record *d_out = nullptr;
+    float *d_iq = nullptr;    // complex64 staging (lazily, c64_chunk * N * 8)
+};
+
+}  // namespace
+
+struct thr_detector {
+    thr_config cfg;
+    Variant var;
+    int device = 0;
+    int sm_count = 0;
+    int ctas_per_sm = 1;
+    int grid = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;       // stream used by the *_device entry points
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float2 *d_tpl = nullptr;
+    float *d_tpl_energy = nullptr;
+    float2 *d_scratch = nullptr;
+    float2 *d_xsave = nullptr;
+    Slot slot[2];
+    int c64_chunk = 0;
+    DetectParams base;                   // constant part of the kernel parameters
+    int64_t launches = 0;
+    std::string err;
+    char device_name[64];
+};
+
+namespace {
+
+int fail(thr_detector *d, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (d) d->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU(d, call)                                                                          \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess)                                                               \
+            return fail((d), THR_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));  \
+    } while (0)
+
+// float64 radix-2 FFT (host, setup only)
+void fft_f64(std::vector<std::complex<double>> &a) {
+    const size_t n = a.size();
+    for (size_t i = 1, j = 0; i < n; ++i) {
+        size_t bit = n >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) std::swap(a[i], a[j]);
+    }
+    const double pi = 3.14159265358979323846;
+    for (size_t len = 2; len <= n; len <<= 1) {
+        std::vector<std::complex<double>> w(len / 2);
+        for (size_t k = 0; k < len / 2; ++k)
+            w[k] = std::complex<double>(std::cos(2 * pi * k / len), -std::sin(2 * pi * k / len));
+        for (size_t i = 0; i < n; i += len)
+            for (size_t k = 0; k < len / 2; ++k) {
+                const std::complex<double> u = a[i + k], v = a[i + k + len / 2] * w[k];
+                a[i + k] = u + v;
+                a[i + k + len / 2] = u - v;
+            }
+    }
+}
+
+// carrier_detect.py:17-58 fft_range_index
+bool range_index(int start, int stop, int length, int *s, int *e) {
+    if (std::abs(start) >= length || std::abs(stop) >= length) return false;
+    if (start < 0 && stop >= 0) { start += length; stop += length; }
+    if (start < 0) start += length;
+    if (stop < 0) stop += length;
+    if (stop < start) std::swap(start, stop);
+    *s = start;
+    *e = stop;
+    return true;
+}
+
+int launch(thr_detector *d, cudaStream_t st, const uint8_t *d_raw, const float *d_iq, const int64_t *d_idx,
+           int n_blocks, thr_record *d_out, float2 *dbg_sfft, float2 *dbg_corr, float *dbg_mag) {
+    if (n_blocks <= 0) return THR_OK;
+    DetectParams p = d->base;
+    p.raw = d_raw;
+    p.iq = reinterpret_cast<const float2 *>(d_iq);
+    p.block_idx = d_idx;
+    p.out = d_out;
+    p.n_blocks = n_blocks;
+    p.dbg_shifted_fft = dbg_sfft;
+    p.dbg_corr = dbg_corr;
+    p.dbg_fft_mag = dbg_mag;
+    const int grid = n_blocks < d->grid ? n_blocks : d->grid;
+    void *args[] = {&p};
+    CU(d, cudaLaunchKernel(d->var.fn, dim3(grid), dim3(d->var.threads), args, d->var.smem, st));
+    d->launches++;
+    return THR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int thr_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+const char *thr_last_error(const thr_detector *det) {
+    return det ? det->err.c_str() : g_create_error.c_str();
+}
+
+void thr_destroy(thr_detector *d) {
+    if (!d) return;
+    cudaSetDevice(d->device);
+    for (auto &s : d->slot) {
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        cudaFree(s.d_in);
+        cudaFree(s.d_idx);
+        cudaFree(s.d_out);
+        cudaFree(s.d_iq);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    if (d->own_stream) { cudaStreamSynchronize(d->own_stream); cudaStreamDestroy(d->own_stream); }
+    if (d->ev0) cudaEventDestroy(d->ev0);
+    if (d->ev1) cudaEventDestroy(d->ev1);
+    cudaFree(d->d_tpl);
+    cudaFree(d->d_tpl_energy);
+    cudaFree(d->d_scratch);
+    cudaFree(d->d_xsave);
+    delete d;
+}
+
+int thr_create(const thr_config *cfg, thr_detector **out) {
+    if (!cfg || !out) return fail(nullptr, THR_ERR_INVALID, "null argument");
+    *out = nullptr;
+    const int N = cfg->block_len, H = cfg->history_len, L = cfg->template_len, NT = cfg->n_templates;
+    Variant var;
+    if (!pick_variant(N, &var))
+        return fail(nullptr, THR_ERR_INVALID, "unsupported block_len %d (power of two 1024..32768)", N);
+    if (NT < 1 || NT > 32) return fail(nullptr, THR_ERR_INVALID, "n_templates must be 1..32");
+    if (!cfg->templates || L < 1 || L > N) return fail(nullptr, THR_ERR_INVALID, "bad template (len %d)", L);
+    if (H < L - 1 || H >= N)   // soa_estimator.py:33 assert history_len >= template_len - 1
+        return fail(nullptr, THR_ERR_INVALID, "history_len %d must satisfy template_len-1 <= H < block_len", H);
+    if (cfg->carrier_len < 1) return fail(nullptr, THR_ERR_INVALID, "carrier_len must be positive");
+    if (cfg->max_batch < 1) return fail(nullptr, THR_ERR_INVALID, "max_batch must be positive");
+    if (cfg->flags != 0) return fail(nullptr, THR_ERR_INVALID, "flags must be 0");
+    int ws, we;
+    if (!range_index(cfg->window_start, cfg->window_stop, N, &ws, &we))   // carrier_detect.py:47-49
+        return fail(nullptr, THR_ERR_INVALID, "Frequency window out of range: %d - %d", cfg->window_start,
+                    cfg->window_stop);
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, THR_ERR_NO_DEVICE, "no CUDA device available");
+    if (cfg->device < 0 || cfg->device >= ndev)
+        return fail(nullptr, THR_ERR_INVALID, "device ordinal %d out of range (%d devices)", cfg->device, ndev);
+
+    thr_detector *d = new thr_detector();
+    d->cfg = *cfg;
+    d->cfg.templates = nullptr;
+    d->var = var;
+    d->device = cfg->device;
+    auto bail = [&](int code) { g_create_error = d->err; thr_destroy(d); return code; };
+#define CUC(call)                                                                            \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess) {                                                             \
+            fail(d, THR_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));           \
+            return bail(THR_ERR_CUDA);                                                       \
+        }                                                                                    \
+    } while (0)
+
+    CUC(cudaSetDevice(d->device));
+    cudaDeviceProp prop;
+    CUC(cudaGetDeviceProperties(&prop, d->device));
+    std::snprintf(d->device_name, sizeof d->device_name, "%s", prop.name);
+    if (prop.major != 10) {
+        fail(d, THR_ERR_NO_DEVICE, "device %d (%s, sm_%d%d) is not sm_100: this library only carries sm_100a code",
+             d->device, prop.name, prop.major, prop.minor);
+        return bail(THR_ERR_NO_DEVICE);
+    }
+    d->sm_count = prop.multiProcessorCount;
+    CUC(cudaFuncSetAttribute(var.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)var.smem));
+    int occ = 0;
+    CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, var.fn, var.threads, var.smem));
+    if (occ < 1) {
+        fail(d, THR_ERR_CUDA, "kernel %s does not fit on an SM (smem %zu)", var.name, var.smem);
+        return bail(THR_ERR_CUDA);
+    }
+    d->ctas_per_sm = occ;
+    d->grid = d->sm_count * occ;
+
+    CUC(cudaStreamCreateWithFlags(&d->own_stream, cudaStreamNonBlocking));
+    d->stream = d->own_stream;
+    CUC(cudaEventCreate(&d->ev0));
+    CUC(cudaEventCreate(&d->ev1));
+
+    // ---- template spectra: conj(FFT(template || zeros))/N, float64 -> float32, kernel order
+    {
+        const int T = var.threads, R2 = var.r2, R3 = var.r3, I3 = var.i3;
+        std::vector<float2> perm((size_t)NT * N);
+        std::vector<float> energy(NT);
+        std::vector<std::complex<double>> a(N);
+        for (int t = 0; t < NT; ++t) {
+            double e = 0.0;
+            for (int i = 0; i < N; ++i) {
+                const double v = i < L ? cfg->templates[(size_t)t * L + i] : 0.0;
+                a[i] = v;
+                e += v * v;
+            }
+            energy[t] = (float)e;
+            fft_f64(a);
+            for (int i = 0; i < I3; ++i)
+                for (int k3 = 0; k3 < R3; ++k3)
+                    for (int tid = 0; tid < T; ++tid) {
+                        const int g = tid + T * i;
+                        const int k = (g / R2) + 32 * (g % R2) + 32 * R2 * k3;
+                        perm[(size_t)t * N + (size_t)(i * R3 + k3) * T + tid] =
+                            make_float2((float)(a[k].real() / N), (float)(-a[k].imag() / N));
+                    }
+        }
+        CUC(cudaMalloc(&d->d_tpl, perm.size() * sizeof(float2)));
+        CUC(cudaMemcpy(d->d_tpl, perm.data(), perm.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        CUC(cudaMalloc(&d->d_tpl_energy, NT * sizeof(float)));
+        CUC(cudaMemcpy(d->d_tpl_energy, energy.data(), NT * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    if (var.gmem) CUC(cudaMalloc(&d->d_scratch, (size_t)d->grid * N * sizeof(float2)));
+    if (NT > 1) CUC(cudaMalloc(&d->d_xsave, (size_t)d->grid * N * sizeof(float2)));
+    for (auto &s : d->slot) {
+        CUC(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        CUC(cudaMalloc(&s.d_in, (size_t)cfg->max_batch * 2 * N));
+        CUC(cudaMalloc(&s.d_idx, (size_t)cfg->max_batch * sizeof(int64_t)));
+        CUC(cudaMalloc(&s.d_out, (size_t)cfg->max_batch * NT * sizeof(thr_record)));
+    }
+    d->c64_chunk = cfg->max_batch < 512 ? cfg->max_batch : 512;
+
+    // ---- constant kernel parameters
+    DetectParams &p = d->base;
+    std::memset(&p, 0, sizeof p);
+    p.n_templates = NT;
+    p.tpl_spec = d->d_tpl;
+    p.tpl_energy = d->d_tpl_energy;
+    p.scratch = d->d_scratch;
+    p.xsave = d->d_xsave;
+    p.win_start = ws % N;
+    p.win_len = (we - ws + 1) > N ? N : (we - ws + 1);
+    p.c_const = (float)cfg->carrier_thresh[0];
+    p.c_snr = (float)cfg->carrier_thresh[1];
+    p.c_std = (float)cfg->carrier_thresh[2];
+    p.k_const = (float)cfg->corr_thresh[0];
+    p.k_snr = (float)cfg->corr_thresh[1];
+    p.k_std = (float)cfg->corr_thresh[2];
+    {   // soa_estimator.py:20-39 calculate_window
+        const int corr_len = N - L + 1, padding = H - L + 1, left = padding / 2, right = padding - left;
+        p.corr_len = corr_len;
+        p.corr_start = left;
+        p.corr_stop = corr_len - right;
+    }
+    p.new_len = N - H;
+    {
+        const double pi = 3.14159265358979323846, a = pi / N, W = cfg->carrier_len;
+        for (int i = 0; i < 7; ++i) {
+            const double x = i - 3;
+            p.fit_tab[i][0] = (float)std::sin(a * W * x);
+            p.fit_tab[i][1] = (float)std::cos(a * W * x);
+            p.fit_tab[i][2] = (float)std::sin(a * x);
+            p.fit_tab[i][3] = (float)std::cos(a * x);
+        }
+        p.fit_W = (float)W;
+        p.fit_WoverN = (float)(W / N);
+        p.fit_invN = (float)(1.0 / N);
+    }
+    *out = d;
+    return THR_OK;
+#undef CUC
+}
+
+int thr_get_info(const thr_detector *d, thr_info *info) {
+    if (!d || !info) return THR_ERR_INVALID;
+    std::memset(info, 0, sizeof *info);
+    info->abi_version = THR_ABI_VERSION;
+    info->device = d->device;
+    info->sm_count = d->sm_count;
+    info->grid = d->grid;
+    info->threads = d->var.threads;
+    info->smem_bytes = (int32_t)d->var.smem;
+    info->ctas_per_sm = d->ctas_per_sm;
+    info->buffer_in_smem = d->var.gmem ? 0 : 1;
+    info->launches = d->launches;
+    std::snprintf(info->device_name, sizeof info->device_name, "%s", d->device_name);
+    std::snprintf(info->kernel, sizeof info->kernel, "%s", d->var.name);
+    return THR_OK;
+}
+
+int thr_set_stream(thr_detector *d, void *cuda_stream) {
+    if (!d) return THR_ERR_INVALID;
+    d->stream = cuda_stream ? (cudaStream_t)cuda_stream : d->own_stream;
+    return THR_OK;
+}
+
+int thr_synchronize(thr_detector *d) {
+    if (!d) return THR_ERR_INVALID;
+    CU(d, cudaSetDevice(d->device));
+    CU(d, cudaStreamSynchronize(d->stream));
+    for (auto &s : d->slot) CU(d, cudaStreamSynchronize(s.stream));
+    return THR_OK;
+}
+
+int thr_timer_start(thr_detector *d) {
+    if (!d) return THR_ERR_INVALID;
+    CU(d, cudaSetDevice(d->device));
+    CU(d, cudaEventRecord(d->ev0, d->stream));
+    return THR_OK;
+}
+
+int thr_timer_stop(thr_detector *d, float *ms) {
+    if (!d || !ms) return THR_ERR_INVALID;
+    CU(d, cudaSetDevice(d->device));
+    CU(d, cudaEventRecord(d->ev1, d->stream));
+    CU(d, cudaEventSynchronize(d->ev1));
+    CU(d, cudaEventElapsedTime(ms, d->ev0, d->ev1));
+    return THR_OK;
+}
+
+int thr_detect_batch_device(thr_detector *d, const uint8_t *d_raw, const int64_t *d_idx, int32_t n_blocks,
+                            thr_record *d_out) {
+    if (!d || !d_raw || !d_out || n_blocks < 0) return d ? fail(d, THR_ERR_INVALID, "null/negative argument") : THR_ERR_INVALID;
+    if (n_blocks > d->cfg.max_batch) return fail(d, THR_ERR_INVALID, "n_blocks %d exceeds max_batch %d", n_blocks, d->cfg.max_batch);
+    if (((uintptr_t)d_raw & 15) != 0) return fail(d, THR_ERR_INVALID, "d_raw must be 16-byte aligned (TMA bulk copy)");
+    CU(d, cudaSetDevice(d->device));
+    return launch(d, d->stream, d_raw, nullptr, d_idx, n_blocks, d_out, nullptr, nullptr, nullptr);
+}
+
+int thr_detect_batch_device_c64(thr_detector *d, const float *d_iq, const int64_t *d_idx, int32_t n_blocks,
+                                thr_record *d_out) {
+    if (!d || !d_iq || !d_out || n_blocks < 0) return d ? fail(d, THR_ERR_INVALID, "null/negative argument") : THR_ERR_INVALID;
+    if (n_blocks > d->cfg.max_batch) return fail(d, THR_ERR_INVALID, "n_blocks %d exceeds max_batch %d", n_blocks, d->cfg.max_batch);
+    if (((uintptr_t)d_iq & 7) != 0) return fail(d, THR_ERR_INVALID, "d_iq must be 8-byte aligned");
+    CU(d, cudaSetDevice(d->device));
+    return launch(d, d->stream, nullptr, d_iq, d_idx, n_blocks, d_out, nullptr, nullptr, nullptr);
+}
+
+static int detect_host(thr_detector *d, const uint8_t *raw, const float *iq, const int64_t *block_idx,
+                       int64_t n_blocks, thr_record *out) {
+    if (!d || (!raw && !iq) || !out || n_blocks < 0) return d ? fail(d, THR_ERR_INVALID, "null/negative argument") : THR_ERR_INVALID;
+    CU(d, cudaSetDevice(d->device));
+    const int N = d->cfg.block_len, NT = d->cfg.n_templates;
+    const int64_t chunk = raw ? d->cfg.max_batch : d->c64_chunk;
+    if (iq) {
+        for (auto &s : d->slot)
+            if (!s.d_iq) CU(d, cudaMalloc(&s.d_iq, (size_t)d->c64_chunk * N * 8));
+    }
+    std::vector<int64_t> iota;
+    int c = 0;
+    for (int64_t b0 = 0; b0 < n_blocks; b0 += chunk, ++c) {
+        Slot &s = d->slot[c & 1];
+        const int nb = (int)((n_blocks - b0) < chunk ? (n_blocks - b0) : chunk);
+        if (raw)
+            CU(d, cudaMemcpyAsync(s.d_in, raw + (size_t)b0 * 2 * N, (size_t)nb * 2 * N, cudaMemcpyHostToDevice, s.stream));
+        else
+            CU(d, cudaMemcpyAsync(s.d_iq, iq + (size_t)b0 * 2 * N, (size_t)nb * N * 8, cudaMemcpyHostToDevice, s.stream));
+        if (block_idx) {
+            CU(d, cudaMemcpyAsync(s.d_idx, block_idx + b0, (size_t)nb * sizeof(int64_t), cudaMemcpyHostToDevice, s.stream));
+        } else {
+            iota.resize(nb);
+            for (int i = 0; i < nb; ++i) iota[i] = b0 + i;
+            // pageable source: the copy is staged before the call returns, so `iota` may be reused
+            CU(d, cudaMemcpyAsync(s.d_idx, iota.data(), (size_t)nb * sizeof(int64_t), cudaMemcpyHostToDevice, s.stream));
+        }
+        int rc = launch(d, s.stream, raw ? s.d_in : nullptr, raw ? nullptr : s.d_iq, s.d_idx, nb, s.d_out, nullptr,
+                        nullptr, nullptr);
+        if (rc != THR_OK) return rc;
+        CU(d, cudaMemcpyAsync(out + (size_t)b0 * NT, s.d_out, (size_t)nb * NT * sizeof(thr_record),
+                              cudaMemcpyDeviceToHost, s.stream));
+    }
+    for (auto &s : d->slot) CU(d, cudaStreamSynchronize(s.stream));
+    CU(d, cudaGetLastError());
+    return THR_OK;
+}
+
+int thr_detect_batch(thr_detector *d, const uint8_t *raw, const int64_t *block_idx, int64_t n_blocks,
+                     thr_record *out) {
+    if (!raw) return d ? fail(d, THR_ERR_INVALID, "raw is NULL") : THR_ERR_INVALID;
+    return detect_host(d, raw, nullptr, block_idx, n_blocks, out);
+}
+
+int thr_detect_batch_c64(thr_detector *d, const float *iq, const int64_t *block_idx, int64_t n_blocks,
+                         thr_record *out) {
+    if (!iq) return d ? fail(d, THR_ERR_INVALID, "iq is NULL") : THR_ERR_INVALID;
+    return detect_host(d, nullptr, iq, block_idx, n_blocks, out);
+}
+
+int thr_detect_block_data(thr_detector *d, const uint8_t *raw, const float *iq, int64_t block_idx, thr_record *out,
+                          float *shifted_fft, float *corr, float *fft_mag) {
+    if (!d || (!raw && !iq) || !out) return d ? fail(d, THR_ERR_INVALID, "null argument") : THR_ERR_INVALID;
+    CU(d, cudaSetDevice(d->device));
+    const int N = d->cfg.block_len, NT = d->cfg.n_templates, L = d->cfg.template_len;
+    const int corr_len = N - L + 1;
+    Slot &s = d->slot[0];
+    float2 *d_sfft = nullptr, *d_corr = nullptr;
+    float *d_mag = nullptr;
+    int rc = THR_OK;
+    cudaError_t e = cudaSuccess;
+    auto done = [&](int code) {
+        cudaFree(d_sfft);
+        cudaFree(d_corr);
+        cudaFree(d_mag);
+        return code;
+    };
+#define CUD(call)                                                                                    \
+    do {                                                                                             \
+        e = (call);                                                                                  \
+        if (e != cudaSuccess) return done(fail(d, THR_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e))); \
+    } while (0)
+    CUD(cudaMalloc(&d_sfft, (size_t)N * 8));
+    CUD(cudaMalloc(&d_corr, (size_t)corr_len * 8));
+    CUD(cudaMalloc(&d_mag, (size_t)N * 4));
+    CUD(cudaMemsetAsync(d_sfft, 0, (size_t)N * 8, s.stream));
+    CUD(cudaMemsetAsync(d_corr, 0, (size_t)corr_len * 8, s.stream));
+    if (iq && !s.d_iq) CUD(cudaMalloc(&s.d_iq, (size_t)d->c64_chunk * N * 8));
+    if (raw) CUD(cudaMemcpyAsync(s.d_in, raw, (size_t)2 * N, cudaMemcpyHostToDevice, s.stream));
+    else CUD(cudaMemcpyAsync(s.d_iq, iq, (size_t)N * 8, cudaMemcpyHostToDevice, s.stream));
+    CUD(cudaMemcpyAsync(s.d_idx, &block_idx, sizeof(int64_t), cudaMemcpyHostToDevice, s.stream));
+    rc = launch(d, s.stream, raw ? s.d_in : nullptr, raw ? nullptr : s.d_iq, s.d_idx, 1, s.d_out, d_sfft, d_corr, d_mag);
+    if (rc != THR_OK) return done(rc);
+    CUD(cudaMemcpyAsync(out, s.d_out, (size_t)NT * sizeof(thr_record), cudaMemcpyDeviceToHost, s.stream));
+    if (shifted_fft) CUD(cudaMemcpyAsync(shifted_fft, d_sfft, (size_t)N * 8, cudaMemcpyDeviceToHost, s.stream));
+    if (corr) CUD(cudaMemcpyAsync(corr, d_corr, (size_t)corr_len * 8, cudaMemcpyDeviceToHost, s.stream));
+    if (fft_mag) CUD(cudaMemcpyAsync(fft_mag, d_mag, (size_t)N * 4, cudaMemcpyDeviceToHost, s.stream));
+    CUD(cudaStreamSynchronize(s.stream));
+    CUD(cudaGetLastError());
+    return done(THR_OK);
+#undef CUD
+}
+
+void *thr_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+    return p;
+}
+void thr_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+void *thr_device_alloc(int device, size_t bytes) {
+    void *p = nullptr;
+    if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+    return p;
+}
+void thr_device_free(int device, void *p) {
+    if (!p) return;
+    cudaSetDevice(device);
+    cudaFree(p);
+}
+int thr_memcpy_h2d(int device, void *dst, const void *src, size_t bytes) {
+    if (cudaSetDevice(device) != cudaSuccess) return THR_ERR_CUDA;
+    return cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess ? THR_OK : THR_ERR_CUDA;
+}
+int thr_memcpy_d2h(int device, void *dst, const void *src, size_t bytes) {
+    if (cudaSetDevice(device) != cudaSuccess) return THR_ERR_CUDA;
+    return cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) == cudaSuccess ? THR_OK : THR_ERR_CUDA;
+}
+
+}  // extern "C"
