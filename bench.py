@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""Benchmark of the fused detect path (BASELINE.json metric: detect Msamples/s, block_len=16384).
+
+    python bench.py --gpus 1 --steps 256 --warmup 8            # our arm (CUDA, via the C ABI)
+    python bench.py --impl reference --steps K --warmup W     # reference algorithm on host cores
+    torchrun ... bench.py --gpus N ...                        # one rank per GPU, weak scaling
+
+A "step" is one pass of the detect hot path over one batch (4096 blocks of 16384 complex
+samples) of synthetic .card payloads.  `value` = blocks/s x block_len / 1e6 with the inputs
+resident in HBM; `e2e` = the same through thr_detect_batch() with pinned HOST buffers (H2D of
+raw blocks + D2H of records inside the timed region).
+
+The oracle (oracle/thrifty_oracle.py, NumPy restatement of the reference) is executed here ONLY
+for the `cpu_baseline` leg and the `--impl reference` arm.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from thrifty_b200 import synth  # noqa: E402
+
+BLOCK_LEN = 16384
+HISTORY = 4920
+WINDOW = (7, 110)
+THRESH = (0.0, 15.0, 0.0)
+TEMPLATE_PATH = os.path.join(ROOT, "tests", "golden", "template_example.npy")
+
+
+def workload_name(args):
+    return ("detect: synthetic .card payloads, block_len=%d, history=%d, example template L=4914, "
+            "window 7-110, thresholds 15*snr, batch=%d, %d%% burst blocks"
+            % (args.block_len, HISTORY, args.batch, round(100 * args.p_signal)))
+
+
+def make_unique_blocks(n_unique, p_signal, seed):
+    tpl = np.load(TEMPLATE_PATH)
+    raw, _ = synth.make_blocks(n_unique, BLOCK_LEN, HISTORY, tpl, p_signal, seed=seed)
+    return tpl, raw
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class ClockSampler(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smmax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            if ts < t0 - 0.05 or ts > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smmax.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:   # timed region shorter than one sample: use everything we have
+            for ts, line in self.rows:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(f[1]))
+                    smmax.append(float(f[2]))
+                except (ValueError, IndexError):
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(smmax)) if smmax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU legs
+_W = {}
+
+
+def _worker_init():
+    os.environ["OMP_NUM_THREADS"] = "1"
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    os.environ["MKL_NUM_THREADS"] = "1"
+    from oracle import thrifty_oracle as orc
+    tpl = np.load(TEMPLATE_PATH)
+    st = orc.DetectorSettings(block_len=BLOCK_LEN, history_len=HISTORY, carrier_len=len(tpl),
+                              carrier_thresh=THRESH, carrier_window=WINDOW, template=tpl,
+                              corr_thresh=THRESH)
+    _W["det"] = orc.Detector(st, rxid=0)
+
+
+def _worker_run(raw_chunk):
+    det = _W["det"]
+    n = 0
+    for i in range(len(raw_chunk)):
+        res = det.detect_raw(0.0, i, raw_chunk[i])
+        n += bool(res.detected)
+    return n
+
+
+def cpu_oracle_rate_single(raw, max_seconds=20.0):
+    """Single-thread oracle port over a bounded sample.  Returns (blocks/s, blocks done)."""
+    _worker_init()
+    det = _W["det"]
+    det.detect_raw(0.0, 0, raw[0])   # warm-up (FFT plan caches, imports)
+    t0 = time.perf_counter()
+    done = 0
+    for i in range(len(raw)):
+        det.detect_raw(0.0, i, raw[i])
+        done += 1
+        if time.perf_counter() - t0 > max_seconds:
+            break
+    dt = time.perf_counter() - t0
+    return done / dt, done
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference algorithm (oracle port of the NumPy path) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    _, uniq = make_unique_blocks(64, args.p_signal, synth.SEED0)
+    # calibrate on one core, then size the per-step sample so the whole run takes ~90 s
+    rate1, _ = cpu_oracle_rate_single(uniq[:16], max_seconds=5.0)
+    total_steps = args.steps + args.warmup
+    budget_s = 90.0
+    sample = int(budget_s * rate1 * cores * 0.8 / total_steps)
+    sample = max(cores, min(args.batch, sample))
+    sample -= sample % cores
+    sample = max(sample, cores)
+    blocks = uniq[np.arange(sample) % len(uniq)]
+    chunks = np.array_split(blocks, cores)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores, initializer=_worker_init) as pool:
+        for _ in range(args.warmup):
+            pool.map(_worker_run, chunks)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_worker_run, chunks)
+        dt = time.perf_counter() - t0
+    ms_per_step = dt / args.steps * 1e3
+    value = sample * BLOCK_LEN / (ms_per_step / 1e3) / 1e6
+    line = {
+        "impl": "reference",
+        "metric": "detect Msamples/s (block_len=16384)", "value": value, "unit": "Msamples/s",
+        "n_gpus": 0, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64 (numpy)",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args), "block_len": BLOCK_LEN, "batch": args.batch,
+                   "sample_blocks_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": "port",
+                         "sample": "%d blocks per step x %d steps of the same synthetic workload, "
+                                   "NumPy/SciPy restatement of thrifty.detect.Detector.detect "
+                                   "(numpy %s pocketfft), %d worker processes"
+                                   % (sample, args.steps, np.__version__, cores)},
+        "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from thrifty_b200._native import NativeDetector, PinnedBuffer, RECORD_DTYPE
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the detect path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node %d" % args.gpus
+
+    n, batch = args.block_len, args.batch
+    tpl, uniq = make_unique_blocks(args.unique, args.p_signal, synth.SEED0 + 100003 * rank)
+    det = NativeDetector(n, HISTORY, tpl, len(tpl), WINDOW, THRESH, THRESH, device=local_rank,
+                         max_batch=batch)
+    info = det.info()
+
+    # device-resident pool of raw blocks, larger than L2 (126 MB): pool_blocks * 32 KiB
+    pool_blocks = args.pool
+    assert pool_blocks % batch == 0
+    uniq_d = torch.from_numpy(uniq).to(dev)
+    reps = (pool_blocks + len(uniq) - 1) // len(uniq)
+    pool = uniq_d.repeat(reps, 1)[:pool_blocks].contiguous()
+    idx = torch.arange(pool_blocks, dtype=torch.int64, device=dev) + rank * (1 << 40)
+    rec = torch.zeros(batch * 64, dtype=torch.uint8, device=dev)
+    gathered = torch.zeros(world * batch * 64, dtype=torch.uint8, device=dev) if world > 1 else None
+    # a real (non-legacy) stream: handle 0 would mean "the detector's own stream" to thr_set_stream
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    det.set_stream(stream.cuda_stream)
+    n_windows = pool_blocks // batch
+
+    def step(i, gather=True):
+        w = i % n_windows
+        det.detect_device(pool[w * batch].data_ptr(), idx[w * batch].data_ptr(), batch, rec.data_ptr())
+        if gather and world > 1:
+            dist.all_gather_into_tensor(gathered, rec)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(k, gather=True):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for i in range(k):
+            step(i, gather)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    launches0 = det.info()["launches"]
+    t_wall0 = time.time()
+    ms_total = timed(args.steps, gather=True)
+    t_wall1 = time.time()
+    launches = det.info()["launches"] - launches0
+    # the timed region may be shorter than the sampler period: keep the GPU busy a little longer
+    # (untimed) so that at least a few clock samples are taken under the same load
+    t_extra0 = time.time()
+    while time.time() - t_extra0 < 1.0:
+        for i in range(8):
+            step(i, gather=False)
+        torch.cuda.synchronize()
+    clocks = sampler.stop(t_wall0, time.time())
+    ms_per_step = ms_total / args.steps
+    value = world * batch * n / (ms_per_step * 1e-3) / 1e6
+
+    # kernel-only timing for the roofline (same launches, no gather)
+    ms_kernel = timed(args.steps, gather=False) / args.steps if world > 1 else ms_per_step
+
+    # records sanity: every block of the last batch must carry a decision
+    recs = np.frombuffer(rec.cpu().numpy().tobytes(), dtype=RECORD_DTYPE)
+    n_det = int(((recs["flags"] & 2) != 0).sum())
+    n_car = int(((recs["flags"] & 1) != 0).sum())
+
+    # ---- e2e: host (pinned) buffers through thr_detect_batch, copies inside the timed region
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    hbuf = [PinnedBuffer(batch * 2 * n) for _ in range(2)]
+    hidx = [PinnedBuffer(batch * 8) for _ in range(2)]
+    hout = [PinnedBuffer(batch * 64) for _ in range(2)]
+    lib = det._lib
+    for b in range(2):
+        src = uniq[(np.arange(batch) + b * 7) % len(uniq)]
+        hbuf[b].array[:] = src.reshape(-1)
+        hidx[b].array.view(np.int64)[:] = np.arange(batch) + b * batch
+    for b in range(2):   # warm-up
+        det._check(lib.thr_detect_batch(det.handle, hbuf[b].ptr, hidx[b].ptr, batch, hout[b].ptr))
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        b = i & 1
+        det._check(lib.thr_detect_batch(det.handle, hbuf[b].ptr, hidx[b].ptr, batch, hout[b].ptr))
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * batch * n / (e2e_ms * 1e-3) / 1e6
+    e2e_recs = hout[(e2e_steps - 1) & 1].array.view(RECORD_DTYPE)
+    e2e_det = int(((e2e_recs["flags"] & 2) != 0).sum())
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak = float(json.load(open(peaks_path))["hbm_gbs"])
+            peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+        else:
+            peak, peak_src = 6650.0, "fallback from B200_PROFILING.md"
+        alg_bytes = batch * (2 * n + 64)                   # raw u8 in + 64-B record out, per launch
+        achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(prof):
+            try:
+                traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": "detect Msamples/s (block_len=16384)", "value": value, "unit": "Msamples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args), "block_len": n, "batch": batch,
+                       "pool_blocks_per_gpu": pool_blocks,
+                       "l2_policy": "inputs larger than L2: %d MiB raw pool cycled per GPU" % (pool_blocks * 2 * n >> 20),
+                       "kernel": info["kernel"], "grid": info["grid"], "threads": info["threads"],
+                       "smem_bytes": info["smem_bytes"], "parallelism": "stripe%d" % world,
+                       "carrier_detected_last_batch": n_car, "corr_detected_last_batch": n_det,
+                       "blocks_per_s": world * batch / (ms_per_step * 1e-3)},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "kernel_ms_per_launch": ms_kernel,
+                         "note": "fused kernel is FP32-issue/shared-memory bound (~125 FLOP/B), see DESIGN.md"},
+            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": batch * (2 * n + 8),
+                    "d2h_bytes_per_step": batch * 64, "ms_per_step": e2e_ms, "steps": e2e_steps,
+                    "api": "thr_detect_batch (pinned host buffers)", "corr_detected_last_batch": e2e_det},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if args.cpu_baseline and world == 1:
+            rate, done = cpu_oracle_rate_single(uniq[np.arange(4096) % len(uniq)], max_seconds=args.cpu_seconds)
+            line["cpu_baseline"] = {
+                "value": rate * n / 1e6, "unit": "Msamples/s", "cores": 1, "kind": "port",
+                "sample": "%d blocks of the same workload, single process, NumPy/SciPy restatement of "
+                          "thrifty.detect.Detector.detect (numpy %s pocketfft, scipy curve_fit)" % (done, np.__version__),
+                "blocks_per_s": rate, "host_cores_available": os.cpu_count()}
+        print(json.dumps(line))
+    for b in hbuf + hidx + hout:
+        b.close()
+    det.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=256)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--block-len", type=int, default=BLOCK_LEN)
+    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--pool", type=int, default=16384, help="device-resident raw blocks per GPU")
+    ap.add_argument("--unique", type=int, default=512, help="distinct synthetic blocks generated on the host")
+    ap.add_argument("--p-signal", type=float, default=1.0,
+                    help="fraction of blocks carrying a burst (a .card holds carrier-positive blocks: 1.0)")
+    ap.add_argument("--e2e-steps", type=int, default=16)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    args = ap.parse_args()
+    if args.block_len != BLOCK_LEN:
+        raise SystemExit("bench.py measures the headline config (block_len=16384); use tools/sweep.py for others")
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

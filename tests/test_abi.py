@@ -1,0 +1,83 @@
+"""C-ABI checks that need no GPU: the library loads, exports every symbol the header declares,
+struct layouts agree, and the product fails loudly without a device."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from thrifty_b200 import _native
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "thrifty_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(thr_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _native.load_library()
+    names = header_functions()
+    assert len(names) >= 20
+    for name in names:
+        assert hasattr(lib, name), "missing export " + name
+    assert sorted(_native.EXPORTS) == names
+
+
+def test_struct_layouts():
+    assert _native.RECORD_DTYPE.itemsize == 64
+    offs = {n: _native.RECORD_DTYPE.fields[n][1] for n in _native.RECORD_DTYPE.names}
+    assert offs["block_idx"] == 0 and offs["soa"] == 8 and offs["carrier_bin"] == 16
+    assert offs["corr_sample"] == 32 and offs["flags"] == 48 and offs["signal_energy"] == 56
+    assert ctypes.sizeof(_native.ThrConfig) == 104
+    assert ctypes.sizeof(_native.ThrInfo) == 40 + 128
+
+
+def test_header_and_binding_agree_on_record_size():
+    text = open(os.path.join(ROOT, "include", "thrifty_b200.h")).read()
+    body = re.search(r"typedef struct thr_record \{(.*?)\} thr_record;", text, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    sizes = {"int64_t": 8, "double": 8, "int32_t": 4, "uint32_t": 4, "float": 4}
+    total = sum(sizes[m.group(1)] for m in re.finditer(r"\b(int64_t|double|int32_t|uint32_t|float)\s+\w+;", body))
+    assert total == 64
+
+
+@pytest.mark.skipif(_native.load_library().thr_device_count() > 0, reason="a GPU is present")
+def test_no_device_fails_loudly():
+    tpl = np.ones(100)
+    with pytest.raises(_native.NativeError) as err:
+        _native.NativeDetector(1024, 120, tpl, 100, (0, -1), (0, 15, 0), (0, 15, 0))
+    assert "no CUDA device" in str(err.value)
+
+
+def test_invalid_config_messages():
+    lib = _native.load_library()
+    cfg = _native.ThrConfig()
+    h = ctypes.c_void_p()
+    cfg.block_len = 1000        # not a supported power of two
+    assert lib.thr_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
+    assert b"unsupported block_len" in lib.thr_last_error(None)
+    tpl = (ctypes.c_double * 100)(*([1.0] * 100))
+    cfg.block_len, cfg.template_len, cfg.n_templates, cfg.templates = 1024, 100, 1, tpl
+    cfg.history_len = 50        # < template_len - 1  (soa_estimator.py:33)
+    assert lib.thr_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
+    assert b"history_len" in lib.thr_last_error(None)
+    cfg.history_len, cfg.carrier_len, cfg.max_batch = 120, 100, 4
+    cfg.window_start, cfg.window_stop = -2000, 5     # carrier_detect.py:47-49
+    assert lib.thr_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
+    assert b"Frequency window out of range" in lib.thr_last_error(None)
+
+
+def test_product_never_touches_the_oracle():
+    """thrifty_b200/ (Python and CUDA/C++) must not import, link or execute oracle/."""
+    pkg = os.path.join(ROOT, "thrifty_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")) or f == "Makefile":
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", text, re.M), f
+                assert "thrifty_oracle" not in text, f
+                assert "/root/reference" not in text, f

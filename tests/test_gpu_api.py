@@ -1,0 +1,327 @@
+"""GPU tests of the reference-facing Python seam (Detector / detector_cli) and of the C-ABI
+entry points, against golden reference outputs and the oracle."""
+import ctypes
+import io
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import parity_util as parity
+from oracle import thrifty_oracle as orc
+from thrifty_b200 import block_data, synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _settings(cfg):
+    from thrifty_b200.detect import DetectorSettings
+    return DetectorSettings(block_len=cfg["block_len"], history_len=cfg["history_len"],
+                            carrier_len=len(cfg["template"]), carrier_thresh=cfg["cthresh"],
+                            carrier_window=cfg["window"], template=cfg["template"],
+                            corr_thresh=cfg["kthresh"])
+
+
+def _results_to_rows(results):
+    rows = np.zeros(len(results), dtype=orc.RECORD_DTYPE)
+    for i, (detected, res) in enumerate(results):
+        rows[i] = orc.result_to_row(orc.OracleResult(detected, res.timestamp, res.block, res.soa,
+                                                     res.carrier_info, res.corr_info, res.rxid))
+    return rows
+
+
+def _rows_as_records(rows):
+    """Oracle-row layout -> thr_record-like array so compare_records can be reused."""
+    from thrifty_b200._native import RECORD_DTYPE
+    rec = np.zeros(len(rows), dtype=RECORD_DTYPE)
+    for f in ("block_idx", "soa", "carrier_bin", "carrier_offset", "carrier_energy", "carrier_noise",
+              "corr_sample", "corr_offset", "corr_energy", "corr_noise"):
+        rec[f] = rows[f]
+    rec["flags"] = rows["carrier_detected"].astype(np.uint32) + 2 * rows["corr_detected"].astype(np.uint32)
+    return rec
+
+
+@pytest.mark.parametrize("name,mode", [("n4096_gold9", "complex"), ("n4096_gold9", "raw"),
+                                       ("n16384_example", "raw"), ("n4096_gold9_tone", "complex")])
+def test_detector_iterator_dropin(name, mode):
+    """Detector(settings, blocks) yields one (detected, result) per block, in order (detect.py:80-91)."""
+    from thrifty_b200.detect import Detector
+    cfg, raw, block_idx, ref, _ = parity.load_golden(name)
+    text = io.StringIO()
+    block_data.write_card(text, raw, block_indices=block_idx)
+    text.seek(0)
+    blocks = block_data.card_reader(text, raw=(mode == "raw"))
+    det = Detector(_settings(cfg), blocks, rxid=0, batch=7)
+    results = list(det)
+    assert len(results) == len(raw)
+    for (detected, res), r in zip(results, ref):
+        assert res.block == r["block_idx"] and res.rxid == 0
+        assert (res.corr_info is None) == (not r["carrier_detected"])
+        assert (res.soa is None) == (not r["carrier_detected"])
+        if res.corr_info is None:
+            assert detected is False and res.carrier_info.offset == 0
+    parity.compare_records(_rows_as_records(_results_to_rows(results)), ref, what=name)
+    det.close()
+
+
+def test_detector_single_and_yield_data(golden_dir):
+    """detect() on one block; yield_data=True returns shifted_fft and corr (detect.py:75-76)."""
+    from thrifty_b200.detect import Detector
+    g = np.load(os.path.join(golden_dir, "arrays_n4096_gold9.npz"))
+    tpl = synth.gold_template(9)
+    cfg = dict(block_len=4096, history_len=len(tpl) + 6, template=tpl, cthresh=(0., 15., 0.),
+               window=(7, 110), kthresh=(0., 15., 0.))
+    raw, _ = synth.make_blocks(1, 4096, len(tpl) + 6, tpl, 1.0, seed=int(g["seed"]))
+    det = Detector(_settings(cfg), rxid=5, yield_data=True)
+    detected, res, sfft, corr = det.detect(12.5, 5, block_data.raw_to_complex(raw[0]))
+    assert detected and res.rxid == 5 and res.timestamp == 12.5 and res.block == 5
+    assert abs(res.soa - float(g["soa"])) < 1e-4
+    ref_sfft, ref_corr = g["shifted_fft"], g["corr"]
+    assert sfft.shape == ref_sfft.shape and corr.shape == ref_corr.shape
+    # complex arrays: error relative to the largest magnitude (float32 FFT vs float64 reference)
+    assert np.abs(sfft - ref_sfft).max() <= 2e-5 * np.abs(ref_sfft).max()
+    assert np.abs(corr - ref_corr).max() <= 2e-5 * np.abs(ref_corr).max()
+    det.close()
+    det2 = Detector(_settings(cfg), rxid=5)
+    d2, r2 = det2.detect(12.5, 5, raw[0])          # raw uint8 block, no yield_data
+    assert d2 and abs(r2.soa - res.soa) < 1e-9 and r2.corr_info.sample == res.corr_info.sample
+    det2.close()
+
+
+def test_fft_mag_debug_output():
+    """|FFT(block)| from the kernel equals numpy's float32 FFT magnitude (Signal.fft.mag)."""
+    from thrifty_b200._native import NativeDetector
+    tpl = synth.gold_template(10)
+    raw, _ = synth.make_blocks(2, 8192, len(tpl) + 6, tpl, 1.0, seed=77)
+    det = NativeDetector(8192, len(tpl) + 6, tpl, len(tpl), (7, 110), (0., 15., 0.), (0., 15., 0.), max_batch=4)
+    _, _, _, mag = det.detect_block_data(raw=raw[1], block_idx=0)
+    ref = np.abs(np.fft.fft(orc.raw_to_complex(raw[1]))).astype(np.float64)
+    assert np.abs(mag - ref).max() <= 2e-6 * ref.max()
+    det.close()
+
+
+def test_cli_card_to_toad(tmp_path):
+    """`thrifty_b200 detect x.card -o x.toad` reproduces the reference's .toad lines."""
+    cfg, raw, block_idx, ref, lines = parity.load_golden("n4096_gold9")
+    np.save(str(tmp_path / "template.npy"), cfg["template"])
+    (tmp_path / "detector.cfg").write_text(
+        "rxid: 0\nsample_rate: 2.4M\nblock_size: 4096\nblock_history: %d\ncarrier_window: 7 - 110\n"
+        "carrier_threshold: 15 * snr\ncorr_threshold: 15 * snr\ntemplate: template.npy\n" % cfg["history_len"])
+    with open(str(tmp_path / "rx.card"), "w") as f:
+        block_data.write_card(f, raw, block_indices=block_idx, t0=1000.0, dt=0.0047767)
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    out = subprocess.run([sys.executable, "-m", "thrifty_b200", "detect", "rx.card", "-o", "rx.toad", "--batch", "16"],
+                         cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    summary = out.stdout.strip().split("\n")
+    assert len(summary) == len(raw) and summary[0].startswith("blk=10; carrier:")
+    got = [l for l in open(str(tmp_path / "rx.toad")).read().split("\n") if l]
+    want = [l for l in lines if l]
+    assert len(got) == len(want)
+    for lg, lw in zip(got, want):
+        fg, fw = lg.split(), lw.split()
+        assert len(fg) == len(fw) == 12
+        assert [fg[0], fg[2], fg[4], fg[8]] == [fw[0], fw[2], fw[4], fw[8]]      # rxid block sample bin
+        assert abs(float(fg[1]) - float(fw[1])) < 2e-6                              # timestamp
+        assert abs(float(fg[3]) - float(fw[3])) < 1e-4                              # soa
+        assert abs(float(fg[5]) - float(fw[5])) < 1e-4 and abs(float(fg[9]) - float(fw[9])) < 1e-4
+        for i in (6, 7, 10, 11):
+            assert abs(float(fg[i]) / float(fw[i]) - 1) < 1e-4
+
+
+@pytest.mark.parametrize("block_len,n_blocks,seed", [(16384, 192, 1), (8192, 128, 2), (4096, 128, 3),
+                                                     (2048, 64, 4), (1024, 64, 5), (32768, 24, 6)])
+def test_fresh_seeds_vs_oracle(block_len, n_blocks, seed):
+    """Parity on seeds that are not in the goldens, every supported block length."""
+    from thrifty_b200._native import NativeDetector
+    if block_len >= 16384:
+        tpl = np.load(os.path.join(parity.GOLDEN, "template_example.npy"))
+        hist = 4920
+    else:
+        bits = {8192: 10, 4096: 9, 2048: 8, 1024: 7}[block_len]
+        tpl = synth.gold_template(bits)
+        hist = len(tpl) + 6
+    window = (7, 110) if block_len >= 2048 else (7, 60)
+    bins = (8.0, 109.0) if block_len >= 2048 else (8.0, 59.0)
+    raw, _ = synth.make_blocks(n_blocks, block_len, hist, tpl, 0.5, seed=900000 + 1000 * seed, bin_range=bins)
+    st = orc.DetectorSettings(block_len, hist, len(tpl), (0., 15., 0.), window, tpl, (0., 15., 0.))
+    idx = np.arange(n_blocks, dtype=np.int64) * 5 + 100
+    ref = orc.detect_blocks(st, raw, idx)
+    det = NativeDetector(block_len, hist, tpl, len(tpl), window, (0., 15., 0.), (0., 15., 0.), max_batch=50)
+    got = det.detect_raw(raw, idx)[:, 0]                 # n_blocks > max_batch: chunked inside the call
+    stats = parity.compare_records(got, ref, what="N=%d" % block_len)
+    print(block_len, stats)
+    assert stats["carrier"] >= n_blocks // 4
+    det.close()
+
+
+def test_whole_spectrum_window_and_degenerate_blocks():
+    """Default window '0--1' (all bins) and degenerate inputs: constant, saturated, DC-only."""
+    from thrifty_b200._native import NativeDetector
+    tpl = synth.gold_template(9)
+    n, hist = 4096, len(tpl) + 6
+    raw, _ = synth.make_blocks(12, n, hist, tpl, 1.0, seed=555)
+    rng = np.random.default_rng(9)
+    raw[3] = 127                                       # constant block -> only the DC bin: NaN noise
+    raw[5] = rng.integers(0, 2, size=2 * n) * 255      # saturated random
+    raw[7] = 0
+    st = orc.DetectorSettings(n, hist, len(tpl), (0., 15., 0.), (0, -1), tpl, (0., 15., 0.))
+    with np.errstate(all="ignore"):
+        ref = orc.detect_blocks(st, raw)
+    det = NativeDetector(n, hist, tpl, len(tpl), (0, -1), (0., 15., 0.), (0., 15., 0.), max_batch=16)
+    got = det.detect_raw(raw)[:, 0]
+    for i in (3, 7):
+        assert not ref["carrier_detected"][i] and not (got["flags"][i] & 1)
+        assert got["carrier_bin"][i] == ref["carrier_bin"][i] == 0
+    keep = np.array([i for i in range(12) if i not in (3, 7)])
+    parity.compare_records(got[keep], ref[keep], what="whole-spectrum")
+    det.close()
+
+
+def test_empty_and_single_block():
+    from thrifty_b200._native import NativeDetector
+    tpl = synth.gold_template(9)
+    n, hist = 4096, len(tpl) + 6
+    det = NativeDetector(n, hist, tpl, len(tpl), (7, 110), (0., 15., 0.), (0., 15., 0.), max_batch=8)
+    assert det.detect_raw(np.zeros((0, 2 * n), dtype=np.uint8)).shape == (0, 1)
+    raw, _ = synth.make_blocks(1, n, hist, tpl, 1.0, seed=31)
+    got = det.detect_raw(raw, [123456789012])
+    assert got.shape == (1, 1) and got["block_idx"][0, 0] == 123456789012
+    assert got["flags"][0, 0] == 3
+    # SoA keeps integer precision for huge block indices (detect.py:67)
+    expect = (n - hist) * 123456789012 + got["corr_sample"][0, 0] + float(got["corr_offset"][0, 0])
+    assert abs(got["soa"][0, 0] - expect) <= 1.0
+    with pytest.raises(ValueError):
+        det.detect_raw(np.zeros((2, 100), dtype=np.uint8))
+    det.close()
+
+
+def test_invalid_settings_raise():
+    from thrifty_b200._native import NativeDetector, NativeError
+    tpl = synth.gold_template(9)
+    with pytest.raises(ValueError):                       # carrier_detect.py:47-49
+        NativeDetector(4096, len(tpl) + 6, tpl, len(tpl), (-5000, 10), (0., 15., 0.), (0., 15., 0.))
+    with pytest.raises(NativeError):                      # soa_estimator.py:33
+        NativeDetector(4096, 100, tpl, len(tpl), (7, 110), (0., 15., 0.), (0., 15., 0.))
+    with pytest.raises(NativeError):
+        NativeDetector(5000, 4000, tpl, len(tpl), (7, 110), (0., 15., 0.), (0., 15., 0.))
+
+
+def test_full_size_properties():
+    """BASELINE full size (N=16384, batch 4096+): size-independent properties.
+
+    * determinism / batch invariance: every copy of a block yields the same record wherever it
+      sits in the batch, across chunk boundaries and CTAs;
+    * SoA linearity in block_idx: soa - (N-H)*block_idx == sample + offset;
+    * u8 and complex64 inputs agree; host-buffer and device-buffer entry points agree."""
+    from thrifty_b200._native import NativeDetector, RECORD_DTYPE, load_library
+    tpl = np.load(os.path.join(parity.GOLDEN, "template_example.npy"))
+    n, hist, uniq_n, total = 16384, 4920, 96, 4096 + 160
+    uniq, _ = synth.make_blocks(uniq_n, n, hist, tpl, 0.75, seed=424242)
+    rng = np.random.default_rng(3)
+    pick = rng.integers(0, uniq_n, size=total)
+    raw = uniq[pick]
+    idx = rng.integers(0, 1 << 33, size=total).astype(np.int64)
+    det = NativeDetector(n, hist, tpl, len(tpl), (7, 110), (0., 15., 0.), (0., 15., 0.), max_batch=4096)
+    got = det.detect_raw(raw, idx)[:, 0]
+    fields = ["carrier_bin", "carrier_offset", "carrier_energy", "carrier_noise", "corr_sample",
+              "corr_offset", "corr_energy", "corr_noise", "flags", "signal_energy"]
+    first = {}
+    for i in range(total):
+        key = tuple(got[f][i].tobytes() for f in fields)
+        assert first.setdefault(pick[i], key) == key, "block copy %d differs" % i
+    car = (got["flags"] & 1) != 0
+    assert car.sum() > total // 2
+    lin = got["soa"][car] - (n - hist) * idx[car].astype(np.float64)
+    np.testing.assert_allclose(lin, got["corr_sample"][car] + got["corr_offset"][car].astype(np.float64),
+                               rtol=0, atol=2e-3)     # float64 ulp at 1e14 is 0.016/8
+    # oracle on the unique blocks
+    st = orc.DetectorSettings(n, hist, len(tpl), (0., 15., 0.), (7, 110), tpl, (0., 15., 0.))
+    ref = orc.detect_blocks(st, uniq)
+    firsts = np.array([np.nonzero(pick == u)[0][0] for u in range(uniq_n)])
+    g = got[firsts].copy()
+    g["block_idx"] = np.arange(uniq_n)
+    g["soa"] = g["soa"] - (n - hist) * idx[firsts].astype(np.float64) + (n - hist) * np.arange(uniq_n)
+    parity.compare_records(g, ref, what="full-size")
+    # complex64 input path, first 300 blocks
+    iq = np.stack([orc.raw_to_complex(r) for r in raw[:300]])
+    got_c = det.detect_c64(iq, idx[:300])[:, 0]
+    for f in fields + ["soa", "block_idx"]:
+        np.testing.assert_array_equal(got_c[f], got[f][:300], err_msg=f)
+    # device-buffer entry point
+    lib = load_library()
+    nb = 1000
+    d_raw = lib.thr_device_alloc(0, nb * 2 * n)
+    d_idx = lib.thr_device_alloc(0, nb * 8)
+    d_out = lib.thr_device_alloc(0, nb * 64)
+    assert d_raw and d_idx and d_out
+    chunk = np.ascontiguousarray(raw[:nb])
+    cidx = np.ascontiguousarray(idx[:nb])
+    assert lib.thr_memcpy_h2d(0, d_raw, chunk.ctypes.data, chunk.nbytes) == 0
+    assert lib.thr_memcpy_h2d(0, d_idx, cidx.ctypes.data, cidx.nbytes) == 0
+    det.detect_device(d_raw, d_idx, nb, d_out)
+    det.synchronize()
+    out = np.zeros(nb, dtype=RECORD_DTYPE)
+    assert lib.thr_memcpy_d2h(0, out.ctypes.data, d_out, out.nbytes) == 0
+    for f in fields + ["soa", "block_idx"]:
+        np.testing.assert_array_equal(out[f], got[f][:nb], err_msg=f)
+    for p in (d_raw, d_idx, d_out):
+        lib.thr_device_free(0, p)
+    assert det.info()["launches"] >= 3
+    det.close()
+
+
+def test_time_shift_property():
+    """Moving the burst by d samples moves the SoA by d (noise-free, N=16384)."""
+    from thrifty_b200._native import NativeDetector
+    tpl = np.load(os.path.join(parity.GOLDEN, "template_example.npy"))
+    n, hist = 16384, 4920
+    idx = np.arange(n)
+    blocks, positions = [], [3, 100, 1001, 5000, 11466]
+    for pos in positions:
+        gate = np.zeros(n)
+        gate[pos:pos + len(tpl)] = (tpl[:n - pos] + 1) / 2 if pos + len(tpl) > n else (tpl + 1) / 2
+        x = 0.3 * gate * np.exp(2j * np.pi * 40.25 * idx / n)
+        blocks.append(synth.complex_to_raw(x))
+    det = NativeDetector(n, hist, tpl, len(tpl), (7, 110), (0., 15., 0.), (0., 15., 0.), max_batch=8)
+    got = det.detect_raw(np.stack(blocks), np.zeros(len(positions), dtype=np.int64))[:, 0]
+    assert np.all(got["flags"] == 3)
+    np.testing.assert_array_equal(got["corr_sample"], positions)
+    np.testing.assert_array_equal(got["carrier_bin"], 40)
+    assert np.ptp(got["corr_offset"]) < 0.02 and np.ptp(got["carrier_offset"]) < 0.01
+    det.close()
+
+
+def test_multi_template_vs_independent_oracles():
+    """4 Gold templates jointly == 4 independent reference detectors (BASELINE config 5)."""
+    from thrifty_b200.detect import DetectorSettings, MultiTemplateDetector
+    n, bits = 4096, 9
+    tpls = np.stack([synth.gold_template(bits, i) for i in range(4)])
+    hist = tpls.shape[1] + 6
+    rng = np.random.default_rng(11)
+    raws, which = [], []
+    for b in range(40):
+        t = int(rng.integers(0, 4))
+        r, _ = synth.make_blocks(1, n, hist, tpls[t], 0.8, seed=7000 + b)
+        raws.append(r[0])
+        which.append(t)
+    raws = np.stack(raws)
+    settings = DetectorSettings(n, hist, tpls.shape[1], (0., 15., 0.), (7, 110), tpls[0], (0., 15., 0.))
+    det = MultiTemplateDetector(settings, tpls, rxid=1, batch=64)
+    out = det.detect_many([(0.0, i, raws[i]) for i in range(len(raws))])
+    for t in range(4):
+        st = orc.DetectorSettings(n, hist, tpls.shape[1], (0., 15., 0.), (7, 110), tpls[t], (0., 15., 0.))
+        ref = orc.detect_blocks(st, raws)
+        rows = _results_to_rows([o[t] for o in out])
+        parity.compare_records(_rows_as_records(rows), ref, what="template %d" % t)
+        assert all(o[t][1].txid == t for o in out)
+    det.close()
+
+
+def test_smoke_entry():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__
+    __graft_entry__.smoke()

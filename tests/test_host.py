@@ -1,0 +1,180 @@
+"""Host-side logic of the drop-in (no GPU): parsers, settings, block I/O, record text."""
+import io
+import os
+
+import numpy as np
+import pytest
+
+from thrifty_b200 import block_data, setting_parsers, settings, stripe, synth, toads_data, util
+
+
+# grammar tables of /root/reference/tests/test_setting_parsers.py:10-99
+def test_freq_range():
+    cases = [('100', (100.0, 100.0, False)), ('-123.4', (-123.4, -123.4, False)),
+             ('100-200', (100.0, 200.0, False)), ('10e1 - 20e1', (100.0, 200.0, False)),
+             ('-100-100', (-100.0, 100.0, False)), ('-200--100', (-200.0, -100.0, False)),
+             ('100hz', (100.0, 100.0, True)), ('100-200 Hz', (100.0, 200.0, True)),
+             ('10-20 khz', (10000.0, 20000.0, True)), ('1.2345-2.3456 KHZ', (1.2345e3, 2.3456e3, True)),
+             ('433-435Mhz', (433e6, 435e6, True)), ('1.2345-2.3456 mhz', (1.2345e6, 2.3456e6, True))]
+    for string, expected in cases:
+        assert setting_parsers.freq_range(string) == expected
+    with pytest.raises(ValueError):
+        setting_parsers.freq_range('garbage')
+
+
+def test_metric_float():
+    for string, expected in [('1337.15', 1337.15), ('15.2M', 15200000.0), ('987k', 987000.0),
+                             ('55m', 0.055), ('164u ', 164e-6)]:
+        assert setting_parsers.metric_float(string) == expected
+    for bad in ['garbage', 'x53m', '500A']:
+        with pytest.raises(ValueError):
+            setting_parsers.metric_float(bad)
+
+
+def test_threshold():
+    cases = [('0', (0.0, 0.0, 0.0)), ('10.2', (10.2, 0.0, 0.0)), ('c', (1.0, 0.0, 0.0)),
+             ('11c', (11.0, 0.0, 0.0)), ('100 * constant', (100.0, 0.0, 0.0)), ('snr', (0.0, 1.0, 0.0)),
+             ('5.2*snr', (0.0, 5.2, 0.0)), (' 8s ', (0.0, 8.0, 0.0)), ('stddev', (0.0, 0.0, 1.0)),
+             ('2.1stddev', (0.0, 0.0, 2.1)), ('8.7*d', (0.0, 0.0, 8.7)), ('10 + 4*snr', (10.0, 4.0, 0)),
+             ('40 + 3.8*snr + 2 stddev', (40.0, 3.8, 2.0)), ('1+2s+3d+4+5s+6d', (5.0, 7.0, 9.0)),
+             ('c + s + d', (1.0, 1.0, 1.0)), ('15 * snr', (0.0, 15.0, 0.0))]
+    for string, expected in cases:
+        assert setting_parsers.threshold(string) == expected
+    for bad in ['', ' ', '5+', 'junk', '+5*stddev', '*snr', 'stddev*snr', '5 * stdde', '2 * sn', 'const']:
+        with pytest.raises(ValueError):
+            setting_parsers.threshold(bad)
+
+
+def test_normalize_freq_range():
+    assert setting_parsers.normalize_freq_range((7.0, 110.0, False), 146.48) == (7, 110)
+    bin_freq = 2.2e6 / 8192
+    assert setting_parsers.normalize_freq_range((-81e3, -79e3, True), bin_freq) == (
+        int(-81e3 / bin_freq), int(-79e3 / bin_freq))
+
+
+@pytest.mark.parametrize("num", [15, 16])
+def test_fft_bin(num):
+    got = np.array([util.fft_bin(i, num) for i in range(num)])
+    np.testing.assert_array_equal(got, np.fft.fftfreq(num, 1. / num))
+
+
+def test_settings_config_overlay(tmp_path):
+    cfg = tmp_path / "detector.cfg"
+    cfg.write_text("rxid: 3\nblock_size: 8192   # comment\ncarrier_window: 7 - 110\n"
+                   "carrier_threshold: 15 * snr\n\ntemplate: t.npy\n")
+    import argparse
+    parser = argparse.ArgumentParser()
+    parser.add_argument("input")
+    keys = ["sample_rate", "block_size", "block_history", "carrier_window", "carrier_threshold",
+            "corr_threshold", "template", "rxid"]
+    config, args = settings.load_args(parser, keys, argv=["x.card", "-c", str(cfg), "--history", "2461"])
+    assert config.rxid == 3 and config.block_size == 8192 and config.block_history == 2461
+    assert config.carrier_window == (7.0, 110.0, False)
+    assert config.carrier_threshold == (0.0, 15.0, 0.0) and config.corr_threshold == (0.0, 15.0, 0.0)
+    assert config.sample_rate == 2.4e6 and config.template == "t.npy"
+    assert args.input == "x.card"
+    with pytest.raises(settings.SettingKeyError):
+        settings.load(config_file=io.StringIO("nonsense: 1\n"))
+    with pytest.raises(settings.ConfigSyntaxError):
+        settings.parse_kvconfig(io.StringIO("no delimiter here\n"))
+
+
+def test_card_reader_reference_vector():
+    # /root/reference/tests/test_block_data.py:59-71 (non-canonical base64 payloads)
+    text = "# Some comments\n# more comments\n1000.5425 10 r0+Om5==\n1000.5442 20 aaaaaa=="
+    for stream in (io.StringIO(text), io.BytesIO(text.encode())):
+        blocks = list(block_data.card_reader(stream, raw=True))
+        assert [b[0] for b in blocks] == [1000.5425, 1000.5442]
+        assert [b[1] for b in blocks] == [10, 20]
+        assert [tuple(b[2]) for b in blocks] == [(175, 79, 142, 155), (105, 166, 154, 105)]
+    cplx = list(block_data.card_reader(io.StringIO(text)))
+    assert cplx[0][2].dtype == np.complex64
+    assert tuple(block_data.complex_to_raw(cplx[0][2])) == (175, 79, 142, 155)
+
+
+def test_card_reader_skips_noise_lines():
+    text = "Using Volk machine: avx2\nlinux; GNU C++\n\n# c\n1.5 7 AAAA\n"
+    blocks = list(block_data.card_reader(io.StringIO(text), raw=True))
+    assert len(blocks) == 1 and blocks[0][1] == 7 and tuple(blocks[0][2]) == (0, 0, 0)
+
+
+def test_card_write_read_roundtrip():
+    rng = np.random.default_rng(1)
+    raw = rng.integers(0, 256, size=(5, 2 * 64), dtype=np.uint8)
+    buf = io.StringIO()
+    block_data.write_card(buf, raw, block_indices=[3, 4, 9, 10, 20])
+    buf.seek(0)
+    blocks = list(block_data.card_reader(buf, raw=True))
+    assert [b[1] for b in blocks] == [3, 4, 9, 10, 20]
+    for (_, _, got), want in zip(blocks, raw):
+        np.testing.assert_array_equal(got, want)
+    # line grammar of fastcard_cli.c:187-192: "<sec>.<usec> <idx> <base64>\n"
+    line = block_data.card_line(1480000000.25, 12, raw[0])
+    ts, idx, payload = line.rstrip("\n").split(" ")
+    assert ts == "1480000000.250000" and idx == "12" and len(payload) == (2 * 64 + 2) // 3 * 4
+
+
+def test_block_reader_overlap():
+    # /root/reference/tests/test_block_data.py:40-56
+    blocks = list(block_data.block_reader(io.BytesIO(bytes(range(14))), 3, 1))
+    raw = [list(block_data.complex_to_raw(b[2])) for b in blocks]
+    assert raw == [[0x7f, 0x7f, 0, 1, 2, 3], [2, 3, 4, 5, 6, 7], [6, 7, 8, 9, 10, 11]]
+    assert [b[1] for b in blocks] == [0, 1, 2]
+    assert blocks[0][2][0] == 0                       # first block's history is exactly zero
+    rawmode = list(block_data.block_reader(io.BytesIO(bytes(range(14))), 3, 1, raw=True))
+    assert rawmode[0][2].dtype == np.complex64 and rawmode[0][2][0] == 0
+    assert [list(b[2]) for b in rawmode[1:]] == [[2, 3, 4, 5, 6, 7], [6, 7, 8, 9, 10, 11]]
+
+
+def test_raw_complex_roundtrip():
+    every = np.arange(256, dtype=np.uint8)
+    np.testing.assert_array_equal(block_data.complex_to_raw(block_data.raw_to_complex(every)), every)
+    np.testing.assert_allclose(block_data.raw_to_complex(np.array([0, 0, 127, 128, 255, 255], dtype=np.uint8)),
+                               [-0.9953 - 0.9953j, -0.0031 + 0.0047j, 0.9969 + 0.9969j], rtol=1e-2)
+
+
+def test_toad_serialize_roundtrip():
+    res = toads_data.DetectionResult(
+        1000.019107, 22, 258721.99332702, toads_data.CarrierSyncInfo(30, 0.4434, np.float32(590.445), np.float32(11.75)),
+        toads_data.CorrDetectionInfo(6514, -0.00667, 445.5628, 5.2213), rxid=0)
+    line = res.serialize()
+    assert line.split()[:4] == ["0", "1000.019107", "22", "258721.99332702"]
+    assert len(line.split()) == 12
+    back = toads_data.DetectionResult.deserialize(line, with_rxid=True)
+    assert back.block == 22 and back.corr_info.sample == 6514 and back.carrier_info.bin == 30
+    assert abs(back.soa - res.soa) < 1e-8 and back.rxid == 0
+    assert toads_data.DetectionResult.deserialize("1 2 3") is None
+    arr = toads_data.toads_array([back], with_ids=False)
+    assert arr["sample"][0] == 6514 and arr["carrier_bin"][0] == 30
+
+
+def test_toad_line_matches_reference_format(golden_dir):
+    # a golden .toad line produced by the real reference parses field-for-field
+    g = np.load(os.path.join(golden_dir, "detect_n4096_gold9.npz"))
+    line = [str(s) for s in g["toad_lines"] if str(s)][0]
+    res = toads_data.DetectionResult.deserialize(line, with_rxid=True)
+    np.testing.assert_allclose([float(v) for v in res.serialize().split()],
+                               [float(v) for v in line.split()], rtol=1e-12)
+
+
+def test_stripe_bounds():
+    for n, w in [(10, 2), (11, 2), (4096, 8), (7, 8), (0, 4), (64 * 2**20, 8)]:
+        spans = [stripe.stripe_bounds(n, w, r) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        for a, b in zip(spans, spans[1:]):
+            assert a[1] == b[0]
+        assert max(hi - lo for lo, hi in spans) <= (n + w - 1) // w
+
+
+def test_gold_templates():
+    # Gold code properties (thrifty/gold.py): length 2^n-1, two-valued-ish cross-correlation
+    c0, c2 = synth.gold(5, 0), synth.gold(5, 2)
+    assert len(c0) == 31 and c0.dtype == bool
+    b0, b2 = np.where(c0, 1, -1), np.where(c2, 1, -1)
+    auto = [int(np.sum(b0 * np.roll(b0, s))) for s in range(1, 31)]
+    assert set(auto) == {-1}                                   # m-sequence autocorrelation
+    cross = {int(np.sum(b0 * np.roll(b2, s))) for s in range(31)}
+    assert cross <= {-9, -1, 7}                                # Gold three-valued bound
+    t = synth.gold_template(9)
+    assert len(t) == 1226 and set(np.unique(t)) == {-1.0, 1.0}
+    assert len(synth.gold_template(10)) == 2455 and len(synth.gold_template(11)) == 4914

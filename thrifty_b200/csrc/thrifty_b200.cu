@@ -91,6 +91,7 @@ struct thr_detector {
     float2 *d_xsave = nullptr;
     Slot slot[2];
     int c64_chunk = 0;
+    int host_chunk = 0;                  // blocks per pipelined chunk of the host-buffer API
     DetectParams base;                   // constant part of the kernel parameters
     int64_t launches = 0;
     std::string err;
@@ -308,6 +309,8 @@ int thr_create(const thr_config *cfg, thr_detector **out) {
         CUC(cudaMalloc(&s.d_out, (size_t)cfg->max_batch * NT * sizeof(thr_record)));
     }
     d->c64_chunk = cfg->max_batch < 512 ? cfg->max_batch : 512;
+    d->host_chunk = d->grid * 4 < 256 ? 256 : d->grid * 4;
+    if (d->host_chunk > cfg->max_batch) d->host_chunk = cfg->max_batch;
 
     // ---- constant kernel parameters
     DetectParams &p = d->base;
@@ -420,7 +423,9 @@ static int detect_host(thr_detector *d, const uint8_t *raw, const float *iq, con
     if (!d || (!raw && !iq) || !out || n_blocks < 0) return d ? fail(d, THR_ERR_INVALID, "null/negative argument") : THR_ERR_INVALID;
     CU(d, cudaSetDevice(d->device));
     const int N = d->cfg.block_len, NT = d->cfg.n_templates;
-    const int64_t chunk = raw ? d->cfg.max_batch : d->c64_chunk;
+    // chunks small enough that the H2D copy of chunk c+1 overlaps the kernel of chunk c even within
+    // one max_batch-sized call, large enough to give every persistent CTA a few blocks
+    int64_t chunk = raw ? d->host_chunk : d->c64_chunk;
     if (iq) {
         for (auto &s : d->slot)
             if (!s.d_iq) CU(d, cudaMalloc(&s.d_iq, (size_t)d->c64_chunk * N * 8));

@@ -1,0 +1,282 @@
+"""Detect positioning signals and estimate sample-of-arrival -- B200 drop-in for thrifty.detect.
+
+Same public surface as thrifty/detect.py:24-227:
+
+  * ``DetectorSettings`` namedtuple (detect.py:24-31),
+  * ``Detector(settings, blocks, rxid, yield_data)``: iterator yielding one
+    ``(detected, DetectionResult)`` per input block, in input order, including blocks
+    without a carrier (detect.py:80-91); ``detect(timestamp, block_idx, block)`` for
+    single blocks (detect.py:60-78); with ``yield_data=True`` the shifted spectrum and the
+    correlation are returned too (detect.py:75-76),
+  * ``SummaryLineFormatter`` (detect.py:103-158) and ``detector_cli(detector_class, ...)``
+    (detect.py:161-223), the plug-in seam used by the reference's experimental detectors.
+
+All arithmetic runs in the fused CUDA kernel behind the C ABI (include/thrifty_b200.h);
+this module only batches blocks (read-ahead of ``batch`` blocks per launch) and converts
+the 64-byte records back into the reference's result types.  There is no CPU fallback.
+"""
+
+from __future__ import print_function
+
+import argparse
+import sys
+from collections import namedtuple
+
+import numpy as np
+
+from thrifty_b200 import toads_data, util
+from thrifty_b200._native import FLAG_CARRIER, FLAG_CORR, NativeDetector
+from thrifty_b200.block_data import block_reader, card_reader
+from thrifty_b200.setting_parsers import normalize_freq_range
+from thrifty_b200.settings import load_args
+
+DetectorSettings = namedtuple("DetectorSettings", [
+    "block_len", "history_len", "carrier_len", "carrier_thresh", "carrier_window",
+    "template", "corr_thresh"])
+
+
+def record_to_result(rec, timestamp, rxid):
+    """thr_record -> (detected, DetectionResult) with the reference's field types."""
+    carrier_found = bool(rec["flags"] & FLAG_CARRIER)
+    detected = bool(rec["flags"] & FLAG_CORR)
+    carrier_info = toads_data.CarrierSyncInfo(
+        int(rec["carrier_bin"]), float(rec["carrier_offset"]) if carrier_found else 0,
+        rec["carrier_energy"], rec["carrier_noise"])
+    if carrier_found:
+        corr_info = toads_data.CorrDetectionInfo(
+            int(rec["corr_sample"]), float(rec["corr_offset"]) if detected else 0,
+            float(rec["corr_energy"]), float(rec["corr_noise"]))
+        soa = float(rec["soa"])
+    else:
+        corr_info, soa = None, None
+    result = toads_data.DetectionResult(timestamp, int(rec["block_idx"]), soa, carrier_info,
+                                        corr_info, rxid)
+    return detected, result
+
+
+class Detector(object):
+    """All-in-one carrier detect / sync / correlate / SoA estimate on the GPU.
+
+    Parameters follow thrifty/detect.py:40; extras: ``batch`` = blocks per kernel launch
+    (read-ahead of the iterator), ``device`` = CUDA ordinal.  ``block`` arguments may be
+    complex arrays of length block_len (reference behaviour) or uint8 arrays of length
+    2*block_len (raw I/Q, conversion then runs on the GPU)."""
+
+    def __init__(self, settings, blocks=None, rxid=-1, yield_data=False, batch=256, device=0):
+        self.settings = settings
+        self.blocks = iter(blocks) if blocks is not None else None
+        self.rxid = rxid
+        self.yield_data = yield_data
+        self.batch = max(1, int(batch))
+        template = np.asarray(settings.template, dtype=np.float64)
+        if template.ndim != 1:
+            raise ValueError("Detector takes a single 1-D template; see MultiTemplateDetector")
+        assert settings.history_len >= len(template) - 1     # soa_estimator.py:33
+        self.native = NativeDetector(
+            settings.block_len, settings.history_len, template, settings.carrier_len,
+            settings.carrier_window, settings.carrier_thresh, settings.corr_thresh,
+            device=device, max_batch=self.batch)
+        self.new_len = settings.block_len - settings.history_len
+        self._pending = []
+
+    # ---- single block (detect.py:60-78)
+    def detect(self, timestamp, block_idx, block):
+        """Process the given block of data."""
+        block = np.asarray(block)
+        is_raw = block.dtype == np.uint8
+        assert len(block) == (2 if is_raw else 1) * self.settings.block_len
+        if self.yield_data:
+            recs, sfft, corr, _ = self.native.detect_block_data(
+                raw=block if is_raw else None, iq=None if is_raw else block, block_idx=block_idx)
+            detected, result = record_to_result(recs[0], timestamp, self.rxid)
+            if result.corr_info is None:
+                return detected, result, None, None
+            return detected, result, sfft, corr
+        if is_raw:
+            recs = self.native.detect_raw(block[None, :], [block_idx])
+        else:
+            recs = self.native.detect_c64(block[None, :], [block_idx])
+        return record_to_result(recs[0, 0], timestamp, self.rxid)
+
+    def __call__(self, timestamp, block_idx, block):
+        return self.detect(timestamp, block_idx, block)
+
+    # ---- batch of blocks: list of (timestamp, block_idx, block)
+    def detect_many(self, items):
+        """One launch for a list of (timestamp, block_idx, block); returns a list of
+        (detected, DetectionResult) in input order."""
+        if not items:
+            return []
+        n = self.settings.block_len
+        idx = np.array([it[1] for it in items], dtype=np.int64)
+        blocks = [np.asarray(it[2]) for it in items]
+        if all(b.dtype == np.uint8 for b in blocks):
+            for b in blocks:
+                assert len(b) == 2 * n
+            recs = self.native.detect_raw(np.stack(blocks), idx)
+        else:
+            from thrifty_b200.block_data import raw_to_complex
+            conv = []
+            for b in blocks:
+                if b.dtype == np.uint8:
+                    assert len(b) == 2 * n
+                    b = raw_to_complex(b)
+                assert len(b) == n                                  # detect.py:62
+                conv.append(np.asarray(b, dtype=np.complex64))
+            recs = self.native.detect_c64(np.stack(conv), idx)
+        return [record_to_result(recs[i, 0], items[i][0], self.rxid) for i in range(len(items))]
+
+    # ---- iterator protocol (detect.py:80-91)
+    def next(self):
+        """Process the next block of data."""
+        if self.yield_data:
+            return self.detect(*next(self.blocks))
+        if not self._pending:
+            items = []
+            for item in self.blocks:
+                items.append(item)
+                if len(items) >= self.batch:
+                    break
+            if not items:
+                raise StopIteration
+            self._pending = self.detect_many(items)
+            self._pending.reverse()
+        return self._pending.pop()
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        return self.next()
+
+    def close(self):
+        self.native.close()
+
+
+class MultiTemplateDetector(object):
+    """Joint correlation against several templates (BASELINE.json config 5).
+
+    FFT #1, the carrier fit, the mix and FFT #2 are shared; the multiply / IFFT / peak stage
+    runs once per template inside the same kernel pass.  ``detect_many`` returns, per block,
+    a list with one (detected, DetectionResult) per template (result.txid = template index).
+    Equivalent to running one reference Detector per template on the same block."""
+
+    def __init__(self, settings, templates, rxid=-1, batch=256, device=0):
+        templates = np.asarray(templates, dtype=np.float64)
+        assert templates.ndim == 2
+        self.settings = settings
+        self.rxid = rxid
+        self.n_templates = templates.shape[0]
+        self.native = NativeDetector(
+            settings.block_len, settings.history_len, templates, settings.carrier_len,
+            settings.carrier_window, settings.carrier_thresh, settings.corr_thresh,
+            device=device, max_batch=batch)
+
+    def detect_many(self, items):
+        idx = np.array([it[1] for it in items], dtype=np.int64)
+        raw = np.stack([np.asarray(it[2], dtype=np.uint8) for it in items])
+        recs = self.native.detect_raw(raw, idx)
+        out = []
+        for i, it in enumerate(items):
+            per_tpl = []
+            for t in range(self.n_templates):
+                detected, res = record_to_result(recs[i, t], it[0], self.rxid)
+                res.txid = t
+                per_tpl.append((detected, res))
+            out.append(per_tpl)
+        return out
+
+    def close(self):
+        self.native.close()
+
+
+def _carrier_freq(carrier_info, block_len, sample_rate):
+    """Carrier bin + offset -> Hz (detect.py:94-100)."""
+    pos = util.fft_bin(carrier_info.bin, block_len) + carrier_info.offset
+    return pos * sample_rate / block_len
+
+
+class SummaryLineFormatter(object):
+    """One-line human-readable summary per block (detect.py:103-158)."""
+
+    def __init__(self, sample_rate, block_len, add_dt=False):
+        self.sample_rate = sample_rate
+        self.block_len = block_len
+        self.add_dt = add_dt
+
+    def __call__(self, detected, result):
+        carrier_detect = result.corr_info is not None
+        ci = result.carrier_info
+        info = ("blk={blk}; carrier: {det} @ {freq:.3f} kHz / {idx:>3.0f}:{offset:+.2f}, "
+                "SNR = {ampl:>4.0f} / {noise:>2.0f} = {snr:>5.2f} dB".format(
+                    blk=result.block, det="yes" if carrier_detect else "no ",
+                    freq=_carrier_freq(ci, self.block_len, self.sample_rate) / 1e3,
+                    idx=ci.bin, offset=ci.offset, ampl=ci.energy, noise=ci.noise,
+                    snr=util.snr(ci.energy, ci.noise)))
+        if carrier_detect:
+            co = result.corr_info
+            info += ("; corr: {det} @ {idx:>4}{offset:+.3f}, "
+                     "SNR = {ampl:>4.0f}/{noise:>2.0f} = {snr:>5.2f} dB".format(
+                         det="yes" if detected else "no ", idx=co.sample, offset=co.offset,
+                         ampl=co.energy, noise=co.noise, snr=util.snr(co.energy, co.noise)))
+        return info
+
+
+def detector_cli(detector_class, parser=None, extra_args=None, argv=None):
+    """`thrifty detect` command line (detect.py:161-223); `detector_class` is the plug-in seam."""
+    if parser is None:
+        parser = argparse.ArgumentParser(description=__doc__,
+                                         formatter_class=argparse.RawDescriptionHelpFormatter)
+    parser.add_argument("input", type=argparse.FileType("rb"), default="-",
+                        help="input data ('-' streams from stdin)")
+    parser.add_argument("--raw", dest="raw", action="store_true", help="input data is raw binary data")
+    parser.add_argument("--quiet", dest="quiet", action="store_true",
+                        help="do not write anything to standard output")
+    parser.add_argument("--batch", dest="batch", type=int, default=256,
+                        help="blocks per GPU launch (read-ahead) [default: 256]")
+    parser.add_argument("--device", dest="device", type=int, default=0, help="CUDA device ordinal")
+    group = parser.add_mutually_exclusive_group()
+    group.add_argument("-o", "--output", dest="output", type=argparse.FileType("w"),
+                       help="Output file (.toad) ('-' for stdout)")
+    group.add_argument("-a", "--append", dest="append", type=argparse.FileType("a"),
+                       help="Output file to append to (.toad)")
+    setting_keys = ["sample_rate", "block_size", "block_history", "carrier_window",
+                    "carrier_threshold", "corr_threshold", "template", "rxid"]
+    config, args = load_args(parser, setting_keys, argv=argv)
+
+    kwargs = {}
+    if extra_args is not None:
+        kwargs = {arg: args[arg] for arg in extra_args}
+    output_file = args.output if args.append is None else args.append
+    info_out = sys.stderr if output_file == sys.stdout else sys.stdout
+    bin_freq = config.sample_rate / config.block_size
+    window = normalize_freq_range(config.carrier_window, bin_freq)
+    if args.raw:
+        blocks = block_reader(args.input, config.block_size, config.block_history, raw=True)
+    else:
+        blocks = card_reader(args.input, raw=True)
+    template = np.load(config.template)
+    settings = DetectorSettings(block_len=config.block_size, history_len=config.block_history,
+                                carrier_len=len(template), carrier_thresh=config.carrier_threshold,
+                                carrier_window=window, template=template,
+                                corr_thresh=config.corr_threshold)
+    if issubclass(detector_class, Detector):
+        kwargs.setdefault("batch", args.batch)
+        kwargs.setdefault("device", args.device)
+    detections = detector_class(settings, blocks, rxid=config.rxid, **kwargs)
+    summary_liner = SummaryLineFormatter(config.sample_rate, config.block_size, add_dt=True)
+    for detected, result in detections:
+        if detected and output_file is not None:
+            print(result.serialize(), file=output_file)
+        if not args.quiet:
+            print(summary_liner(detected, result), file=info_out)
+    if output_file is not None:
+        output_file.flush()
+
+
+def _main(argv=None):
+    detector_cli(Detector, argv=argv)
+
+
+if __name__ == "__main__":
+    _main()
