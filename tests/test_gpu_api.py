@@ -192,7 +192,7 @@ def test_empty_and_single_block():
     assert got.shape == (1, 1) and got["block_idx"][0, 0] == 123456789012
     assert got["flags"][0, 0] == 3
     # SoA keeps integer precision for huge block indices (detect.py:67)
-    expect = (n - hist) * 123456789012 + got["corr_sample"][0, 0] + float(got["corr_offset"][0, 0])
+    expect = (n - hist) * 123456789012 + int(got["corr_sample"][0, 0]) + float(got["corr_offset"][0, 0])
     assert abs(got["soa"][0, 0] - expect) <= 1.0
     with pytest.raises(ValueError):
         det.detect_raw(np.zeros((2, 100), dtype=np.uint8))
@@ -237,14 +237,16 @@ def test_full_size_properties():
     assert car.sum() > total // 2
     lin = got["soa"][car] - (n - hist) * idx[car].astype(np.float64)
     np.testing.assert_allclose(lin, got["corr_sample"][car] + got["corr_offset"][car].astype(np.float64),
-                               rtol=0, atol=2e-3)     # float64 ulp at 1e14 is 0.016/8
+                               rtol=0, atol=1e-2)     # float64 ulp at (N-H)*2^33 ~ 1e14 is 0.016
     # oracle on the unique blocks
     st = orc.DetectorSettings(n, hist, len(tpl), (0., 15., 0.), (7, 110), tpl, (0., 15., 0.))
     ref = orc.detect_blocks(st, uniq)
     firsts = np.array([np.nonzero(pick == u)[0][0] for u in range(uniq_n)])
     g = got[firsts].copy()
     g["block_idx"] = np.arange(uniq_n)
-    g["soa"] = g["soa"] - (n - hist) * idx[firsts].astype(np.float64) + (n - hist) * np.arange(uniq_n)
+    # re-base the SoA on small block indices (at idx ~ 2^33 a float64 SoA only resolves 0.016 samples;
+    # linearity in block_idx was checked above)
+    g["soa"] = (n - hist) * np.arange(uniq_n) + g["corr_sample"] + g["corr_offset"].astype(np.float64)
     parity.compare_records(g, ref, what="full-size")
     # complex64 input path, first 300 blocks
     iq = np.stack([orc.raw_to_complex(r) for r in raw[:300]])

@@ -97,14 +97,50 @@ __host__ __device__ constexpr int brev(int v, int bits) {
 }
 __host__ __device__ constexpr int ilog2(int v) { return v <= 1 ? 0 : 1 + ilog2(v >> 1); }
 
-// cos / sin of 2*pi*q/32, q in [0,16)
-__host__ __device__ constexpr float cos32(int q) {
-    return q == 0 ? 1.0f : q == 1 ? 0.98078528040323043f : q == 2 ? 0.92387953251128674f
-         : q == 3 ? 0.83146961230254524f : q == 4 ? 0.70710678118654752f
-         : q == 5 ? 0.55557023301960218f : q == 6 ? 0.38268343236508977f
-         : q == 7 ? 0.19509032201612825f : q == 8 ? 0.0f : -cos32(16 - q);
+// cos / sin of 2*pi*q/32, q in [0,16).  Flat switches (no recursion) so that the calls always
+// inline and fold to immediates once the butterfly loops are unrolled.
+__host__ __device__ __forceinline__ constexpr float cos32(int q) {
+    switch (q) {
+        case 0: return 1.0f;
+        case 1: return 0.98078528040323043f;
+        case 2: return 0.92387953251128674f;
+        case 3: return 0.83146961230254524f;
+        case 4: return 0.70710678118654757f;
+        case 5: return 0.55557023301960229f;
+        case 6: return 0.38268343236508984f;
+        case 7: return 0.19509032201612833f;
+        case 8: return 0.0f;
+        case 9: return -0.19509032201612819f;
+        case 10: return -0.38268343236508973f;
+        case 11: return -0.55557023301960196f;
+        case 12: return -0.70710678118654746f;
+        case 13: return -0.83146961230254535f;
+        case 14: return -0.92387953251128674f;
+        case 15: return -0.98078528040323043f;
+        default: return 0.0f;
+    }
 }
-__host__ __device__ constexpr float sin32(int q) { return q <= 8 ? cos32(8 - q) : cos32(q - 8); }
+__host__ __device__ __forceinline__ constexpr float sin32(int q) {
+    switch (q) {
+        case 0: return 0.0f;
+        case 1: return 0.19509032201612825f;
+        case 2: return 0.38268343236508978f;
+        case 3: return 0.55557023301960218f;
+        case 4: return 0.70710678118654746f;
+        case 5: return 0.83146961230254524f;
+        case 6: return 0.92387953251128674f;
+        case 7: return 0.98078528040323043f;
+        case 8: return 1.0f;
+        case 9: return 0.98078528040323043f;
+        case 10: return 0.92387953251128674f;
+        case 11: return 0.83146961230254546f;
+        case 12: return 0.70710678118654757f;
+        case 13: return 0.55557023301960218f;
+        case 14: return 0.38268343236508989f;
+        case 15: return 0.19509032201612861f;
+        default: return 0.0f;
+    }
+}
 
 // In-register radix-2 DIF FFT of size R (power of two <= 32), forward sign (e^{-i...}).
 // Output k is left at index brev(k).  Calling it as fft_dif(xi, xr) computes the inverse
@@ -242,7 +278,8 @@ __device__ __forceinline__ RedOut block_reduce(float s0, float s1, unsigned long
 
 // ------------------------------------------------------------------ Dirichlet-kernel fit
 // Least-squares fit of A*|D(x - d)| to 7 magnitudes at x = -3..3 (carrier_sync.py:150-196,
-// scipy curve_fit 'lm' from p0 = (y[0], 0)).  Executed by one warp: lane i < 7 owns point i.
+// scipy curve_fit 'lm' from p0 = (y[0], 0)).  Executed by one warp: lane i (mod 8) < 7 owns
+// point i; the four groups of 8 lanes compute the same thing so control flow stays uniform.
 // D(z) = sin(aWz) / (W sin(az)), a = pi/N.  The trig of the fixed abscissae comes from
 // fit_tab; each iteration only needs sincos of a*W*d and a*d (angle-difference identities).
 struct FitSums {
@@ -262,10 +299,10 @@ __device__ __forceinline__ FitSums fit_eval(float y, bool active, float A, float
         D = 1.0f;
         Dp = 0.0f;
     } else {
-        const float inv = 1.0f / (W * s2);
+        const float inv = __fdividef(1.0f, W * s2);
         D = s1 * inv;
         const float a = 3.14159265358979f * invN;
-        Dp = a * (W * c1 * s2 - s1 * c2) * inv / s2;
+        Dp = a * (W * c1 * s2 - s1 * c2) * inv * __fdividef(1.0f, s2);
     }
     const float g = fabsf(D);
     const float gp = D < 0.f ? -Dp : Dp;
@@ -280,7 +317,7 @@ __device__ __forceinline__ FitSums fit_eval(float y, bool active, float A, float
     f.jdr = active ? jd * r : 0.f;
     f.cost = active ? r * r : 0.f;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {   // full warp: keeps every lane's control flow uniform
+    for (int o = 4; o > 0; o >>= 1) {   // within each group of 8 lanes (all groups identical)
         f.jaa += __shfl_xor_sync(0xffffffffu, f.jaa, o);
         f.jad += __shfl_xor_sync(0xffffffffu, f.jad, o);
         f.jdd += __shfl_xor_sync(0xffffffffu, f.jdd, o);
@@ -291,39 +328,51 @@ __device__ __forceinline__ FitSums fit_eval(float y, bool active, float A, float
     return f;
 }
 
-// returns delta (uniform over the calling warp; all 32 lanes must call)
+// y: magnitude of point (lane & 7) (ignored for (lane & 7) == 7).  Returns delta, warp-uniform.
 __device__ __forceinline__ float dirichlet_fit(float y, int lane, const DetectParams &p) {
-    const bool active = lane < 7;
+    const int li = lane & 7;
+    const bool active = li < 7;
     float tab[4];
-    const int li = active ? lane : 0;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) tab[q] = p.fit_tab[li][q];
+    for (int q = 0; q < 4; ++q) tab[q] = p.fit_tab[active ? li : 0][q];
     float A = __shfl_sync(0xffffffffu, y, 3);
     float d = 0.f;
-    float lambda = 1e-4f;
+    float lambda = 0.f;                   // Gauss-Newton first; Marquardt damping only if a step fails
     FitSums f = fit_eval(y, active, A, d, tab, p.fit_W, p.fit_WoverN, p.fit_invN);
-    for (int it = 0; it < 40; ++it) {
-        // (J^T J + lambda diag) step = J^T r
+    for (int it = 0; it < 30; ++it) {
         const float a11 = f.jaa * (1.f + lambda), a22 = f.jdd * (1.f + lambda), a12 = f.jad;
         const float det = a11 * a22 - a12 * a12;
         if (!(fabsf(det) > 0.f)) break;
-        const float dA = (a22 * f.jar - a12 * f.jdr) / det;
-        const float dd = (a11 * f.jdr - a12 * f.jar) / det;
+        const float idet = 1.0f / det;
+        const float dA = (a22 * f.jar - a12 * f.jdr) * idet;
+        const float dd = (a11 * f.jdr - a12 * f.jar) * idet;
+        const bool tiny = fabsf(dd) < 5e-7f && fabsf(dA) <= 1e-6f * fabsf(A);
         const float An = A + dA, dn = d + dd;
         const FitSums fn = fit_eval(y, active, An, dn, tab, p.fit_W, p.fit_WoverN, p.fit_invN);
-        if (fn.cost <= f.cost) {
+        if (fn.cost <= f.cost * 1.000001f) {
             A = An;
             d = dn;
             f = fn;
             lambda *= 0.1f;
-            if (fabsf(dd) < 1e-7f && fabsf(dA) <= 1e-7f * fabsf(A)) break;
+            if (tiny) break;
         } else {
-            if (fabsf(dd) < 1e-7f && fabsf(dA) <= 1e-7f * fabsf(A)) break;   // converged to rounding
-            lambda = lambda * 10.f + 1e-6f;
-            if (lambda > 1e10f) break;
+            if (tiny) break;
+            lambda = lambda * 10.f + 1e-3f;
+            if (lambda > 1e8f) break;
         }
     }
     return d;
+}
+
+// ------------------------------------------------------------------ rawconv
+// (b - 127.4f) / 128 exactly as numpy float32 does it (block_data.py:38-52), without I2F:
+// 0x4B000000 | b is the float 2^23 + b; subtracting 2^23 is exact, and the fused multiply-add
+// rounds the exact value (b - 127.4f) * 2^-7, which is representable.
+__device__ __forceinline__ float2 rawconv(uint32_t w16) {
+    const float fx = __uint_as_float(__byte_perm(w16, 0x4B000000u, 0x7650)) - 8388608.0f;
+    const float fy = __uint_as_float(__byte_perm(w16, 0x4B000000u, 0x7651)) - 8388608.0f;
+    constexpr float c = -127.4f * 0.0078125f;
+    return make_float2(fmaf(fx, 0.0078125f, c), fmaf(fy, 0.0078125f, c));
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -342,11 +391,11 @@ detect_kernel(const __grid_constant__ DetectParams p) {
 
     // ---- shared memory carve-up
     size_t off = 0;
-    float2 *buf;
+    unsigned char *bufc;                 // FFT buffer, byte-addressed
     if (GMEM) {
-        buf = p.scratch + (size_t)blockIdx.x * N;
+        bufc = reinterpret_cast<unsigned char *>(p.scratch + (size_t)blockIdx.x * N);
     } else {
-        buf = reinterpret_cast<float2 *>(smem);
+        bufc = smem;
         off += (size_t)N * 8;
     }
     unsigned char *raw_s = smem + off;
@@ -359,6 +408,24 @@ detect_kernel(const __grid_constant__ DetectParams p) {
     float *bc = reinterpret_cast<float *>(smem + off + 256);    // broadcast scratch (64 floats)
     off += 1024;
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + off);  // 2 barriers
+
+    // FFT buffer access.  Shared memory: element e lives at e ^ ((e >> 4) & 15) (8-byte units),
+    // which every pass below expresses as (per-item byte address) XOR (compile-time constant)
+    // plus a compile-time offset.  Global scratch (GMEM): plain layout, L2-only accesses.
+    auto ld8 = [&](uint32_t byte_off) -> float2 {
+        if constexpr (GMEM) return __ldcg(reinterpret_cast<const float2 *>(bufc + byte_off));
+        else return *reinterpret_cast<const float2 *>(bufc + byte_off);
+    };
+    auto st8 = [&](uint32_t byte_off, float2 v) {
+        if constexpr (GMEM) __stcg(reinterpret_cast<float2 *>(bufc + byte_off), v);
+        else *reinterpret_cast<float2 *>(bufc + byte_off) = v;
+    };
+    // pass-1 item j, element k1 (logical e = k1*M + j)
+    auto a1_base = [&](int j) -> uint32_t { return GMEM ? (uint32_t)j * 8u : (uint32_t)(j ^ ((j >> 4) & 15)) * 8u; };
+    // element k1 of a pass-1 item sits at base + k1*M*8 when M is a multiple of 256 (the swizzle
+    // then only depends on j); smaller sizes recompute the swizzle from the logical index
+    auto pos_generic = [&](int e) -> uint32_t { return (uint32_t)C::pos(e) * 8u; };
+    constexpr bool FAST_ADDR = GMEM || (M % 256 == 0);
 
     // ---- one-time per-CTA setup: twiddles
     for (int idx = tid; idx < M; idx += T) {
@@ -374,6 +441,9 @@ detect_kernel(const __grid_constant__ DetectParams p) {
         w4[i] = cispi(-2.0f * (float)((4 * j) & (N - 1)) / (float)N);
     }
     const bool use_raw = (p.raw != nullptr);
+    const bool dbg = (p.dbg_fft_mag != nullptr) || (p.dbg_shifted_fft != nullptr) || (p.dbg_corr != nullptr);
+    const bool need_std_c = (p.c_std != 0.f);
+    const bool need_std_k = (p.k_std != 0.f);
     if (tid == 0) {
         mbar_init(&mbar[0], 1);
         mbar_init(&mbar[1], 1);
@@ -390,7 +460,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
 
     for (int blk = blockIdx.x; blk < p.n_blocks; blk += gridDim.x) {
         // ---- prefetch the next block's raw tile into the other stage, wait for ours
-        const unsigned char *rawt = raw_s + (size_t)stage * RAW_BYTES;
+        const uint16_t *rawt = reinterpret_cast<const uint16_t *>(raw_s + (size_t)stage * RAW_BYTES);
         if (use_raw) {
             const int nxt = blk + gridDim.x;
             if (tid == 0 && nxt < p.n_blocks) {
@@ -404,38 +474,36 @@ detect_kernel(const __grid_constant__ DetectParams p) {
         const float2 *iqb = use_raw ? nullptr : p.iq + (size_t)blk * N;
         const int64_t bidx = p.block_idx ? p.block_idx[blk] : (int64_t)blk;
 
-        // sample loader: rawconv (block_data.py:38-52) or complex64 passthrough
-        auto load_x = [&](int n) -> float2 {
-            if (use_raw) {
-                const uchar2 b = reinterpret_cast<const uchar2 *>(rawt)[n];
-                return make_float2(((float)b.x - 127.4f) * 0.0078125f, ((float)b.y - 127.4f) * 0.0078125f);
-            } else {
-                return __ldg(&iqb[n]);
-            }
-        };
-
-        // FFT buffer accessors: swizzled shared memory, or L2-only global scratch
-        auto bld = [&](int e) -> float2 {
-            if constexpr (GMEM) return __ldcg(&buf[e]);
-            else return buf[C::pos(e)];
-        };
-        auto bst = [&](int e, float2 v) {
-            if constexpr (GMEM) __stcg(&buf[e], v);
-            else buf[C::pos(e)] = v;
-        };
-
         // ================= forward FFT passes (shared by FFT#1 and FFT#2) =================
-        // pass 1: radix-32 over n1 (stride M), twiddle W_N^{j k1}, in-place store
-        auto fwd_pass1 = [&](auto &&loader) {
+        // pass 1: samples (rawconv or complex64) [* mix phasor] -> radix-32 over n1 (stride M)
+        //         -> twiddle W_N^{j k1} -> in-place store
+        auto fwd_pass1 = [&](bool mix, const float2 (&ph0)[I1]) {
 #pragma unroll
             for (int i = 0; i < I1; ++i) {
                 const int j = tid + T * i;
                 float xr[32], xi[32];
+                if (use_raw) {
 #pragma unroll
-                for (int n1 = 0; n1 < 32; ++n1) {
-                    const float2 v = loader(n1 * M + j, n1, i);
-                    xr[n1] = v.x;
-                    xi[n1] = v.y;
+                    for (int n1 = 0; n1 < 32; ++n1) {
+                        const float2 v = rawconv(rawt[n1 * M + j]);
+                        xr[n1] = v.x;
+                        xi[n1] = v.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int n1 = 0; n1 < 32; ++n1) {
+                        const float2 v = __ldg(&iqb[n1 * M + j]);
+                        xr[n1] = v.x;
+                        xi[n1] = v.y;
+                    }
+                }
+                if (mix) {
+#pragma unroll
+                    for (int n1 = 0; n1 < 32; ++n1) {
+                        const float2 v = cmul(make_float2(xr[n1], xi[n1]), cmul(ph0[i], rho[n1]));
+                        xr[n1] = v.x;
+                        xi[n1] = v.y;
+                    }
                 }
                 fft_dif<32>(xr, xi);
                 float2 cur[4];
@@ -443,14 +511,27 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 cur[1] = cmul(w1[i], w1[i]);
                 cur[2] = cmul(cur[1], w1[i]);
                 cur[3] = w4[i];
-                bst(j, make_float2(xr[0], xi[0]));
+                const uint32_t ab = a1_base(j);
+                if constexpr (FAST_ADDR) st8(ab, make_float2(xr[0], xi[0]));
+                else st8(pos_generic(j), make_float2(xr[0], xi[0]));
 #pragma unroll
                 for (int k1 = 1; k1 < 32; ++k1) {
                     const int r = brev(k1, 5);
                     if (k1 > 4) cur[(k1 - 1) & 3] = cmul(cur[(k1 - 1) & 3], w4[i]);
-                    bst(k1 * M + j, cmul(make_float2(xr[r], xi[r]), cur[(k1 - 1) & 3]));
+                    const float2 v = cmul(make_float2(xr[r], xi[r]), cur[(k1 - 1) & 3]);
+                    if constexpr (FAST_ADDR) st8(ab + (uint32_t)k1 * (M * 8u), v);
+                    else st8(pos_generic(k1 * M + j), v);
                 }
             }
+        };
+        // pass-2 addressing: item (k1, n3), element n2 (logical e = k1*M + n2*R3 + n3)
+        auto a2_base = [&](int k1, int n3) -> uint32_t {
+            if constexpr (GMEM) return (uint32_t)(k1 * M + n3) * 8u;
+            else return (uint32_t)(k1 * M) * 8u + (((uint32_t)n3 ^ (((uint32_t)k1 * R2) & 15u)) * 8u);
+        };
+        auto a2 = [&](uint32_t base, int n2) -> uint32_t {
+            if constexpr (GMEM) return base + (uint32_t)n2 * (R3 * 8u);
+            else return (base ^ (((uint32_t)n2 & 15u) * 8u)) + (uint32_t)n2 * (R3 * 8u);
         };
         // pass 2: radix-R2 over n2 (stride R3) inside each k1 slab, twiddle W_M^{n3 k2}
         auto fwd_pass2 = [&]() {
@@ -459,11 +540,11 @@ detect_kernel(const __grid_constant__ DetectParams p) {
             for (int i = 0; i < I2; ++i) {
                 const int w = tid + T * i;
                 const int k1 = w >> LOG2R3, n3 = w & (R3 - 1);
-                const int base = k1 * M + n3;
+                const uint32_t ab = a2_base(k1, n3);
                 float xr[R2], xi[R2];
 #pragma unroll
                 for (int n2 = 0; n2 < R2; ++n2) {
-                    const float2 v = bld(base + n2 * R3);
+                    const float2 v = ld8(a2(ab, n2));
                     xr[n2] = v.x;
                     xi[n2] = v.y;
                 }
@@ -473,13 +554,25 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                     const int r = brev(k2, LOG2R2);
                     float2 v = make_float2(xr[r], xi[r]);
                     if (k2 > 0) v = cmul(v, tw2[k2 * R3 + n3]);
-                    bst(base + k2 * R3, v);
+                    st8(a2(ab, k2), v);
                 }
             }
         };
+        // pass-3 addressing: item g, element n3 (logical e = g*R3 + n3)
+        auto a3_base = [&](int g) -> uint32_t {
+            if constexpr (GMEM) return (uint32_t)g * (R3 * 8u);
+            else return (uint32_t)g * (R3 * 8u) + ((uint32_t)g & 15u) * 8u;
+        };
+        auto a3 = [&](uint32_t base, int n3) -> uint32_t {
+            if constexpr (GMEM) return base + (uint32_t)n3 * 8u;
+            else return base ^ ((uint32_t)n3 * 8u);
+        };
 
         // ================= FFT #1 =================
-        fwd_pass1([&](int n, int, int) { return load_x(n); });
+        float2 ph_unused[I1];
+#pragma unroll
+        for (int i = 0; i < I1; ++i) ph_unused[i] = make_float2(1.f, 0.f);
+        fwd_pass1(false, ph_unused);
         __syncthreads();
         fwd_pass2();
         if (R2 > 1) __syncthreads();
@@ -487,15 +580,16 @@ detect_kernel(const __grid_constant__ DetectParams p) {
         // pass 3 + power spectrum (Signal.mag, signal_utils.py:99-107) + windowed arg-max
         float pw[I3][R3];
         float esum = 0.f, msum = 0.f;
-        unsigned long long best = 0ull;
-        const bool need_std_c = (p.c_std != 0.f);
+        float bestv = -1.f;
+        uint32_t bestrel = 0;
 #pragma unroll
         for (int i = 0; i < I3; ++i) {
             const int g = tid + T * i;
+            const uint32_t ab = a3_base(g);
             float xr[R3], xi[R3];
 #pragma unroll
             for (int n3 = 0; n3 < R3; ++n3) {
-                const float2 v = bld(g * R3 + n3);
+                const float2 v = ld8(a3(ab, n3));
                 xr[n3] = v.x;
                 xi[n3] = v.y;
             }
@@ -507,17 +601,30 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 const float pv = xr[r] * xr[r] + xi[r] * xi[r];
                 pw[i][k3] = pv;
                 esum += pv;
-                if (need_std_c) msum += sqrtf(pv);
-                const int k = kb + S * k3;
-                const uint32_t rel = (uint32_t)(k - p.win_start) & (uint32_t)(N - 1);
-                if (rel < (uint32_t)p.win_len) {
-                    const unsigned long long c = pack_cand(pv, rel);
-                    best = c > best ? c : best;
+            }
+            if (need_std_c) {
+#pragma unroll
+                for (int k3 = 0; k3 < R3; ++k3) msum += sqrtf(pw[i][k3]);
+            }
+            // window test: bin k = kb + S*k3, rel = (k - win_start) mod N must be < win_len.
+            // rel mod S does not depend on k3, so a narrow window rejects most items at once.
+            const uint32_t relb = (uint32_t)(kb - p.win_start) & (uint32_t)(N - 1);
+            if ((relb & (uint32_t)(S - 1)) < (uint32_t)p.win_len) {
+#pragma unroll
+                for (int k3 = 0; k3 < R3; ++k3) {
+                    const uint32_t rel = (relb + (uint32_t)(S * k3)) & (uint32_t)(N - 1);
+                    if (rel < (uint32_t)p.win_len && pw[i][k3] > bestv) {
+                        bestv = pw[i][k3];
+                        bestrel = rel;
+                    }
                 }
-                if (p.dbg_fft_mag) p.dbg_fft_mag[k] = sqrtf(pv);
+            }
+            if (dbg && p.dbg_fft_mag) {
+#pragma unroll
+                for (int k3 = 0; k3 < R3; ++k3) p.dbg_fft_mag[kb + S * k3] = sqrtf(pw[i][k3]);
             }
         }
-        const RedOut ra = block_reduce<T>(esum, msum, best, red, tid);
+        const RedOut ra = block_reduce<T>(esum, msum, bestv >= 0.f ? pack_cand(bestv, bestrel) : 0ull, red, tid);
 
         // ---- carrier decision in float32 (carrier_detect.py:99-115)
         const float peak_pw = __uint_as_float((uint32_t)(ra.best >> 32));
@@ -529,9 +636,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
         float var_c = 0.f;
         if (need_std_c) {
             const float mean = ra.s1 / (float)N;
-            var_c = ra.s0 / (float)N - mean * mean;
-            var_c = sqrtf(fmaxf(var_c, 0.f));
-            var_c = var_c * var_c;
+            var_c = fmaxf(ra.s0 / (float)N - mean * mean, 0.f);
         }
         const float thr_c = sqrtf(p.c_const + p.c_snr * (noise_c * noise_c) + p.c_std * var_c);
         const bool carrier = peak_mag > thr_c;
@@ -577,7 +682,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
         }
         __syncthreads();
         if (tid < 32) {
-            const float y = lane < 7 ? bc[lane] : 0.f;
+            const float y = (lane & 7) < 7 ? bc[lane & 7] : 0.f;
             const float d = dirichlet_fit(y, lane, p);
             // mix phasors for the 32 radix-1 positions: rho[n1] = exp(-2 pi i (k+d) n1 / 32)
             const int e = (kpeak * lane) & 31;
@@ -599,10 +704,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
             turns += 0.5f * (float)(kpeak & 1) + 0.5f * delta;
             ph0[i] = cispi(2.f * turns);
         }
-        fwd_pass1([&](int n, int n1, int i) {
-            const float2 ph = cmul(ph0[i], rho[n1]);
-            return cmul(load_x(n), ph);
-        });
+        fwd_pass1(true, ph0);
         __syncthreads();
         fwd_pass2();
         if (R2 > 1) __syncthreads();
@@ -614,24 +716,39 @@ detect_kernel(const __grid_constant__ DetectParams p) {
 #pragma unroll
             for (int i = 0; i < I3; ++i) {
                 const int g = tid + T * i;
+                const uint32_t ab = a3_base(g);
+                float2 tv[R3];                                    // template spectrum, issued early
+#pragma unroll
+                for (int k3 = 0; k3 < R3; ++k3) tv[k3] = __ldg(&tsp[(size_t)(i * R3 + k3) * T + tid]);
                 float xr[R3], xi[R3];
                 if (tpl == 0) {
 #pragma unroll
                     for (int n3 = 0; n3 < R3; ++n3) {
-                        const float2 v = bld(g * R3 + n3);
+                        const float2 v = ld8(a3(ab, n3));
                         xr[n3] = v.x;
                         xi[n3] = v.y;
                     }
                     fft_dif<R3>(xr, xi);
-                    const int kb = (g >> LOG2R2) + 32 * (g & (R2 - 1));
 #pragma unroll
                     for (int k3 = 0; k3 < R3; ++k3) {
                         const int r = brev(k3, LOG2R3);
                         e2sum += xr[r] * xr[r] + xi[r] * xi[r];
-                        if (p.dbg_shifted_fft) p.dbg_shifted_fft[kb + S * k3] = make_float2(xr[r], xi[r]);
-                        if (p.n_templates > 1)
+                    }
+                    if (p.n_templates > 1) {
+#pragma unroll
+                        for (int k3 = 0; k3 < R3; ++k3) {
+                            const int r = brev(k3, LOG2R3);
                             p.xsave[(size_t)blockIdx.x * N + (size_t)(i * R3 + k3) * T + tid] =
                                 make_float2(xr[r], xi[r]);
+                        }
+                    }
+                    if (dbg && p.dbg_shifted_fft) {
+                        const int kb = (g >> LOG2R2) + 32 * (g & (R2 - 1));
+#pragma unroll
+                        for (int k3 = 0; k3 < R3; ++k3) {
+                            const int r = brev(k3, LOG2R3);
+                            p.dbg_shifted_fft[kb + S * k3] = make_float2(xr[r], xi[r]);
+                        }
                     }
                 } else {
 #pragma unroll
@@ -647,8 +764,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
 #pragma unroll
                 for (int k3 = 0; k3 < R3; ++k3) {
                     const int r = brev(k3, LOG2R3);
-                    const float2 t = __ldg(&tsp[(size_t)(i * R3 + k3) * T + tid]);
-                    const float2 v = cmul(make_float2(xr[r], xi[r]), t);
+                    const float2 v = cmul(make_float2(xr[r], xi[r]), tv[k3]);
                     yr[k3] = v.x;
                     yi[k3] = v.y;
                 }
@@ -656,7 +772,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
 #pragma unroll
                 for (int n3 = 0; n3 < R3; ++n3) {
                     const int r = brev(n3, LOG2R3);
-                    bst(g * R3 + n3, make_float2(yr[r], yi[r]));
+                    st8(a3(ab, n3), make_float2(yr[r], yi[r]));
                 }
             }
             __syncthreads();
@@ -666,11 +782,11 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 for (int i = 0; i < I2; ++i) {
                     const int w = tid + T * i;
                     const int k1 = w >> LOG2R3, n3 = w & (R3 - 1);
-                    const int base = k1 * M + n3;
+                    const uint32_t ab = a2_base(k1, n3);
                     float xr[R2], xi[R2];
 #pragma unroll
                     for (int k2 = 0; k2 < R2; ++k2) {
-                        float2 v = bld(base + k2 * R3);
+                        float2 v = ld8(a2(ab, k2));
                         if (k2 > 0) v = cmulc(v, tw2[k2 * R3 + n3]);
                         xr[k2] = v.x;
                         xi[k2] = v.y;
@@ -679,7 +795,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
 #pragma unroll
                     for (int n2 = 0; n2 < R2; ++n2) {
                         const int r = brev(n2, LOG2R2);
-                        bst(base + n2 * R3, make_float2(xr[r], xi[r]));
+                        st8(a2(ab, n2), make_float2(xr[r], xi[r]));
                     }
                 }
                 __syncthreads();
@@ -687,11 +803,12 @@ detect_kernel(const __grid_constant__ DetectParams p) {
             // inverse pass 1': conj twiddle on load, radix-32 over k1 -> c[n1*M + j]
             float cp[I1][32];
             float c1sum = 0.f, c2sum = 0.f;
-            unsigned long long cbest = 0ull;
-            const bool need_std_k = (p.k_std != 0.f);
+            float cbestv = -1.f;
+            int cbestn = 0;
 #pragma unroll
             for (int i = 0; i < I1; ++i) {
                 const int j = tid + T * i;
+                const uint32_t ab = a1_base(j);
                 float xr[32], xi[32];
                 float2 cur[4];
                 cur[0] = w1[i];
@@ -699,40 +816,59 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 cur[2] = cmul(cur[1], w1[i]);
                 cur[3] = w4[i];
                 {
-                    const float2 v = bld(j);
+                    float2 v;
+                    if constexpr (FAST_ADDR) v = ld8(ab);
+                    else v = ld8(pos_generic(j));
                     xr[0] = v.x;
                     xi[0] = v.y;
                 }
 #pragma unroll
                 for (int k1 = 1; k1 < 32; ++k1) {
                     if (k1 > 4) cur[(k1 - 1) & 3] = cmul(cur[(k1 - 1) & 3], w4[i]);
-                    const float2 v = cmulc(bld(k1 * M + j), cur[(k1 - 1) & 3]);
+                    float2 v;
+                    if constexpr (FAST_ADDR) v = ld8(ab + (uint32_t)k1 * (M * 8u));
+                    else v = ld8(pos_generic(k1 * M + j));
+                    v = cmulc(v, cur[(k1 - 1) & 3]);
                     xr[k1] = v.x;
                     xi[k1] = v.y;
                 }
                 fft_dif<32>(xi, xr);
+                // |c|^2 and windowed arg-max over [corr_start, corr_stop) (soa_estimator.py:137-143);
+                // n = n1*M + j grows with n1, so '>' keeps the first maximum
+                const uint32_t wlen = (uint32_t)(p.corr_stop - p.corr_start);
+                const uint32_t jrel = (uint32_t)(j - p.corr_start);
 #pragma unroll
                 for (int n1 = 0; n1 < 32; ++n1) {
                     const int r = brev(n1, 5);
-                    const int n = n1 * M + j;
                     const float pv = xr[r] * xr[r] + xi[r] * xi[r];
                     cp[i][n1] = pv;
-                    if (n >= p.corr_start && n < p.corr_stop) {
-                        const unsigned long long c = pack_cand(pv, (uint32_t)n);
-                        cbest = c > cbest ? c : cbest;
+                    if (jrel + (uint32_t)(n1 * M) < wlen && pv > cbestv) {
+                        cbestv = pv;
+                        cbestn = n1 * M + j;
                     }
-                    if (need_std_k && n < p.corr_len) {
-                        c1sum += sqrtf(pv);
-                        c2sum += pv;
+                }
+                if (need_std_k) {
+#pragma unroll
+                    for (int n1 = 0; n1 < 32; ++n1) {
+                        if (n1 * M + j < p.corr_len) {
+                            c1sum += sqrtf(cp[i][n1]);
+                            c2sum += cp[i][n1];
+                        }
                     }
-                    if (p.dbg_corr && tpl == 0 && n < p.corr_len) p.dbg_corr[n] = make_float2(xr[r], xi[r]);
+                }
+                if (dbg && p.dbg_corr && tpl == 0) {
+#pragma unroll
+                    for (int n1 = 0; n1 < 32; ++n1) {
+                        const int r = brev(n1, 5);
+                        if (n1 * M + j < p.corr_len) p.dbg_corr[n1 * M + j] = make_float2(xr[r], xi[r]);
+                    }
                 }
             }
             // reduce: (energy of X' | sum|c|), sum|c|^2, arg-max
-            const RedOut rb = block_reduce<T>(need_std_k ? c1sum : e2sum, need_std_k ? c2sum : 0.f, cbest, red, tid);
+            const unsigned long long ccand = cbestv >= 0.f ? pack_cand(cbestv, (uint32_t)cbestn) : 0ull;
+            const RedOut rb = block_reduce<T>(need_std_k ? c1sum : e2sum, need_std_k ? c2sum : 0.f, ccand, red, tid);
             float e2tot;
             if (need_std_k) {
-                // need the X' energy as well: second (cheap) reduction
                 const RedOut rc = block_reduce<T>(e2sum, 0.f, 0ull, red, tid);
                 e2tot = rc.s0;
             } else {
@@ -758,44 +894,41 @@ detect_kernel(const __grid_constant__ DetectParams p) {
             }
             __syncthreads();
             if (tid == 0) {
-                // float64 scalar tail (soa_estimator.py:78-134,159-170)
-                const double peak_mag_k = sqrt((double)peak_cp);
-                const double sig_energy = (double)e2tot / (double)N;
-                const double noise_pw = (sig_energy * (double)p.tpl_energy[tpl] - (double)peak_cp) / (double)N;
-                const double noise_k = sqrt(noise_pw);                     // NaN if negative
-                double var_k = 0.0;
+                // scalar tail (soa_estimator.py:78-134,159-170); float32 except the SoA itself
+                const float peak_mag_k = sqrtf(peak_cp);
+                const float sig_energy = e2tot / (float)N;
+                const float noise_pw = (sig_energy * p.tpl_energy[tpl] - peak_cp) / (float)N;
+                const float noise_k = sqrtf(noise_pw);                     // NaN if negative
+                float var_k = 0.f;
                 if (need_std_k) {
-                    const double mean = (double)rb.s0 / (double)p.corr_len;
-                    var_k = (double)rb.s1 / (double)p.corr_len - mean * mean;
-                    if (var_k < 0.0) var_k = 0.0;
+                    const float mean = rb.s0 / (float)p.corr_len;
+                    var_k = fmaxf(rb.s1 / (float)p.corr_len - mean * mean, 0.f);
                 }
-                const double thr_k = sqrt((double)p.k_const + (double)p.k_snr * (noise_k * noise_k) +
-                                          (double)p.k_std * var_k);
+                const float thr_k = sqrtf(p.k_const + p.k_snr * (noise_k * noise_k) + p.k_std * var_k);
                 const bool detected = peak_mag_k > thr_k;
-                double offset = 0.0;
+                float offset = 0.f;
                 if (detected && s > 0 && s < p.corr_len - 1) {
-                    const double pa = (double)bc[16], pc = (double)bc[18], pb = (double)peak_cp;
-                    // a,b,c = ln|c|: offset = 0.5 (c-a) / (2b-a-c), on magnitudes = sqrt(power)
-                    const double num = 0.5 * log(pc / pa);
-                    const double den = 0.5 * log(pb * pb / (pa * pc));
-                    offset = 0.5 * num / den;
-                    if (!(offset == offset)) offset = __longlong_as_double(0x7ff8000000000000ll);
-                    offset = offset < -0.6 ? -0.6 : (offset > 0.6 ? 0.6 : offset);
+                    // a,b,c = ln|c|; offset = 0.5 (c-a) / (2b-a-c) with |c| = sqrt(power)
+                    const float pa = bc[16], pc = bc[18], pb = peak_cp;
+                    const float num = logf(pc / pa);
+                    const float den = logf((pb / pa) * (pb / pc));
+                    offset = 0.5f * num / den;
+                    offset = fminf(fmaxf(offset, -0.6f), 0.6f);
                 }
                 thr_record rec;
                 rec.block_idx = bidx;
-                rec.soa = (double)p.new_len * (double)bidx + (double)s + offset;
+                rec.soa = (double)p.new_len * (double)bidx + (double)s + (double)offset;
                 rec.carrier_bin = kpeak;
                 rec.carrier_offset = delta;
                 rec.carrier_energy = peak_mag;
                 rec.carrier_noise = noise_c;
                 rec.corr_sample = s;
-                rec.corr_offset = (float)offset;
-                rec.corr_energy = (float)peak_mag_k;
-                rec.corr_noise = (float)noise_k;
+                rec.corr_offset = offset;
+                rec.corr_energy = peak_mag_k;
+                rec.corr_noise = noise_k;
                 rec.flags = THR_FLAG_CARRIER_DETECTED | (detected ? THR_FLAG_CORR_DETECTED : 0u);
                 rec.template_idx = tpl;
-                rec.signal_energy = (float)sig_energy;
+                rec.signal_energy = sig_energy;
                 rec.reserved = 0.f;
                 p.out[(size_t)blk * p.n_templates + tpl] = rec;
             }
