@@ -78,11 +78,24 @@ struct Cfg {
 };
 
 // ------------------------------------------------------------------ small helpers
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+// Packed FP32x2 arithmetic (sm_100 FADD2 / FMUL2 / FFMA2): a complex number is one aligned
+// register pair; operand swizzles (LO_HI), per-half negation and scalar broadcast are folded
+// into the instruction by ptxas, so a complex add is 1 instruction and a complex multiply 2.
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 f2sub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ float2 rot_mj(float2 v) { return make_float2(v.y, -v.x); }   // v * (-i)
+__device__ __forceinline__ float2 rot_pj(float2 v) { return make_float2(-v.y, v.x); }   // v * (+i)
+__device__ __forceinline__ float2 f2scale(float2 v, float h) { return __fmul2_rn(v, make_float2(h, h)); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 w) {    // a * w
+    return __ffma2_rn(rot_pj(a), make_float2(w.y, w.y), __fmul2_rn(a, make_float2(w.x, w.x)));
 }
-__device__ __forceinline__ float2 cmulc(float2 a, float2 b) {   // a * conj(b)
-    return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+__device__ __forceinline__ float2 cmulc(float2 a, float2 w) {   // a * conj(w)
+    return __ffma2_rn(rot_mj(a), make_float2(w.y, w.y), __fmul2_rn(a, make_float2(w.x, w.x)));
+}
+// v * (c - i s) (forward twiddle) or v * (c + i s) (INV)
+template <bool INV>
+__device__ __forceinline__ float2 mul_tw(float2 v, float c, float s) {
+    return __ffma2_rn(INV ? rot_pj(v) : rot_mj(v), make_float2(s, s), __fmul2_rn(v, make_float2(c, c)));
 }
 // cis(pi * x): cos(pi x) + i sin(pi x), exact range reduction
 __device__ __forceinline__ float2 cispi(float x) {
@@ -142,11 +155,11 @@ __host__ __device__ __forceinline__ constexpr float sin32(int q) {
     }
 }
 
-// In-register radix-2 DIF FFT of size R (power of two <= 32), forward sign (e^{-i...}).
-// Output k is left at index brev(k).  Calling it as fft_dif(xi, xr) computes the inverse
-// (unnormalised) transform, by the swap identity idft(x) = swap(dft(swap(x))).
-template <int R>
-__device__ __forceinline__ void fft_dif(float (&xr)[R], float (&xi)[R]) {
+// In-register radix-2 DIF FFT of size R (power of two <= 32) on packed complex values.
+// INV = false: forward (e^{-i...}); INV = true: inverse (e^{+i...}, unnormalised).
+// Output k is left at index brev(k).
+template <int R, bool INV>
+__device__ __forceinline__ void fft_dif(float2 (&x)[R]) {
 #pragma unroll
     for (int len = R; len >= 2; len >>= 1) {
         const int half = len >> 1;
@@ -156,28 +169,19 @@ __device__ __forceinline__ void fft_dif(float (&xr)[R], float (&xi)[R]) {
             for (int i = 0; i < half; ++i) {
                 const int a = base + i, b = a + half;
                 const int q = i * (32 / len);            // twiddle W_len^i = W_32^q
-                const float ur = xr[a] + xr[b], ui = xi[a] + xi[b];
-                const float vr = xr[a] - xr[b], vi = xi[a] - xi[b];
-                xr[a] = ur;
-                xi[a] = ui;
+                const float2 u = f2add(x[a], x[b]);
+                const float2 v = f2sub(x[a], x[b]);
+                x[a] = u;
                 if (q == 0) {
-                    xr[b] = vr;
-                    xi[b] = vi;
-                } else if (q == 8) {                     // * (-i)
-                    xr[b] = vi;
-                    xi[b] = -vr;
-                } else if (q == 4) {                     // * (1 - i)/sqrt2
-                    const float h = 0.70710678118654752f;
-                    xr[b] = (vr + vi) * h;
-                    xi[b] = (vi - vr) * h;
-                } else if (q == 12) {                    // * (-1 - i)/sqrt2
-                    const float h = 0.70710678118654752f;
-                    xr[b] = (vi - vr) * h;
-                    xi[b] = -(vr + vi) * h;
+                    x[b] = v;
+                } else if (q == 8) {                     // * (-i)   [inverse: * (+i)]
+                    x[b] = INV ? rot_pj(v) : rot_mj(v);
+                } else if (q == 4) {                     // * (1 -+ i)/sqrt2
+                    x[b] = f2scale(f2add(v, INV ? rot_pj(v) : rot_mj(v)), 0.70710678118654752f);
+                } else if (q == 12) {                    // * (-1 -+ i)/sqrt2
+                    x[b] = f2scale(f2add(v, INV ? rot_mj(v) : rot_pj(v)), -0.70710678118654752f);
                 } else {
-                    const float c = cos32(q), s = sin32(q);   // W = c - i s
-                    xr[b] = vr * c + vi * s;
-                    xi[b] = vi * c - vr * s;
+                    x[b] = mul_tw<INV>(v, cos32(q), sin32(q));
                 }
             }
         }
@@ -481,44 +485,38 @@ detect_kernel(const __grid_constant__ DetectParams p) {
 #pragma unroll
             for (int i = 0; i < I1; ++i) {
                 const int j = tid + T * i;
-                float xr[32], xi[32];
+                float2 x[32];
                 if (use_raw) {
 #pragma unroll
                     for (int n1 = 0; n1 < 32; ++n1) {
-                        const float2 v = rawconv(rawt[n1 * M + j]);
-                        xr[n1] = v.x;
-                        xi[n1] = v.y;
+                        x[n1] = rawconv(rawt[n1 * M + j]);
                     }
                 } else {
 #pragma unroll
                     for (int n1 = 0; n1 < 32; ++n1) {
-                        const float2 v = __ldg(&iqb[n1 * M + j]);
-                        xr[n1] = v.x;
-                        xi[n1] = v.y;
+                        x[n1] = __ldg(&iqb[n1 * M + j]);
                     }
                 }
                 if (mix) {
 #pragma unroll
                     for (int n1 = 0; n1 < 32; ++n1) {
-                        const float2 v = cmul(make_float2(xr[n1], xi[n1]), cmul(ph0[i], rho[n1]));
-                        xr[n1] = v.x;
-                        xi[n1] = v.y;
+                        x[n1] = cmul(x[n1], cmul(ph0[i], rho[n1]));
                     }
                 }
-                fft_dif<32>(xr, xi);
+                fft_dif<32, false>(x);
                 float2 cur[4];
                 cur[0] = w1[i];
                 cur[1] = cmul(w1[i], w1[i]);
                 cur[2] = cmul(cur[1], w1[i]);
                 cur[3] = w4[i];
                 const uint32_t ab = a1_base(j);
-                if constexpr (FAST_ADDR) st8(ab, make_float2(xr[0], xi[0]));
-                else st8(pos_generic(j), make_float2(xr[0], xi[0]));
+                if constexpr (FAST_ADDR) st8(ab, x[0]);
+                else st8(pos_generic(j), x[0]);
 #pragma unroll
                 for (int k1 = 1; k1 < 32; ++k1) {
                     const int r = brev(k1, 5);
                     if (k1 > 4) cur[(k1 - 1) & 3] = cmul(cur[(k1 - 1) & 3], w4[i]);
-                    const float2 v = cmul(make_float2(xr[r], xi[r]), cur[(k1 - 1) & 3]);
+                    const float2 v = cmul(x[r], cur[(k1 - 1) & 3]);
                     if constexpr (FAST_ADDR) st8(ab + (uint32_t)k1 * (M * 8u), v);
                     else st8(pos_generic(k1 * M + j), v);
                 }
@@ -541,18 +539,16 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 const int w = tid + T * i;
                 const int k1 = w >> LOG2R3, n3 = w & (R3 - 1);
                 const uint32_t ab = a2_base(k1, n3);
-                float xr[R2], xi[R2];
+                float2 x[R2];
 #pragma unroll
                 for (int n2 = 0; n2 < R2; ++n2) {
-                    const float2 v = ld8(a2(ab, n2));
-                    xr[n2] = v.x;
-                    xi[n2] = v.y;
+                    x[n2] = ld8(a2(ab, n2));
                 }
-                fft_dif<R2>(xr, xi);
+                fft_dif<R2, false>(x);
 #pragma unroll
                 for (int k2 = 0; k2 < R2; ++k2) {
                     const int r = brev(k2, LOG2R2);
-                    float2 v = make_float2(xr[r], xi[r]);
+                    float2 v = x[r];
                     if (k2 > 0) v = cmul(v, tw2[k2 * R3 + n3]);
                     st8(a2(ab, k2), v);
                 }
@@ -586,19 +582,17 @@ detect_kernel(const __grid_constant__ DetectParams p) {
         for (int i = 0; i < I3; ++i) {
             const int g = tid + T * i;
             const uint32_t ab = a3_base(g);
-            float xr[R3], xi[R3];
+            float2 x[R3];
 #pragma unroll
             for (int n3 = 0; n3 < R3; ++n3) {
-                const float2 v = ld8(a3(ab, n3));
-                xr[n3] = v.x;
-                xi[n3] = v.y;
+                x[n3] = ld8(a3(ab, n3));
             }
-            fft_dif<R3>(xr, xi);
+            fft_dif<R3, false>(x);
             const int kb = (g >> LOG2R2) + 32 * (g & (R2 - 1));     // k1 + 32 k2
 #pragma unroll
             for (int k3 = 0; k3 < R3; ++k3) {
                 const int r = brev(k3, LOG2R3);
-                const float pv = xr[r] * xr[r] + xi[r] * xi[r];
+                const float pv = x[r].x * x[r].x + x[r].y * x[r].y;
                 pw[i][k3] = pv;
                 esum += pv;
             }
@@ -720,26 +714,24 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 float2 tv[R3];                                    // template spectrum, issued early
 #pragma unroll
                 for (int k3 = 0; k3 < R3; ++k3) tv[k3] = __ldg(&tsp[(size_t)(i * R3 + k3) * T + tid]);
-                float xr[R3], xi[R3];
+                float2 x[R3];
                 if (tpl == 0) {
 #pragma unroll
                     for (int n3 = 0; n3 < R3; ++n3) {
-                        const float2 v = ld8(a3(ab, n3));
-                        xr[n3] = v.x;
-                        xi[n3] = v.y;
+                        x[n3] = ld8(a3(ab, n3));
                     }
-                    fft_dif<R3>(xr, xi);
+                    fft_dif<R3, false>(x);
 #pragma unroll
                     for (int k3 = 0; k3 < R3; ++k3) {
                         const int r = brev(k3, LOG2R3);
-                        e2sum += xr[r] * xr[r] + xi[r] * xi[r];
+                        e2sum += x[r].x * x[r].x + x[r].y * x[r].y;
                     }
                     if (p.n_templates > 1) {
 #pragma unroll
                         for (int k3 = 0; k3 < R3; ++k3) {
                             const int r = brev(k3, LOG2R3);
                             p.xsave[(size_t)blockIdx.x * N + (size_t)(i * R3 + k3) * T + tid] =
-                                make_float2(xr[r], xi[r]);
+                                x[r];
                         }
                     }
                     if (dbg && p.dbg_shifted_fft) {
@@ -747,32 +739,28 @@ detect_kernel(const __grid_constant__ DetectParams p) {
 #pragma unroll
                         for (int k3 = 0; k3 < R3; ++k3) {
                             const int r = brev(k3, LOG2R3);
-                            p.dbg_shifted_fft[kb + S * k3] = make_float2(xr[r], xi[r]);
+                            p.dbg_shifted_fft[kb + S * k3] = x[r];
                         }
                     }
                 } else {
 #pragma unroll
                     for (int k3 = 0; k3 < R3; ++k3) {
                         const int r = brev(k3, LOG2R3);
-                        const float2 v = p.xsave[(size_t)blockIdx.x * N + (size_t)(i * R3 + k3) * T + tid];
-                        xr[r] = v.x;
-                        xi[r] = v.y;
+                        x[r] = p.xsave[(size_t)blockIdx.x * N + (size_t)(i * R3 + k3) * T + tid];
                     }
                 }
                 // multiply by conj(T)/N (soa_estimator.py:99) and run the inverse radix-R3 DFT
-                float yr[R3], yi[R3];
+                float2 y[R3];
 #pragma unroll
                 for (int k3 = 0; k3 < R3; ++k3) {
                     const int r = brev(k3, LOG2R3);
-                    const float2 v = cmul(make_float2(xr[r], xi[r]), tv[k3]);
-                    yr[k3] = v.x;
-                    yi[k3] = v.y;
+                    y[k3] = cmul(x[r], tv[k3]);
                 }
-                fft_dif<R3>(yi, yr);          // inverse: swapped roles
+                fft_dif<R3, true>(y);
 #pragma unroll
                 for (int n3 = 0; n3 < R3; ++n3) {
                     const int r = brev(n3, LOG2R3);
-                    st8(a3(ab, n3), make_float2(yr[r], yi[r]));
+                    st8(a3(ab, n3), y[r]);
                 }
             }
             __syncthreads();
@@ -783,19 +771,18 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                     const int w = tid + T * i;
                     const int k1 = w >> LOG2R3, n3 = w & (R3 - 1);
                     const uint32_t ab = a2_base(k1, n3);
-                    float xr[R2], xi[R2];
+                    float2 x[R2];
 #pragma unroll
                     for (int k2 = 0; k2 < R2; ++k2) {
                         float2 v = ld8(a2(ab, k2));
                         if (k2 > 0) v = cmulc(v, tw2[k2 * R3 + n3]);
-                        xr[k2] = v.x;
-                        xi[k2] = v.y;
+                        x[k2] = v;
                     }
-                    fft_dif<R2>(xi, xr);
+                    fft_dif<R2, true>(x);
 #pragma unroll
                     for (int n2 = 0; n2 < R2; ++n2) {
                         const int r = brev(n2, LOG2R2);
-                        st8(a2(ab, n2), make_float2(xr[r], xi[r]));
+                        st8(a2(ab, n2), x[r]);
                     }
                 }
                 __syncthreads();
@@ -809,7 +796,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
             for (int i = 0; i < I1; ++i) {
                 const int j = tid + T * i;
                 const uint32_t ab = a1_base(j);
-                float xr[32], xi[32];
+                float2 x[32];
                 float2 cur[4];
                 cur[0] = w1[i];
                 cur[1] = cmul(w1[i], w1[i]);
@@ -819,8 +806,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                     float2 v;
                     if constexpr (FAST_ADDR) v = ld8(ab);
                     else v = ld8(pos_generic(j));
-                    xr[0] = v.x;
-                    xi[0] = v.y;
+                    x[0] = v;
                 }
 #pragma unroll
                 for (int k1 = 1; k1 < 32; ++k1) {
@@ -829,10 +815,9 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                     if constexpr (FAST_ADDR) v = ld8(ab + (uint32_t)k1 * (M * 8u));
                     else v = ld8(pos_generic(k1 * M + j));
                     v = cmulc(v, cur[(k1 - 1) & 3]);
-                    xr[k1] = v.x;
-                    xi[k1] = v.y;
+                    x[k1] = v;
                 }
-                fft_dif<32>(xi, xr);
+                fft_dif<32, true>(x);
                 // |c|^2 and windowed arg-max over [corr_start, corr_stop) (soa_estimator.py:137-143);
                 // n = n1*M + j grows with n1, so '>' keeps the first maximum
                 const uint32_t wlen = (uint32_t)(p.corr_stop - p.corr_start);
@@ -840,7 +825,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
 #pragma unroll
                 for (int n1 = 0; n1 < 32; ++n1) {
                     const int r = brev(n1, 5);
-                    const float pv = xr[r] * xr[r] + xi[r] * xi[r];
+                    const float pv = x[r].x * x[r].x + x[r].y * x[r].y;
                     cp[i][n1] = pv;
                     if (jrel + (uint32_t)(n1 * M) < wlen && pv > cbestv) {
                         cbestv = pv;
@@ -860,7 +845,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
 #pragma unroll
                     for (int n1 = 0; n1 < 32; ++n1) {
                         const int r = brev(n1, 5);
-                        if (n1 * M + j < p.corr_len) p.dbg_corr[n1 * M + j] = make_float2(xr[r], xi[r]);
+                        if (n1 * M + j < p.corr_len) p.dbg_corr[n1 * M + j] = x[r];
                     }
                 }
             }
