@@ -504,18 +504,23 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                     }
                 }
                 fft_dif<32, false>(x);
+                // Twiddles W_N^{j k1} are regenerated per block from two per-thread seeds.  The opaque
+                // asm keeps the compiler from hoisting all 31 powers out of the block loop, which
+                // would turn them into a 124 KB per-CTA local-memory table (L2 traffic + latency).
+                float2 ws = w1[i], ws4 = w4[i];
+                asm volatile("" : "+f"(ws.x), "+f"(ws.y), "+f"(ws4.x), "+f"(ws4.y));
                 float2 cur[4];
-                cur[0] = w1[i];
-                cur[1] = cmul(w1[i], w1[i]);
-                cur[2] = cmul(cur[1], w1[i]);
-                cur[3] = w4[i];
+                cur[0] = ws;
+                cur[1] = cmul(ws, ws);
+                cur[2] = cmul(cur[1], ws);
+                cur[3] = ws4;
                 const uint32_t ab = a1_base(j);
                 if constexpr (FAST_ADDR) st8(ab, x[0]);
                 else st8(pos_generic(j), x[0]);
 #pragma unroll
                 for (int k1 = 1; k1 < 32; ++k1) {
                     const int r = brev(k1, 5);
-                    if (k1 > 4) cur[(k1 - 1) & 3] = cmul(cur[(k1 - 1) & 3], w4[i]);
+                    if (k1 > 4) cur[(k1 - 1) & 3] = cmul(cur[(k1 - 1) & 3], ws4);
                     const float2 v = cmul(x[r], cur[(k1 - 1) & 3]);
                     if constexpr (FAST_ADDR) st8(ab + (uint32_t)k1 * (M * 8u), v);
                     else st8(pos_generic(k1 * M + j), v);
@@ -797,11 +802,13 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 const int j = tid + T * i;
                 const uint32_t ab = a1_base(j);
                 float2 x[32];
+                float2 ws = w1[i], ws4 = w4[i];
+                asm volatile("" : "+f"(ws.x), "+f"(ws.y), "+f"(ws4.x), "+f"(ws4.y));
                 float2 cur[4];
-                cur[0] = w1[i];
-                cur[1] = cmul(w1[i], w1[i]);
-                cur[2] = cmul(cur[1], w1[i]);
-                cur[3] = w4[i];
+                cur[0] = ws;
+                cur[1] = cmul(ws, ws);
+                cur[2] = cmul(cur[1], ws);
+                cur[3] = ws4;
                 {
                     float2 v;
                     if constexpr (FAST_ADDR) v = ld8(ab);
@@ -810,7 +817,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 }
 #pragma unroll
                 for (int k1 = 1; k1 < 32; ++k1) {
-                    if (k1 > 4) cur[(k1 - 1) & 3] = cmul(cur[(k1 - 1) & 3], w4[i]);
+                    if (k1 > 4) cur[(k1 - 1) & 3] = cmul(cur[(k1 - 1) & 3], ws4);
                     float2 v;
                     if constexpr (FAST_ADDR) v = ld8(ab + (uint32_t)k1 * (M * 8u));
                     else v = ld8(pos_generic(k1 * M + j));
