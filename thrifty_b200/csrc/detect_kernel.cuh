@@ -72,8 +72,16 @@ struct Cfg {
     __device__ __forceinline__ static int pos(int e) {
         return GMEM_ ? e : (e ^ ((e >> 4) & 15));
     }
-    static constexpr size_t smem_bytes() {
-        return (GMEM_ ? 0 : (size_t)N * 8) + 2 * (size_t)(2 * N) + (size_t)M * 8 + 32 * 8 + 1024 + 64;
+    // T == 512 (one CTA per SM): a dedicated service warpgroup runs the serial fit / tail while the
+    // workers go on with the next block; registers are re-split with setmaxnreg (workers 112,
+    // service 32).  Smaller T: several CTAs per SM hide the serial parts, warp 0 runs them inline.
+    static constexpr bool SERVICE = (T >= 512);
+    static constexpr int LAUNCH_THREADS = SERVICE ? T + 128 : T;
+    static constexpr int MIN_CTAS = T >= 512 ? 1 : (T >= 256 ? 2 : (T >= 128 ? 4 : 8));
+    static constexpr int MAX_TPL = 32;               // templates per detector (tail mailbox size)
+    static constexpr size_t smem_bytes() {           // must cover the carve-up in detect_kernel
+        return (GMEM_ ? 0 : (size_t)N * 8) + 2 * (size_t)(2 * N) + (size_t)M * 8
+               + 2 * 320 + 2 * 32 + 2 * MAX_TPL * 32 + 256 + 64;
     }
 };
 
@@ -379,21 +387,100 @@ __device__ __forceinline__ float2 rawconv(uint32_t w16) {
     return make_float2(fmaf(fx, 0.0078125f, c), fmaf(fy, 0.0078125f, c));
 }
 
+// ------------------------------------------------------------------ named barriers
+// The CTA has T "main" threads (the FFT workers) and one extra "service" warp.  Main threads
+// synchronise among themselves on barrier BAR_MAIN; requests to / completions from the
+// service warp use arrive/sync pairs on per-parity barrier ids, so neither side can run two
+// generations ahead on the same id.
+enum : int { BAR_FITREQ = 1, BAR_FITDONE = 3, BAR_TAILREQ = 5, BAR_MAIN = 7 };
+__device__ __forceinline__ void bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(int id, int count) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+// per-parity mailbox between the main threads and the service warp
+struct FitSlot {            // written by main after FFT#1 (A stage), completed by the service warp
+    float mags[8];          // 7 magnitudes around the carrier peak
+    int   kpeak;
+    int   carrier;          // carrier detected?
+    float peak_mag, noise_c, sig_energy1;
+    float delta;            // <- service warp
+    float pad[2];
+    float2 rho[32];         // <- service warp: exp(-2 pi i (k+delta) n1 / 32)
+};
+struct TailSlot {           // written by main at the end of the correlation stage
+    float peak_cp;          // |c|^2 at the peak
+    int   s;                // peak lag
+    float e2tot;            // sum |X'|^2
+    float pa, pc;           // |c|^2 at s-1, s+1
+    float c1, c2;           // sum |c|, sum |c|^2 over [0, corr_len) (stddev threshold term only)
+    float pad;
+};
+struct TailHdr {            // carrier fields copied for the record
+    int   kpeak, carrier;
+    float peak_mag, noise_c, sig_energy1, delta;
+    float pad[2];
+};
+
+static_assert(sizeof(FitSlot) == 320 && sizeof(TailSlot) == 32 && sizeof(TailHdr) == 32, "mailbox layout");
+
+template <int T>
+struct MainReduce {
+    // block-wide reduction over the T main threads only (two BAR_MAIN syncs)
+    __device__ __forceinline__ static RedOut run(float s0, float s1, unsigned long long best, uint32_t *red,
+                                                 int tid) {
+        constexpr int NW = T / 32;
+        s0 = warp_sum(s0);
+        s1 = warp_sum(s1);
+        best = warp_max_u64(best);
+        const int w = tid >> 5;
+        if ((tid & 31) == 0) {
+            red[w * 4 + 0] = __float_as_uint(s0);
+            red[w * 4 + 1] = __float_as_uint(s1);
+            red[w * 4 + 2] = (uint32_t)(best >> 32);
+            red[w * 4 + 3] = (uint32_t)best;
+        }
+        bar_sync(BAR_MAIN, T);
+        RedOut r;
+        r.s0 = 0.f;
+        r.s1 = 0.f;
+        r.best = 0ull;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+            r.s0 += __uint_as_float(red[i * 4 + 0]);
+            r.s1 += __uint_as_float(red[i * 4 + 1]);
+            unsigned long long b = ((unsigned long long)red[i * 4 + 2] << 32) | red[i * 4 + 3];
+            r.best = b > r.best ? b : r.best;
+        }
+        bar_sync(BAR_MAIN, T);
+        return r;
+    }
+};
+
 // ------------------------------------------------------------------ the kernel
+// Launched with T + 32 threads: warps 0..T/32-1 are the FFT workers, the last warp is the
+// service warp (Dirichlet fit + mix phasor table, scalar tail + record store).  Software
+// pipeline per CTA:   A(b+1) || fit(b)   ->   B(b) || tail(b-1)
+//   A(b): raw tile -> FFT#1 -> |X|^2, arg-max, carrier decision, 7 magnitudes posted
+//   B(b): mix + FFT#2 -> x conj(T)/N -> IFFT -> |c|^2 arg-max, neighbours posted
 template <int LOG2N, int T, bool GMEM>
-__global__ void __launch_bounds__(T, (T >= 512 ? 1 : (T >= 256 ? 2 : (T >= 128 ? 4 : 8))))
+__global__ void __launch_bounds__(Cfg<LOG2N, T, GMEM>::LAUNCH_THREADS, Cfg<LOG2N, T, GMEM>::MIN_CTAS)
 detect_kernel(const __grid_constant__ DetectParams p) {
     using C = Cfg<LOG2N, T, GMEM>;
+    constexpr bool SERVICE = C::SERVICE;
     constexpr int N = C::N, M = C::M, R2 = C::R2, R3 = C::R3, S = C::S;
     constexpr int I1 = C::I1, I2 = C::I2, I3 = C::I3;
     constexpr int LOG2M = ilog2(M), LOG2R3 = ilog2(R3), LOG2R2 = ilog2(R2), LOG2S = ilog2(S);
     constexpr uint32_t RAW_BYTES = 2u * N;
+    constexpr int NTHREADS = T + 32;     // participants of the worker<->service barriers
 
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
 
-    // ---- shared memory carve-up
+    // ---- shared memory carve-up (Cfg::smem_bytes() must cover it)
     size_t off = 0;
     unsigned char *bufc;                 // FFT buffer, byte-addressed
     if (GMEM) {
@@ -406,13 +493,134 @@ detect_kernel(const __grid_constant__ DetectParams p) {
     off += 2 * (size_t)RAW_BYTES;
     float2 *tw2 = reinterpret_cast<float2 *>(smem + off);
     off += (size_t)M * 8;
-    float2 *rho = reinterpret_cast<float2 *>(smem + off);
-    off += 32 * 8;
-    uint32_t *red = reinterpret_cast<uint32_t *>(smem + off);   // 64 words reduction scratch
-    float *bc = reinterpret_cast<float *>(smem + off + 256);    // broadcast scratch (64 floats)
-    off += 1024;
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + off);  // 2 barriers
+    FitSlot *fitslot = reinterpret_cast<FitSlot *>(smem + off);      // [2]
+    off += 2 * sizeof(FitSlot);
+    TailHdr *tailhdr = reinterpret_cast<TailHdr *>(smem + off);      // [2]
+    off += 2 * sizeof(TailHdr);
+    TailSlot *tailslot = reinterpret_cast<TailSlot *>(smem + off);   // [2][MAX_TPL]
+    off += 2 * (size_t)C::MAX_TPL * sizeof(TailSlot);
+    uint32_t *red = reinterpret_cast<uint32_t *>(smem + off);        // 64 words reduction scratch
+    off += 256;
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + off);       // 2 barriers
 
+    const bool use_raw = (p.raw != nullptr);
+    const bool dbg = (p.dbg_fft_mag != nullptr) || (p.dbg_shifted_fft != nullptr) || (p.dbg_corr != nullptr);
+    const bool need_std_c = (p.c_std != 0.f);
+    const bool need_std_k = (p.k_std != 0.f);
+    // blocks of this CTA: blockIdx.x + i * gridDim.x, i in [0, nb)
+    const int nb = ((int)blockIdx.x < p.n_blocks) ? (p.n_blocks - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        mbar_fence_init();
+    }
+    // inter-pass twiddle table W_M^{n3 k2} (all threads help)
+    for (int idx = tid; idx < M; idx += C::LAUNCH_THREADS) {
+        const int k2 = idx >> LOG2R3, n3 = idx & (R3 - 1);
+        const int e = (n3 * k2) & (M - 1);
+        tw2[idx] = cispi(-2.0f * (float)e / (float)M);
+    }
+    __syncthreads();
+
+    // =====================================================================================
+    // serial work: Dirichlet fit + mix phasor table, scalar tail + record store.  Executed by
+    // the service warp (SERVICE) or inline by warp 0 of the workers.
+    // =====================================================================================
+    auto do_fit = [&](int q) {
+        FitSlot &fs = fitslot[q];
+        if (fs.carrier) {
+            const float y = (lane & 7) < 7 ? fs.mags[lane & 7] : 0.f;
+            const float d = dirichlet_fit(y, lane, p);
+            // mix phasors of the 32 pass-1 rows: rho[n1] = exp(-2 pi i (k+d) n1 / 32)
+            const int e = (fs.kpeak * lane) & 31;
+            const float turns = -((float)e * 0.03125f) - d * ((float)lane * 0.03125f);
+            fs.rho[lane] = cispi(2.f * turns);
+            if (lane == 0) fs.delta = d;
+        }
+    };
+    auto do_tail = [&](int i, int q) {
+        const TailHdr &h = tailhdr[q];
+        const int blk = (int)blockIdx.x + i * (int)gridDim.x;
+        if (lane < p.n_templates) {
+            const int tpl = lane;
+            const int64_t bidx = p.block_idx ? p.block_idx[blk] : (int64_t)blk;
+            thr_record rec;
+            rec.block_idx = bidx;
+            rec.carrier_bin = h.kpeak;
+            rec.carrier_energy = h.peak_mag;
+            rec.carrier_noise = h.noise_c;
+            rec.template_idx = tpl;
+            rec.reserved = 0.f;
+            if (!h.carrier) {
+                rec.soa = __longlong_as_double(0x7ff8000000000000ll);
+                rec.carrier_offset = 0.f;
+                rec.corr_sample = -1;
+                rec.corr_offset = __int_as_float(0x7fc00000);
+                rec.corr_energy = __int_as_float(0x7fc00000);
+                rec.corr_noise = __int_as_float(0x7fc00000);
+                rec.flags = 0u;
+                rec.signal_energy = h.sig_energy1;
+            } else {
+                // scalar tail (soa_estimator.py:78-134,159-170); float32 except the SoA itself
+                const TailSlot &ts = tailslot[q * C::MAX_TPL + tpl];
+                const float peak_mag_k = sqrtf(ts.peak_cp);
+                const float sig_energy = ts.e2tot / (float)N;
+                const float noise_pw = (sig_energy * p.tpl_energy[tpl] - ts.peak_cp) / (float)N;
+                const float noise_k = sqrtf(noise_pw);                 // NaN if negative
+                float var_k = 0.f;
+                if (need_std_k) {
+                    const float mean = ts.c1 / (float)p.corr_len;
+                    var_k = fmaxf(ts.c2 / (float)p.corr_len - mean * mean, 0.f);
+                }
+                const float thr_k = sqrtf(p.k_const + p.k_snr * (noise_k * noise_k) + p.k_std * var_k);
+                const bool detected = peak_mag_k > thr_k;
+                float offset = 0.f;
+                if (detected && ts.s > 0 && ts.s < p.corr_len - 1) {
+                    // a,b,c = ln|c|; offset = 0.5 (c-a) / (2b-a-c) with |c| = sqrt(power)
+                    const float num = logf(ts.pc / ts.pa);
+                    const float den = logf((ts.peak_cp / ts.pa) * (ts.peak_cp / ts.pc));
+                    offset = fminf(fmaxf(0.5f * num / den, -0.6f), 0.6f);
+                }
+                rec.soa = (double)p.new_len * (double)bidx + (double)ts.s + (double)offset;
+                rec.carrier_offset = h.delta;
+                rec.corr_sample = ts.s;
+                rec.corr_offset = offset;
+                rec.corr_energy = peak_mag_k;
+                rec.corr_noise = noise_k;
+                rec.flags = THR_FLAG_CARRIER_DETECTED | (detected ? THR_FLAG_CORR_DETECTED : 0u);
+                rec.signal_energy = sig_energy;
+            }
+            p.out[(size_t)blk * p.n_templates + tpl] = rec;
+        }
+    };
+
+    if constexpr (SERVICE) {
+        if (tid >= T) {
+            // service warpgroup: hand registers to the workers; only its first warp works
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+            if (tid >= T + 32) return;
+            for (int i = -1; i < nb; ++i) {
+                if (i + 1 < nb) {
+                    const int q = (i + 1) & 1;
+                    bar_sync(BAR_FITREQ + q, NTHREADS);               // A(i+1) posted
+                    do_fit(q);
+                    bar_arrive(BAR_FITDONE + q, NTHREADS);
+                }
+                if (i >= 0) {
+                    const int q = i & 1;
+                    bar_sync(BAR_TAILREQ + q, NTHREADS);              // B(i) (or the no-carrier shortcut) posted
+                    do_tail(i, q);
+                }
+            }
+            return;
+        }
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    }
+
+    // =====================================================================================
+    // main (FFT worker) threads
+    // =====================================================================================
     // FFT buffer access.  Shared memory: element e lives at e ^ ((e >> 4) & 15) (8-byte units),
     // which every pass below expresses as (per-item byte address) XOR (compile-time constant)
     // plus a compile-time offset.  Global scratch (GMEM): plain layout, L2-only accesses.
@@ -424,19 +632,30 @@ detect_kernel(const __grid_constant__ DetectParams p) {
         if constexpr (GMEM) __stcg(reinterpret_cast<float2 *>(bufc + byte_off), v);
         else *reinterpret_cast<float2 *>(bufc + byte_off) = v;
     };
-    // pass-1 item j, element k1 (logical e = k1*M + j)
+    // pass-1 item j, element k1 (logical e = k1*M + j): base + k1*M*8 when M is a multiple of 256
+    // (the swizzle then only depends on j); smaller sizes recompute it from the logical index
     auto a1_base = [&](int j) -> uint32_t { return GMEM ? (uint32_t)j * 8u : (uint32_t)(j ^ ((j >> 4) & 15)) * 8u; };
-    // element k1 of a pass-1 item sits at base + k1*M*8 when M is a multiple of 256 (the swizzle
-    // then only depends on j); smaller sizes recompute the swizzle from the logical index
     auto pos_generic = [&](int e) -> uint32_t { return (uint32_t)C::pos(e) * 8u; };
     constexpr bool FAST_ADDR = GMEM || (M % 256 == 0);
+    // pass-2 addressing: item (k1, n3), element n2 (logical e = k1*M + n2*R3 + n3)
+    auto a2_base = [&](int k1, int n3) -> uint32_t {
+        if constexpr (GMEM) return (uint32_t)(k1 * M + n3) * 8u;
+        else return (uint32_t)(k1 * M) * 8u + (((uint32_t)n3 ^ (((uint32_t)k1 * R2) & 15u)) * 8u);
+    };
+    auto a2 = [&](uint32_t base, int n2) -> uint32_t {
+        if constexpr (GMEM) return base + (uint32_t)n2 * (R3 * 8u);
+        else return (base ^ (((uint32_t)n2 & 15u) * 8u)) + (uint32_t)n2 * (R3 * 8u);
+    };
+    // pass-3 addressing: item g, element n3 (logical e = g*R3 + n3)
+    auto a3_base = [&](int g) -> uint32_t {
+        if constexpr (GMEM) return (uint32_t)g * (R3 * 8u);
+        else return (uint32_t)g * (R3 * 8u) + ((uint32_t)g & 15u) * 8u;
+    };
+    auto a3 = [&](uint32_t base, int n3) -> uint32_t {
+        if constexpr (GMEM) return base + (uint32_t)n3 * 8u;
+        else return base ^ ((uint32_t)n3 * 8u);
+    };
 
-    // ---- one-time per-CTA setup: twiddles
-    for (int idx = tid; idx < M; idx += T) {
-        const int k2 = idx >> LOG2R3, n3 = idx & (R3 - 1);
-        const int e = (n3 * k2) & (M - 1);
-        tw2[idx] = cispi(-2.0f * (float)e / (float)M);          // W_M^{n3 k2}
-    }
     float2 w1[I1], w4[I1];                                      // W_N^j and W_N^{4j}
 #pragma unroll
     for (int i = 0; i < I1; ++i) {
@@ -444,111 +663,76 @@ detect_kernel(const __grid_constant__ DetectParams p) {
         w1[i] = cispi(-2.0f * (float)j / (float)N);
         w4[i] = cispi(-2.0f * (float)((4 * j) & (N - 1)) / (float)N);
     }
-    const bool use_raw = (p.raw != nullptr);
-    const bool dbg = (p.dbg_fft_mag != nullptr) || (p.dbg_shifted_fft != nullptr) || (p.dbg_corr != nullptr);
-    const bool need_std_c = (p.c_std != 0.f);
-    const bool need_std_k = (p.k_std != 0.f);
-    if (tid == 0) {
-        mbar_init(&mbar[0], 1);
-        mbar_init(&mbar[1], 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
 
+    auto issue_tile = [&](int i) {      // thread 0: TMA bulk copy of block i's raw tile into stage i&1
+        const int blk = (int)blockIdx.x + i * (int)gridDim.x;
+        mbar_expect_tx(&mbar[i & 1], RAW_BYTES);
+        tma_bulk_g2s(raw_s + (size_t)(i & 1) * RAW_BYTES, p.raw + (size_t)blk * RAW_BYTES, RAW_BYTES, &mbar[i & 1]);
+    };
+    if (use_raw && tid == 0) {
+        if (nb > 0) issue_tile(0);
+        if (nb > 1) issue_tile(1);
+    }
     uint32_t par0 = 0, par1 = 0;    // phase parity of the two tile barriers
-    int stage = 0;
-    if (use_raw && tid == 0 && (int)blockIdx.x < p.n_blocks) {
-        mbar_expect_tx(&mbar[0], RAW_BYTES);
-        tma_bulk_g2s(raw_s, p.raw + (size_t)blockIdx.x * RAW_BYTES, RAW_BYTES, &mbar[0]);
-    }
 
-    for (int blk = blockIdx.x; blk < p.n_blocks; blk += gridDim.x) {
-        // ---- prefetch the next block's raw tile into the other stage, wait for ours
-        const uint16_t *rawt = reinterpret_cast<const uint16_t *>(raw_s + (size_t)stage * RAW_BYTES);
-        if (use_raw) {
-            const int nxt = blk + gridDim.x;
-            if (tid == 0 && nxt < p.n_blocks) {
-                mbar_expect_tx(&mbar[stage ^ 1], RAW_BYTES);
-                tma_bulk_g2s(raw_s + (size_t)(stage ^ 1) * RAW_BYTES, p.raw + (size_t)nxt * RAW_BYTES,
-                             RAW_BYTES, &mbar[stage ^ 1]);
-            }
-            mbar_wait(&mbar[stage], stage ? par1 : par0);
-            if (stage) par1 ^= 1; else par0 ^= 1;
-        }
-        const float2 *iqb = use_raw ? nullptr : p.iq + (size_t)blk * N;
-        const int64_t bidx = p.block_idx ? p.block_idx[blk] : (int64_t)blk;
-
-        // ================= forward FFT passes (shared by FFT#1 and FFT#2) =================
+    // forward passes 1 and 2 of block i (shared by FFT#1 and FFT#2)
+    auto fwd_pass12 = [&](int i, bool mix, const float2 (&ph0)[I1], const float2 *rho) {
+        const uint16_t *rawt = reinterpret_cast<const uint16_t *>(raw_s + (size_t)(i & 1) * RAW_BYTES);
+        const float2 *iqb = use_raw ? nullptr : p.iq + (size_t)((int)blockIdx.x + i * (int)gridDim.x) * N;
         // pass 1: samples (rawconv or complex64) [* mix phasor] -> radix-32 over n1 (stride M)
         //         -> twiddle W_N^{j k1} -> in-place store
-        auto fwd_pass1 = [&](bool mix, const float2 (&ph0)[I1]) {
 #pragma unroll
-            for (int i = 0; i < I1; ++i) {
-                const int j = tid + T * i;
-                float2 x[32];
-                if (use_raw) {
+        for (int it = 0; it < I1; ++it) {
+            const int j = tid + T * it;
+            float2 x[32];
+            if (use_raw) {
 #pragma unroll
-                    for (int n1 = 0; n1 < 32; ++n1) {
-                        x[n1] = rawconv(rawt[n1 * M + j]);
-                    }
-                } else {
+                for (int n1 = 0; n1 < 32; ++n1) x[n1] = rawconv(rawt[n1 * M + j]);
+            } else {
 #pragma unroll
-                    for (int n1 = 0; n1 < 32; ++n1) {
-                        x[n1] = __ldg(&iqb[n1 * M + j]);
-                    }
-                }
-                if (mix) {
-#pragma unroll
-                    for (int n1 = 0; n1 < 32; ++n1) {
-                        x[n1] = cmul(x[n1], cmul(ph0[i], rho[n1]));
-                    }
-                }
-                fft_dif<32, false>(x);
-                // Twiddles W_N^{j k1} are regenerated per block from two per-thread seeds.  The opaque
-                // asm keeps the compiler from hoisting all 31 powers out of the block loop, which
-                // would turn them into a 124 KB per-CTA local-memory table (L2 traffic + latency).
-                float2 ws = w1[i], ws4 = w4[i];
-                asm volatile("" : "+f"(ws.x), "+f"(ws.y), "+f"(ws4.x), "+f"(ws4.y));
-                float2 cur[4];
-                cur[0] = ws;
-                cur[1] = cmul(ws, ws);
-                cur[2] = cmul(cur[1], ws);
-                cur[3] = ws4;
-                const uint32_t ab = a1_base(j);
-                if constexpr (FAST_ADDR) st8(ab, x[0]);
-                else st8(pos_generic(j), x[0]);
-#pragma unroll
-                for (int k1 = 1; k1 < 32; ++k1) {
-                    const int r = brev(k1, 5);
-                    if (k1 > 4) cur[(k1 - 1) & 3] = cmul(cur[(k1 - 1) & 3], ws4);
-                    const float2 v = cmul(x[r], cur[(k1 - 1) & 3]);
-                    if constexpr (FAST_ADDR) st8(ab + (uint32_t)k1 * (M * 8u), v);
-                    else st8(pos_generic(k1 * M + j), v);
-                }
+                for (int n1 = 0; n1 < 32; ++n1) x[n1] = __ldg(&iqb[n1 * M + j]);
             }
-        };
-        // pass-2 addressing: item (k1, n3), element n2 (logical e = k1*M + n2*R3 + n3)
-        auto a2_base = [&](int k1, int n3) -> uint32_t {
-            if constexpr (GMEM) return (uint32_t)(k1 * M + n3) * 8u;
-            else return (uint32_t)(k1 * M) * 8u + (((uint32_t)n3 ^ (((uint32_t)k1 * R2) & 15u)) * 8u);
-        };
-        auto a2 = [&](uint32_t base, int n2) -> uint32_t {
-            if constexpr (GMEM) return base + (uint32_t)n2 * (R3 * 8u);
-            else return (base ^ (((uint32_t)n2 & 15u) * 8u)) + (uint32_t)n2 * (R3 * 8u);
-        };
-        // pass 2: radix-R2 over n2 (stride R3) inside each k1 slab, twiddle W_M^{n3 k2}
-        auto fwd_pass2 = [&]() {
-            if (R2 == 1) return;
+            if (mix) {
 #pragma unroll
-            for (int i = 0; i < I2; ++i) {
-                const int w = tid + T * i;
+                for (int n1 = 0; n1 < 32; ++n1) x[n1] = cmul(x[n1], cmul(ph0[it], rho[n1]));
+            }
+            fft_dif<32, false>(x);
+            // Twiddles W_N^{j k1} are regenerated per block from two per-thread seeds.  The opaque
+            // asm keeps the compiler from hoisting all 31 powers out of the block loop, which
+            // would turn them into a 124 KB per-CTA local-memory table (L2 traffic + latency).
+            float2 ws = w1[it], ws4 = w4[it];
+            asm volatile("" : "+f"(ws.x), "+f"(ws.y), "+f"(ws4.x), "+f"(ws4.y));
+            float2 cur[4];
+            cur[0] = ws;
+            cur[1] = cmul(ws, ws);
+            cur[2] = cmul(cur[1], ws);
+            cur[3] = ws4;
+            const uint32_t ab = a1_base(j);
+            if constexpr (FAST_ADDR) st8(ab, x[0]);
+            else st8(pos_generic(j), x[0]);
+#pragma unroll
+            for (int k1 = 1; k1 < 32; ++k1) {
+                const int r = brev(k1, 5);
+                if (k1 > 4) cur[(k1 - 1) & 3] = cmul(cur[(k1 - 1) & 3], ws4);
+                const float2 v = cmul(x[r], cur[(k1 - 1) & 3]);
+                if constexpr (FAST_ADDR) st8(ab + (uint32_t)k1 * (M * 8u), v);
+                else st8(pos_generic(k1 * M + j), v);
+            }
+        }
+        bar_sync(BAR_MAIN, T);
+        // after the pass-1 barrier of the mix pass nobody reads this raw stage any more:
+        // prefetch the tile of block i+2 into it
+        if (mix && use_raw && tid == 0 && i + 2 < nb) issue_tile(i + 2);
+        // pass 2: radix-R2 over n2 (stride R3) inside each k1 slab, twiddle W_M^{n3 k2}
+        if (R2 > 1) {
+#pragma unroll
+            for (int it = 0; it < I2; ++it) {
+                const int w = tid + T * it;
                 const int k1 = w >> LOG2R3, n3 = w & (R3 - 1);
                 const uint32_t ab = a2_base(k1, n3);
                 float2 x[R2];
 #pragma unroll
-                for (int n2 = 0; n2 < R2; ++n2) {
-                    x[n2] = ld8(a2(ab, n2));
-                }
+                for (int n2 = 0; n2 < R2; ++n2) x[n2] = ld8(a2(ab, n2));
                 fft_dif<R2, false>(x);
 #pragma unroll
                 for (int k2 = 0; k2 < R2; ++k2) {
@@ -558,375 +742,345 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                     st8(a2(ab, k2), v);
                 }
             }
-        };
-        // pass-3 addressing: item g, element n3 (logical e = g*R3 + n3)
-        auto a3_base = [&](int g) -> uint32_t {
-            if constexpr (GMEM) return (uint32_t)g * (R3 * 8u);
-            else return (uint32_t)g * (R3 * 8u) + ((uint32_t)g & 15u) * 8u;
-        };
-        auto a3 = [&](uint32_t base, int n3) -> uint32_t {
-            if constexpr (GMEM) return base + (uint32_t)n3 * 8u;
-            else return base ^ ((uint32_t)n3 * 8u);
-        };
-
-        // ================= FFT #1 =================
-        float2 ph_unused[I1];
-#pragma unroll
-        for (int i = 0; i < I1; ++i) ph_unused[i] = make_float2(1.f, 0.f);
-        fwd_pass1(false, ph_unused);
-        __syncthreads();
-        fwd_pass2();
-        if (R2 > 1) __syncthreads();
-
-        // pass 3 + power spectrum (Signal.mag, signal_utils.py:99-107) + windowed arg-max
-        float pw[I3][R3];
-        float esum = 0.f, msum = 0.f;
-        float bestv = -1.f;
-        uint32_t bestrel = 0;
-#pragma unroll
-        for (int i = 0; i < I3; ++i) {
-            const int g = tid + T * i;
-            const uint32_t ab = a3_base(g);
-            float2 x[R3];
-#pragma unroll
-            for (int n3 = 0; n3 < R3; ++n3) {
-                x[n3] = ld8(a3(ab, n3));
-            }
-            fft_dif<R3, false>(x);
-            const int kb = (g >> LOG2R2) + 32 * (g & (R2 - 1));     // k1 + 32 k2
-#pragma unroll
-            for (int k3 = 0; k3 < R3; ++k3) {
-                const int r = brev(k3, LOG2R3);
-                const float pv = x[r].x * x[r].x + x[r].y * x[r].y;
-                pw[i][k3] = pv;
-                esum += pv;
-            }
-            if (need_std_c) {
-#pragma unroll
-                for (int k3 = 0; k3 < R3; ++k3) msum += sqrtf(pw[i][k3]);
-            }
-            // window test: bin k = kb + S*k3, rel = (k - win_start) mod N must be < win_len.
-            // rel mod S does not depend on k3, so a narrow window rejects most items at once.
-            const uint32_t relb = (uint32_t)(kb - p.win_start) & (uint32_t)(N - 1);
-            if ((relb & (uint32_t)(S - 1)) < (uint32_t)p.win_len) {
-#pragma unroll
-                for (int k3 = 0; k3 < R3; ++k3) {
-                    const uint32_t rel = (relb + (uint32_t)(S * k3)) & (uint32_t)(N - 1);
-                    if (rel < (uint32_t)p.win_len && pw[i][k3] > bestv) {
-                        bestv = pw[i][k3];
-                        bestrel = rel;
-                    }
-                }
-            }
-            if (dbg && p.dbg_fft_mag) {
-#pragma unroll
-                for (int k3 = 0; k3 < R3; ++k3) p.dbg_fft_mag[kb + S * k3] = sqrtf(pw[i][k3]);
-            }
+            bar_sync(BAR_MAIN, T);
         }
-        const RedOut ra = block_reduce<T>(esum, msum, bestv >= 0.f ? pack_cand(bestv, bestrel) : 0ull, red, tid);
+    };
 
-        // ---- carrier decision in float32 (carrier_detect.py:99-115)
-        const float peak_pw = __uint_as_float((uint32_t)(ra.best >> 32));
-        const uint32_t peak_rel = 0xffffffffu - (uint32_t)ra.best;
-        const int kpeak = (p.win_start + (int)peak_rel) & (N - 1);
-        const float peak_mag = sqrtf(peak_pw);
-        const float noise_pw_c = (ra.s0 - 2.f * (peak_mag * peak_mag)) / (float)(N - 1);
-        const float noise_c = sqrtf(noise_pw_c);
-        float var_c = 0.f;
-        if (need_std_c) {
-            const float mean = ra.s1 / (float)N;
-            var_c = fmaxf(ra.s0 / (float)N - mean * mean, 0.f);
-        }
-        const float thr_c = sqrtf(p.c_const + p.c_snr * (noise_c * noise_c) + p.c_std * var_c);
-        const bool carrier = peak_mag > thr_c;
-
-        if (!carrier) {
-            if (tid < p.n_templates) {
-                thr_record rec;
-                rec.block_idx = bidx;
-                rec.soa = __longlong_as_double(0x7ff8000000000000ll);
-                rec.carrier_bin = kpeak;
-                rec.carrier_offset = 0.f;
-                rec.carrier_energy = peak_mag;
-                rec.carrier_noise = noise_c;
-                rec.corr_sample = -1;
-                rec.corr_offset = __int_as_float(0x7fc00000);
-                rec.corr_energy = __int_as_float(0x7fc00000);
-                rec.corr_noise = __int_as_float(0x7fc00000);
-                rec.flags = 0u;
-                rec.template_idx = tid;
-                rec.signal_energy = ra.s0 / (float)N;
-                rec.reserved = 0.f;
-                p.out[(size_t)blk * p.n_templates + tid] = rec;
+    for (int i = -1; i < nb; ++i) {
+        // ================================================================= A(i+1): FFT #1
+        if (i + 1 < nb) {
+            const int ia = i + 1, q = ia & 1;
+            if (use_raw) {
+                mbar_wait(&mbar[q], q ? par1 : par0);
+                if (q) par1 ^= 1; else par0 ^= 1;
             }
-            stage ^= 1;
-            __syncthreads();     // raw tile reads done before the next prefetch overwrites it
-            continue;
-        }
+            float2 ph_unused[I1];
+#pragma unroll
+            for (int it = 0; it < I1; ++it) ph_unused[it] = make_float2(1.f, 0.f);
+            fwd_pass12(ia, false, ph_unused, nullptr);
 
-        // ---- gather the 7 magnitudes around the peak for the Dirichlet fit
+            // pass 3 + power spectrum (Signal.mag, signal_utils.py:99-107) + windowed arg-max
+            float pw[I3][R3];
+            float esum = 0.f, msum = 0.f;
+            float bestv = -1.f;
+            uint32_t bestrel = 0;
 #pragma unroll
-        for (int i = 0; i < I3; ++i) {
-            const int g = tid + T * i;
-            const int kb = (g >> LOG2R2) + 32 * (g & (R2 - 1));
-            const uint32_t u = (uint32_t)(kb - kpeak + 3) & (uint32_t)(N - 1);
-            const uint32_t lo = u & (uint32_t)(S - 1);
-            if (lo < 7u) {
-                const int k3s = (R3 - (int)(u >> LOG2S)) & (R3 - 1);
-                float v = 0.f;
-#pragma unroll
-                for (int k3 = 0; k3 < R3; ++k3) v = (k3 == k3s) ? pw[i][k3] : v;
-                bc[lo] = sqrtf(v);
-            }
-        }
-        __syncthreads();
-        if (tid < 32) {
-            const float y = (lane & 7) < 7 ? bc[lane & 7] : 0.f;
-            const float d = dirichlet_fit(y, lane, p);
-            // mix phasors for the 32 radix-1 positions: rho[n1] = exp(-2 pi i (k+d) n1 / 32)
-            const int e = (kpeak * lane) & 31;
-            const float turns = -((float)e * 0.03125f) - d * ((float)lane * 0.03125f);
-            rho[lane] = cispi(2.f * turns);
-            if (lane == 0) bc[8] = d;
-        }
-        __syncthreads();
-        const float delta = bc[8];
-
-        // ================= mix + FFT #2 (carrier_sync.py:222-238) =================
-        // x'[n] = x[n] exp(2 pi i shift (n/N - 1/2)), shift = -(k + delta); n = n1*M + j
-        float2 ph0[I1];
-#pragma unroll
-        for (int i = 0; i < I1; ++i) {
-            const int j = tid + T * i;
-            const int e = (int)(((long long)kpeak * j) & (N - 1));
-            float turns = -((float)e / (float)N) - delta * ((float)j / (float)N);
-            turns += 0.5f * (float)(kpeak & 1) + 0.5f * delta;
-            ph0[i] = cispi(2.f * turns);
-        }
-        fwd_pass1(true, ph0);
-        __syncthreads();
-        fwd_pass2();
-        if (R2 > 1) __syncthreads();
-
-        // pass 3 of FFT#2, energy of X', then per template: x conj(T)/N and inverse pass 3'
-        float e2sum = 0.f;
-        for (int tpl = 0; tpl < p.n_templates; ++tpl) {
-            const float2 *tsp = p.tpl_spec + (size_t)tpl * N;
-#pragma unroll
-            for (int i = 0; i < I3; ++i) {
-                const int g = tid + T * i;
+            for (int it = 0; it < I3; ++it) {
+                const int g = tid + T * it;
                 const uint32_t ab = a3_base(g);
-                float2 tv[R3];                                    // template spectrum, issued early
-#pragma unroll
-                for (int k3 = 0; k3 < R3; ++k3) tv[k3] = __ldg(&tsp[(size_t)(i * R3 + k3) * T + tid]);
                 float2 x[R3];
-                if (tpl == 0) {
 #pragma unroll
-                    for (int n3 = 0; n3 < R3; ++n3) {
-                        x[n3] = ld8(a3(ab, n3));
-                    }
-                    fft_dif<R3, false>(x);
-#pragma unroll
-                    for (int k3 = 0; k3 < R3; ++k3) {
-                        const int r = brev(k3, LOG2R3);
-                        e2sum += x[r].x * x[r].x + x[r].y * x[r].y;
-                    }
-                    if (p.n_templates > 1) {
-#pragma unroll
-                        for (int k3 = 0; k3 < R3; ++k3) {
-                            const int r = brev(k3, LOG2R3);
-                            p.xsave[(size_t)blockIdx.x * N + (size_t)(i * R3 + k3) * T + tid] =
-                                x[r];
-                        }
-                    }
-                    if (dbg && p.dbg_shifted_fft) {
-                        const int kb = (g >> LOG2R2) + 32 * (g & (R2 - 1));
-#pragma unroll
-                        for (int k3 = 0; k3 < R3; ++k3) {
-                            const int r = brev(k3, LOG2R3);
-                            p.dbg_shifted_fft[kb + S * k3] = x[r];
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int k3 = 0; k3 < R3; ++k3) {
-                        const int r = brev(k3, LOG2R3);
-                        x[r] = p.xsave[(size_t)blockIdx.x * N + (size_t)(i * R3 + k3) * T + tid];
-                    }
-                }
-                // multiply by conj(T)/N (soa_estimator.py:99) and run the inverse radix-R3 DFT
-                float2 y[R3];
+                for (int n3 = 0; n3 < R3; ++n3) x[n3] = ld8(a3(ab, n3));
+                fft_dif<R3, false>(x);
+                const int kb = (g >> LOG2R2) + 32 * (g & (R2 - 1));     // k1 + 32 k2
 #pragma unroll
                 for (int k3 = 0; k3 < R3; ++k3) {
                     const int r = brev(k3, LOG2R3);
-                    y[k3] = cmul(x[r], tv[k3]);
-                }
-                fft_dif<R3, true>(y);
-#pragma unroll
-                for (int n3 = 0; n3 < R3; ++n3) {
-                    const int r = brev(n3, LOG2R3);
-                    st8(a3(ab, n3), y[r]);
-                }
-            }
-            __syncthreads();
-            // inverse pass 2': conj twiddle on load, radix-R2 over k2
-            if (R2 > 1) {
-#pragma unroll
-                for (int i = 0; i < I2; ++i) {
-                    const int w = tid + T * i;
-                    const int k1 = w >> LOG2R3, n3 = w & (R3 - 1);
-                    const uint32_t ab = a2_base(k1, n3);
-                    float2 x[R2];
-#pragma unroll
-                    for (int k2 = 0; k2 < R2; ++k2) {
-                        float2 v = ld8(a2(ab, k2));
-                        if (k2 > 0) v = cmulc(v, tw2[k2 * R3 + n3]);
-                        x[k2] = v;
-                    }
-                    fft_dif<R2, true>(x);
-#pragma unroll
-                    for (int n2 = 0; n2 < R2; ++n2) {
-                        const int r = brev(n2, LOG2R2);
-                        st8(a2(ab, n2), x[r]);
-                    }
-                }
-                __syncthreads();
-            }
-            // inverse pass 1': conj twiddle on load, radix-32 over k1 -> c[n1*M + j]
-            float cp[I1][32];
-            float c1sum = 0.f, c2sum = 0.f;
-            float cbestv = -1.f;
-            int cbestn = 0;
-#pragma unroll
-            for (int i = 0; i < I1; ++i) {
-                const int j = tid + T * i;
-                const uint32_t ab = a1_base(j);
-                float2 x[32];
-                float2 ws = w1[i], ws4 = w4[i];
-                asm volatile("" : "+f"(ws.x), "+f"(ws.y), "+f"(ws4.x), "+f"(ws4.y));
-                float2 cur[4];
-                cur[0] = ws;
-                cur[1] = cmul(ws, ws);
-                cur[2] = cmul(cur[1], ws);
-                cur[3] = ws4;
-                {
-                    float2 v;
-                    if constexpr (FAST_ADDR) v = ld8(ab);
-                    else v = ld8(pos_generic(j));
-                    x[0] = v;
-                }
-#pragma unroll
-                for (int k1 = 1; k1 < 32; ++k1) {
-                    if (k1 > 4) cur[(k1 - 1) & 3] = cmul(cur[(k1 - 1) & 3], ws4);
-                    float2 v;
-                    if constexpr (FAST_ADDR) v = ld8(ab + (uint32_t)k1 * (M * 8u));
-                    else v = ld8(pos_generic(k1 * M + j));
-                    v = cmulc(v, cur[(k1 - 1) & 3]);
-                    x[k1] = v;
-                }
-                fft_dif<32, true>(x);
-                // |c|^2 and windowed arg-max over [corr_start, corr_stop) (soa_estimator.py:137-143);
-                // n = n1*M + j grows with n1, so '>' keeps the first maximum
-                const uint32_t wlen = (uint32_t)(p.corr_stop - p.corr_start);
-                const uint32_t jrel = (uint32_t)(j - p.corr_start);
-#pragma unroll
-                for (int n1 = 0; n1 < 32; ++n1) {
-                    const int r = brev(n1, 5);
                     const float pv = x[r].x * x[r].x + x[r].y * x[r].y;
-                    cp[i][n1] = pv;
-                    if (jrel + (uint32_t)(n1 * M) < wlen && pv > cbestv) {
-                        cbestv = pv;
-                        cbestn = n1 * M + j;
-                    }
+                    pw[it][k3] = pv;
+                    esum += pv;
                 }
-                if (need_std_k) {
+                if (need_std_c) {
 #pragma unroll
-                    for (int n1 = 0; n1 < 32; ++n1) {
-                        if (n1 * M + j < p.corr_len) {
-                            c1sum += sqrtf(cp[i][n1]);
-                            c2sum += cp[i][n1];
+                    for (int k3 = 0; k3 < R3; ++k3) msum += sqrtf(pw[it][k3]);
+                }
+                // window test: bin k = kb + S*k3, rel = (k - win_start) mod N must be < win_len.
+                // rel mod S does not depend on k3, so a narrow window rejects most items at once.
+                const uint32_t relb = (uint32_t)(kb - p.win_start) & (uint32_t)(N - 1);
+                if ((relb & (uint32_t)(S - 1)) < (uint32_t)p.win_len) {
+#pragma unroll
+                    for (int k3 = 0; k3 < R3; ++k3) {
+                        const uint32_t rel = (relb + (uint32_t)(S * k3)) & (uint32_t)(N - 1);
+                        if (rel < (uint32_t)p.win_len && pw[it][k3] > bestv) {
+                            bestv = pw[it][k3];
+                            bestrel = rel;
                         }
                     }
                 }
-                if (dbg && p.dbg_corr && tpl == 0) {
+                if (dbg && p.dbg_fft_mag) {
+#pragma unroll
+                    for (int k3 = 0; k3 < R3; ++k3) p.dbg_fft_mag[kb + S * k3] = sqrtf(pw[it][k3]);
+                }
+            }
+            const RedOut ra = MainReduce<T>::run(esum, msum, bestv >= 0.f ? pack_cand(bestv, bestrel) : 0ull, red, tid);
+
+            // ---- carrier decision in float32 (carrier_detect.py:99-115)
+            const float peak_pw = __uint_as_float((uint32_t)(ra.best >> 32));
+            const uint32_t peak_rel = 0xffffffffu - (uint32_t)ra.best;
+            const int kpeak = (p.win_start + (int)peak_rel) & (N - 1);
+            const float peak_mag = sqrtf(peak_pw);
+            const float noise_pw_c = (ra.s0 - 2.f * (peak_mag * peak_mag)) / (float)(N - 1);
+            const float noise_c = sqrtf(noise_pw_c);
+            float var_c = 0.f;
+            if (need_std_c) {
+                const float mean = ra.s1 / (float)N;
+                var_c = fmaxf(ra.s0 / (float)N - mean * mean, 0.f);
+            }
+            const float thr_c = sqrtf(p.c_const + p.c_snr * (noise_c * noise_c) + p.c_std * var_c);
+            const bool carrier = peak_mag > thr_c;
+
+            FitSlot &fs = fitslot[q];
+            if (tid == 0) {
+                fs.kpeak = kpeak;
+                fs.carrier = carrier ? 1 : 0;
+                fs.peak_mag = peak_mag;
+                fs.noise_c = noise_c;
+                fs.sig_energy1 = ra.s0 / (float)N;
+                fs.delta = 0.f;
+            }
+            // ---- the 7 magnitudes around the peak for the Dirichlet fit (compare-select, no
+            //      dynamic register indexing)
+            if (carrier) {
+#pragma unroll
+                for (int it = 0; it < I3; ++it) {
+                    const int g = tid + T * it;
+                    const int kb = (g >> LOG2R2) + 32 * (g & (R2 - 1));
+                    const uint32_t u = (uint32_t)(kb - kpeak + 3) & (uint32_t)(N - 1);
+                    const uint32_t lo = u & (uint32_t)(S - 1);
+                    if (lo < 7u) {
+                        const int k3s = (R3 - (int)(u >> LOG2S)) & (R3 - 1);
+                        float v = 0.f;
+#pragma unroll
+                        for (int k3 = 0; k3 < R3; ++k3) v = (k3 == k3s) ? pw[it][k3] : v;
+                        fs.mags[lo] = sqrtf(v);
+                    }
+                }
+            }
+            if constexpr (SERVICE) {
+                bar_arrive(BAR_FITREQ + q, NTHREADS);  // service warp: fit(i+1) may start
+            } else {
+                bar_sync(BAR_MAIN, T);
+                if (tid < 32) do_fit(q);               // visible to all after the next BAR_MAIN
+            }
+        }
+
+        // ================================================================= B(i): mix, FFT #2, correlation
+        if (i >= 0) {
+            const int q = i & 1;
+            if constexpr (SERVICE) bar_sync(BAR_FITDONE + q, NTHREADS);   // fit(i) finished
+            else bar_sync(BAR_MAIN, T);
+            const FitSlot &fs = fitslot[q];
+            const int kpeak = fs.kpeak;
+            const bool carrier = fs.carrier != 0;
+            if (tid == 0) {
+                TailHdr &h = tailhdr[q];
+                h.kpeak = kpeak;
+                h.carrier = fs.carrier;
+                h.peak_mag = fs.peak_mag;
+                h.noise_c = fs.noise_c;
+                h.sig_energy1 = fs.sig_energy1;
+                h.delta = fs.delta;
+            }
+            if (!carrier) {
+                // raw stage i&1 is free (A(i) finished long ago): prefetch block i+2 into it
+                if (use_raw && tid == 0 && i + 2 < nb) issue_tile(i + 2);
+                if constexpr (SERVICE) {
+                    bar_arrive(BAR_TAILREQ + q, NTHREADS);
+                } else {
+                    bar_sync(BAR_MAIN, T);
+                    if (tid < 32) do_tail(i, q);
+                }
+                continue;
+            }
+            const float delta = fs.delta;
+
+            // ---- mix + FFT #2 (carrier_sync.py:222-238)
+            // x'[n] = x[n] exp(2 pi i shift (n/N - 1/2)), shift = -(k + delta); n = n1*M + j
+            float2 ph0[I1];
+#pragma unroll
+            for (int it = 0; it < I1; ++it) {
+                const int j = tid + T * it;
+                const int e = (int)(((long long)kpeak * j) & (N - 1));
+                float turns = -((float)e / (float)N) - delta * ((float)j / (float)N);
+                turns += 0.5f * (float)(kpeak & 1) + 0.5f * delta;
+                ph0[it] = cispi(2.f * turns);
+            }
+            fwd_pass12(i, true, ph0, fs.rho);
+
+            // ---- pass 3 of FFT#2, energy of X', then per template: x conj(T)/N and inverse pass 3'
+            float e2sum = 0.f;
+            for (int tpl = 0; tpl < p.n_templates; ++tpl) {
+                const float2 *tsp = p.tpl_spec + (size_t)tpl * N;
+#pragma unroll
+                for (int it = 0; it < I3; ++it) {
+                    const int g = tid + T * it;
+                    const uint32_t ab = a3_base(g);
+                    float2 tv[R3];                                    // template spectrum, issued early
+#pragma unroll
+                    for (int k3 = 0; k3 < R3; ++k3) tv[k3] = __ldg(&tsp[(size_t)(it * R3 + k3) * T + tid]);
+                    float2 x[R3];
+                    if (tpl == 0) {
+#pragma unroll
+                        for (int n3 = 0; n3 < R3; ++n3) x[n3] = ld8(a3(ab, n3));
+                        fft_dif<R3, false>(x);
+#pragma unroll
+                        for (int k3 = 0; k3 < R3; ++k3) {
+                            const int r = brev(k3, LOG2R3);
+                            e2sum += x[r].x * x[r].x + x[r].y * x[r].y;
+                        }
+                        if (p.n_templates > 1) {
+#pragma unroll
+                            for (int k3 = 0; k3 < R3; ++k3) {
+                                const int r = brev(k3, LOG2R3);
+                                p.xsave[(size_t)blockIdx.x * N + (size_t)(it * R3 + k3) * T + tid] = x[r];
+                            }
+                        }
+                        if (dbg && p.dbg_shifted_fft) {
+                            const int kb = (g >> LOG2R2) + 32 * (g & (R2 - 1));
+#pragma unroll
+                            for (int k3 = 0; k3 < R3; ++k3) {
+                                const int r = brev(k3, LOG2R3);
+                                p.dbg_shifted_fft[kb + S * k3] = x[r];
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int k3 = 0; k3 < R3; ++k3) {
+                            const int r = brev(k3, LOG2R3);
+                            x[r] = p.xsave[(size_t)blockIdx.x * N + (size_t)(it * R3 + k3) * T + tid];
+                        }
+                    }
+                    // multiply by conj(T)/N (soa_estimator.py:99) and run the inverse radix-R3 DFT
+                    float2 y[R3];
+#pragma unroll
+                    for (int k3 = 0; k3 < R3; ++k3) {
+                        const int r = brev(k3, LOG2R3);
+                        y[k3] = cmul(x[r], tv[k3]);
+                    }
+                    fft_dif<R3, true>(y);
+#pragma unroll
+                    for (int n3 = 0; n3 < R3; ++n3) {
+                        const int r = brev(n3, LOG2R3);
+                        st8(a3(ab, n3), y[r]);
+                    }
+                }
+                bar_sync(BAR_MAIN, T);
+                // inverse pass 2': conj twiddle on load, radix-R2 over k2
+                if (R2 > 1) {
+#pragma unroll
+                    for (int it = 0; it < I2; ++it) {
+                        const int w = tid + T * it;
+                        const int k1 = w >> LOG2R3, n3 = w & (R3 - 1);
+                        const uint32_t ab = a2_base(k1, n3);
+                        float2 x[R2];
+#pragma unroll
+                        for (int k2 = 0; k2 < R2; ++k2) {
+                            float2 v = ld8(a2(ab, k2));
+                            if (k2 > 0) v = cmulc(v, tw2[k2 * R3 + n3]);
+                            x[k2] = v;
+                        }
+                        fft_dif<R2, true>(x);
+#pragma unroll
+                        for (int n2 = 0; n2 < R2; ++n2) {
+                            const int r = brev(n2, LOG2R2);
+                            st8(a2(ab, n2), x[r]);
+                        }
+                    }
+                    bar_sync(BAR_MAIN, T);
+                }
+                // inverse pass 1': conj twiddle on load, radix-32 over k1 -> c[n1*M + j]
+                float cp[I1][32];
+                float c1sum = 0.f, c2sum = 0.f;
+                float cbestv = -1.f;
+                int cbestn = 0;
+#pragma unroll
+                for (int it = 0; it < I1; ++it) {
+                    const int j = tid + T * it;
+                    const uint32_t ab = a1_base(j);
+                    float2 x[32];
+                    float2 ws = w1[it], ws4 = w4[it];
+                    asm volatile("" : "+f"(ws.x), "+f"(ws.y), "+f"(ws4.x), "+f"(ws4.y));
+                    float2 cur[4];
+                    cur[0] = ws;
+                    cur[1] = cmul(ws, ws);
+                    cur[2] = cmul(cur[1], ws);
+                    cur[3] = ws4;
+                    if constexpr (FAST_ADDR) x[0] = ld8(ab);
+                    else x[0] = ld8(pos_generic(j));
+#pragma unroll
+                    for (int k1 = 1; k1 < 32; ++k1) {
+                        if (k1 > 4) cur[(k1 - 1) & 3] = cmul(cur[(k1 - 1) & 3], ws4);
+                        float2 v;
+                        if constexpr (FAST_ADDR) v = ld8(ab + (uint32_t)k1 * (M * 8u));
+                        else v = ld8(pos_generic(k1 * M + j));
+                        x[k1] = cmulc(v, cur[(k1 - 1) & 3]);
+                    }
+                    fft_dif<32, true>(x);
+                    // |c|^2 and windowed arg-max over [corr_start, corr_stop) (soa_estimator.py:137-143);
+                    // n = n1*M + j grows with n1, so '>' keeps the first maximum
+                    const uint32_t wlen = (uint32_t)(p.corr_stop - p.corr_start);
+                    const uint32_t jrel = (uint32_t)(j - p.corr_start);
 #pragma unroll
                     for (int n1 = 0; n1 < 32; ++n1) {
                         const int r = brev(n1, 5);
-                        if (n1 * M + j < p.corr_len) p.dbg_corr[n1 * M + j] = x[r];
+                        const float pv = x[r].x * x[r].x + x[r].y * x[r].y;
+                        cp[it][n1] = pv;
+                        if (jrel + (uint32_t)(n1 * M) < wlen && pv > cbestv) {
+                            cbestv = pv;
+                            cbestn = n1 * M + j;
+                        }
+                    }
+                    if (need_std_k) {
+#pragma unroll
+                        for (int n1 = 0; n1 < 32; ++n1) {
+                            if (n1 * M + j < p.corr_len) {
+                                c1sum += sqrtf(cp[it][n1]);
+                                c2sum += cp[it][n1];
+                            }
+                        }
+                    }
+                    if (dbg && p.dbg_corr && tpl == 0) {
+#pragma unroll
+                        for (int n1 = 0; n1 < 32; ++n1) {
+                            const int r = brev(n1, 5);
+                            if (n1 * M + j < p.corr_len) p.dbg_corr[n1 * M + j] = x[r];
+                        }
                     }
                 }
-            }
-            // reduce: (energy of X' | sum|c|), sum|c|^2, arg-max
-            const unsigned long long ccand = cbestv >= 0.f ? pack_cand(cbestv, (uint32_t)cbestn) : 0ull;
-            const RedOut rb = block_reduce<T>(need_std_k ? c1sum : e2sum, need_std_k ? c2sum : 0.f, ccand, red, tid);
-            float e2tot;
-            if (need_std_k) {
-                const RedOut rc = block_reduce<T>(e2sum, 0.f, 0ull, red, tid);
-                e2tot = rc.s0;
-            } else {
-                e2tot = rb.s0;
-            }
-            const float peak_cp = __uint_as_float((uint32_t)(rb.best >> 32));
-            const int s = (int)(0xffffffffu - (uint32_t)rb.best);
-            // neighbours of the peak for the Gaussian interpolation
-#pragma unroll
-            for (int i = 0; i < I1; ++i) {
-                const int j = tid + T * i;
-#pragma unroll
-                for (int dd = -1; dd <= 1; dd += 2) {
-                    const int nt = s + dd;
-                    if (nt >= 0 && nt < N && (nt & (M - 1)) == j) {
-                        const int n1s = nt >> LOG2M;
-                        float v = 0.f;
-#pragma unroll
-                        for (int n1 = 0; n1 < 32; ++n1) v = (n1 == n1s) ? cp[i][n1] : v;
-                        bc[16 + (dd + 1)] = v;
-                    }
-                }
-            }
-            __syncthreads();
-            if (tid == 0) {
-                // scalar tail (soa_estimator.py:78-134,159-170); float32 except the SoA itself
-                const float peak_mag_k = sqrtf(peak_cp);
-                const float sig_energy = e2tot / (float)N;
-                const float noise_pw = (sig_energy * p.tpl_energy[tpl] - peak_cp) / (float)N;
-                const float noise_k = sqrtf(noise_pw);                     // NaN if negative
-                float var_k = 0.f;
+                // reduce: (energy of X' | sum|c|), sum|c|^2, arg-max
+                const unsigned long long ccand = cbestv >= 0.f ? pack_cand(cbestv, (uint32_t)cbestn) : 0ull;
+                const RedOut rb = MainReduce<T>::run(need_std_k ? c1sum : e2sum, need_std_k ? c2sum : 0.f, ccand, red, tid);
+                float e2tot;
                 if (need_std_k) {
-                    const float mean = rb.s0 / (float)p.corr_len;
-                    var_k = fmaxf(rb.s1 / (float)p.corr_len - mean * mean, 0.f);
+                    const RedOut rc = MainReduce<T>::run(e2sum, 0.f, 0ull, red, tid);
+                    e2tot = rc.s0;
+                } else {
+                    e2tot = rb.s0;
                 }
-                const float thr_k = sqrtf(p.k_const + p.k_snr * (noise_k * noise_k) + p.k_std * var_k);
-                const bool detected = peak_mag_k > thr_k;
-                float offset = 0.f;
-                if (detected && s > 0 && s < p.corr_len - 1) {
-                    // a,b,c = ln|c|; offset = 0.5 (c-a) / (2b-a-c) with |c| = sqrt(power)
-                    const float pa = bc[16], pc = bc[18], pb = peak_cp;
-                    const float num = logf(pc / pa);
-                    const float den = logf((pb / pa) * (pb / pc));
-                    offset = 0.5f * num / den;
-                    offset = fminf(fmaxf(offset, -0.6f), 0.6f);
+                const int s = (int)(0xffffffffu - (uint32_t)rb.best);
+                TailSlot &ts = tailslot[q * C::MAX_TPL + tpl];
+                if (tid == 0) {
+                    ts.peak_cp = __uint_as_float((uint32_t)(rb.best >> 32));
+                    ts.s = s;
+                    ts.e2tot = e2tot;
+                    ts.c1 = rb.s0;
+                    ts.c2 = rb.s1;
                 }
-                thr_record rec;
-                rec.block_idx = bidx;
-                rec.soa = (double)p.new_len * (double)bidx + (double)s + (double)offset;
-                rec.carrier_bin = kpeak;
-                rec.carrier_offset = delta;
-                rec.carrier_energy = peak_mag;
-                rec.carrier_noise = noise_c;
-                rec.corr_sample = s;
-                rec.corr_offset = offset;
-                rec.corr_energy = peak_mag_k;
-                rec.corr_noise = noise_k;
-                rec.flags = THR_FLAG_CARRIER_DETECTED | (detected ? THR_FLAG_CORR_DETECTED : 0u);
-                rec.template_idx = tpl;
-                rec.signal_energy = sig_energy;
-                rec.reserved = 0.f;
-                p.out[(size_t)blk * p.n_templates + tpl] = rec;
+                // neighbours of the peak for the Gaussian interpolation
+#pragma unroll
+                for (int it = 0; it < I1; ++it) {
+                    const int j = tid + T * it;
+#pragma unroll
+                    for (int dd = -1; dd <= 1; dd += 2) {
+                        const int nt = s + dd;
+                        if (nt >= 0 && nt < N && (nt & (M - 1)) == j) {
+                            const int n1s = nt >> LOG2M;
+                            float v = 0.f;
+#pragma unroll
+                            for (int n1 = 0; n1 < 32; ++n1) v = (n1 == n1s) ? cp[it][n1] : v;
+                            if (dd < 0) ts.pa = v; else ts.pc = v;
+                        }
+                    }
+                }
+                // next template reuses the FFT buffer: all pass-1' loads are done (reduction barriers)
             }
-            __syncthreads();
+            if constexpr (SERVICE) {
+                bar_arrive(BAR_TAILREQ + q, NTHREADS); // service warp: tail(i) may start
+            } else {
+                bar_sync(BAR_MAIN, T);
+                if (tid < 32) do_tail(i, q);
+            }
         }
-        stage ^= 1;
     }
 }
 

@@ -32,6 +32,7 @@ struct Variant {
     int threads;
     bool gmem;
     int r2, r3, i3;
+    int launch_threads;
     size_t smem;
     const void *fn;
     const char *name;
@@ -47,6 +48,7 @@ Variant make_variant(const char *name) {
     v.r2 = C::R2;
     v.r3 = C::R3;
     v.i3 = C::I3;
+    v.launch_threads = C::LAUNCH_THREADS;
     v.smem = C::smem_bytes();
     v.fn = (const void *)&thr::detect_kernel<LOG2N, T, GMEM>;
     v.name = name;
@@ -166,7 +168,8 @@ int launch(thr_detector *d, cudaStream_t st, const uint8_t *d_raw, const float *
     p.dbg_fft_mag = dbg_mag;
     const int grid = n_blocks < d->grid ? n_blocks : d->grid;
     void *args[] = {&p};
-    CU(d, cudaLaunchKernel(d->var.fn, dim3(grid), dim3(d->var.threads), args, d->var.smem, st));
+    // T worker threads + one service warp (see detect_kernel.cuh)
+    CU(d, cudaLaunchKernel(d->var.fn, dim3(grid), dim3(d->var.launch_threads), args, d->var.smem, st));
     d->launches++;
     return THR_OK;
 }
@@ -258,7 +261,7 @@ int thr_create(const thr_config *cfg, thr_detector **out) {
     d->sm_count = prop.multiProcessorCount;
     CUC(cudaFuncSetAttribute(var.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)var.smem));
     int occ = 0;
-    CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, var.fn, var.threads, var.smem));
+    CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, var.fn, var.launch_threads, var.smem));
     if (occ < 1) {
         fail(d, THR_ERR_CUDA, "kernel %s does not fit on an SM (smem %zu)", var.name, var.smem);
         return bail(THR_ERR_CUDA);
@@ -360,7 +363,7 @@ int thr_get_info(const thr_detector *d, thr_info *info) {
     info->device = d->device;
     info->sm_count = d->sm_count;
     info->grid = d->grid;
-    info->threads = d->var.threads;
+    info->threads = d->var.launch_threads;
     info->smem_bytes = (int32_t)d->var.smem;
     info->ctas_per_sm = d->ctas_per_sm;
     info->buffer_in_smem = d->var.gmem ? 0 : 1;
