@@ -11,7 +11,7 @@
 //   -> noise / threshold (:108-134) -> Gaussian interpolation (:159-170) -> 64-byte record.
 //
 // FFT: N = 32 * R2 * R3 decimation-in-frequency, in place in a per-CTA complex buffer
-// (shared memory for N <= 16384, XOR-swizzled so that every pass is bank-conflict free;
+// (shared memory for N <= 16384, rows padded 16->17 so that every pass is bank-conflict free;
 // an L2-resident global scratch for N = 32768).  Each pass is a radix-32/R2/R3 DFT held
 // entirely in registers.  The forward transform leaves the spectrum digit-reversed across
 // threads; the template spectrum is stored pre-permuted to match and the inverse transform
@@ -68,10 +68,11 @@ struct Cfg {
     static_assert((32 * R3) % T == 0 && I2 >= 1, "bad thread count");
     static_assert((32 * R2) % T == 0 && I3 >= 1, "bad thread count");
     static_assert(R2 >= 1 && R2 <= 32 && R3 <= 32, "unsupported size");
-    // position of logical element e in the FFT buffer
-    __device__ __forceinline__ static int pos(int e) {
-        return GMEM_ ? e : (e ^ ((e >> 4) & 15));
-    }
+    // Shared-memory FFT buffer: rows of 16 complex values padded to 17 (136 bytes), so that a
+    // half-warp touches 16 different 8-byte bank pairs both when it walks along a row (passes
+    // 1, 2) and when it walks across rows (pass 3), and every access is base + immediate.
+    static constexpr int ROW_BYTES = GMEM_ ? R3 * 8 : 136;
+    static constexpr size_t BUF_BYTES = GMEM_ ? 0 : (size_t)(N / 16) * 136;
     // T == 512 (one CTA per SM): a dedicated service warpgroup runs the serial fit / tail while the
     // workers go on with the next block; registers are re-split with setmaxnreg (workers 112,
     // service 32).  Smaller T: several CTAs per SM hide the serial parts, warp 0 runs them inline.
@@ -80,7 +81,7 @@ struct Cfg {
     static constexpr int MIN_CTAS = T >= 512 ? 1 : (T >= 256 ? 2 : (T >= 128 ? 4 : 8));
     static constexpr int MAX_TPL = 32;               // templates per detector (tail mailbox size)
     static constexpr size_t smem_bytes() {           // must cover the carve-up in detect_kernel
-        return (GMEM_ ? 0 : (size_t)N * 8) + 2 * (size_t)(2 * N) + (size_t)M * 8
+        return BUF_BYTES + 2 * (size_t)(2 * N) + (size_t)M * 8
                + 2 * 320 + 2 * 32 + 2 * MAX_TPL * 32 + 256 + 64;
     }
 };
@@ -163,33 +164,37 @@ __host__ __device__ __forceinline__ constexpr float sin32(int q) {
     }
 }
 
-// In-register radix-2 DIF FFT of size R (power of two <= 32) on packed complex values.
+// In-register radix-2 decimation-in-time FFT of size R (power of two <= 32) on packed complex
+// values.  Input n must be placed at index brev(n); output k comes out at index k.
 // INV = false: forward (e^{-i...}); INV = true: inverse (e^{+i...}, unnormalised).
-// Output k is left at index brev(k).
+// Butterfly (a, b, w) -> (a + w b, a - w b) costs 3 packed instructions when w is non-trivial:
+//   u = fma(rot(b), s, fma(b, c, a));  v = fma(a, 2, -u)
+// and 2 when w is 1 or -+i (the rotation is an operand swizzle).
 template <int R, bool INV>
-__device__ __forceinline__ void fft_dif(float2 (&x)[R]) {
+__device__ __forceinline__ void fft_dit(float2 (&x)[R]) {
 #pragma unroll
-    for (int len = R; len >= 2; len >>= 1) {
+    for (int len = 2; len <= R; len <<= 1) {
         const int half = len >> 1;
 #pragma unroll
         for (int base = 0; base < R; base += len) {
 #pragma unroll
             for (int i = 0; i < half; ++i) {
-                const int a = base + i, b = a + half;
-                const int q = i * (32 / len);            // twiddle W_len^i = W_32^q
-                const float2 u = f2add(x[a], x[b]);
-                const float2 v = f2sub(x[a], x[b]);
-                x[a] = u;
+                const int ia = base + i, ib = ia + half;
+                const int q = i * (32 / len);            // twiddle W_len^i = W_32^q, q in [0,16)
+                const float2 a = x[ia], b = x[ib];
                 if (q == 0) {
-                    x[b] = v;
-                } else if (q == 8) {                     // * (-i)   [inverse: * (+i)]
-                    x[b] = INV ? rot_pj(v) : rot_mj(v);
-                } else if (q == 4) {                     // * (1 -+ i)/sqrt2
-                    x[b] = f2scale(f2add(v, INV ? rot_pj(v) : rot_mj(v)), 0.70710678118654752f);
-                } else if (q == 12) {                    // * (-1 -+ i)/sqrt2
-                    x[b] = f2scale(f2add(v, INV ? rot_mj(v) : rot_pj(v)), -0.70710678118654752f);
+                    x[ia] = f2add(a, b);
+                    x[ib] = f2sub(a, b);
+                } else if (q == 8) {                     // w = -i (forward) / +i (inverse)
+                    const float2 t = INV ? rot_pj(b) : rot_mj(b);
+                    x[ia] = f2add(a, t);
+                    x[ib] = f2sub(a, t);
                 } else {
-                    x[b] = mul_tw<INV>(v, cos32(q), sin32(q));
+                    const float c = cos32(q), sn = sin32(q);       // w = c -+ i sn
+                    const float2 u = __ffma2_rn(INV ? rot_pj(b) : rot_mj(b), make_float2(sn, sn),
+                                                __ffma2_rn(b, make_float2(c, c), a));
+                    x[ia] = u;
+                    x[ib] = __ffma2_rn(a, make_float2(2.0f, 2.0f), make_float2(-u.x, -u.y));
                 }
             }
         }
@@ -487,7 +492,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
         bufc = reinterpret_cast<unsigned char *>(p.scratch + (size_t)blockIdx.x * N);
     } else {
         bufc = smem;
-        off += (size_t)N * 8;
+        off += C::BUF_BYTES;
     }
     unsigned char *raw_s = smem + off;
     off += 2 * (size_t)RAW_BYTES;
@@ -621,9 +626,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
     // =====================================================================================
     // main (FFT worker) threads
     // =====================================================================================
-    // FFT buffer access.  Shared memory: element e lives at e ^ ((e >> 4) & 15) (8-byte units),
-    // which every pass below expresses as (per-item byte address) XOR (compile-time constant)
-    // plus a compile-time offset.  Global scratch (GMEM): plain layout, L2-only accesses.
+    // FFT buffer access: shared memory (padded rows) or, for GMEM, L2-only global scratch.
     auto ld8 = [&](uint32_t byte_off) -> float2 {
         if constexpr (GMEM) return __ldcg(reinterpret_cast<const float2 *>(bufc + byte_off));
         else return *reinterpret_cast<const float2 *>(bufc + byte_off);
@@ -632,29 +635,19 @@ detect_kernel(const __grid_constant__ DetectParams p) {
         if constexpr (GMEM) __stcg(reinterpret_cast<float2 *>(bufc + byte_off), v);
         else *reinterpret_cast<float2 *>(bufc + byte_off) = v;
     };
-    // pass-1 item j, element k1 (logical e = k1*M + j): base + k1*M*8 when M is a multiple of 256
-    // (the swizzle then only depends on j); smaller sizes recompute it from the logical index
-    auto a1_base = [&](int j) -> uint32_t { return GMEM ? (uint32_t)j * 8u : (uint32_t)(j ^ ((j >> 4) & 15)) * 8u; };
-    auto pos_generic = [&](int e) -> uint32_t { return (uint32_t)C::pos(e) * 8u; };
-    constexpr bool FAST_ADDR = GMEM || (M % 256 == 0);
-    // pass-2 addressing: item (k1, n3), element n2 (logical e = k1*M + n2*R3 + n3)
+    // logical element e -> byte offset: GMEM plain (8e); shared: row (e >> 4) of 136 bytes.
+    // pass 1: item j, element k1       e = k1*M + j          -> a1_base(j) + k1 * A1_STEP
+    // pass 2: item (k1,n3), element n2 e = k1*M + n2*R3 + n3 -> a2_base(k1,n3) + n2 * A2_STEP
+    // pass 3: item g, element n3       e = g*R3 + n3         -> a3_base(g) + n3 * 8
+    constexpr uint32_t A1_STEP = GMEM ? (uint32_t)M * 8u : (uint32_t)(M / 16) * 136u;
+    constexpr uint32_t A2_STEP = GMEM ? (uint32_t)R3 * 8u : 136u;
+    auto a1_base = [&](int j) -> uint32_t {
+        return GMEM ? (uint32_t)j * 8u : (uint32_t)(j >> 4) * 136u + (uint32_t)(j & 15) * 8u;
+    };
     auto a2_base = [&](int k1, int n3) -> uint32_t {
-        if constexpr (GMEM) return (uint32_t)(k1 * M + n3) * 8u;
-        else return (uint32_t)(k1 * M) * 8u + (((uint32_t)n3 ^ (((uint32_t)k1 * R2) & 15u)) * 8u);
+        return GMEM ? (uint32_t)(k1 * M + n3) * 8u : (uint32_t)k1 * A1_STEP + (uint32_t)n3 * 8u;
     };
-    auto a2 = [&](uint32_t base, int n2) -> uint32_t {
-        if constexpr (GMEM) return base + (uint32_t)n2 * (R3 * 8u);
-        else return (base ^ (((uint32_t)n2 & 15u) * 8u)) + (uint32_t)n2 * (R3 * 8u);
-    };
-    // pass-3 addressing: item g, element n3 (logical e = g*R3 + n3)
-    auto a3_base = [&](int g) -> uint32_t {
-        if constexpr (GMEM) return (uint32_t)g * (R3 * 8u);
-        else return (uint32_t)g * (R3 * 8u) + ((uint32_t)g & 15u) * 8u;
-    };
-    auto a3 = [&](uint32_t base, int n3) -> uint32_t {
-        if constexpr (GMEM) return base + (uint32_t)n3 * 8u;
-        else return base ^ ((uint32_t)n3 * 8u);
-    };
+    auto a3_base = [&](int g) -> uint32_t { return (uint32_t)g * (uint32_t)C::ROW_BYTES; };
 
     float2 w1[I1], w4[I1];                                      // W_N^j and W_N^{4j}
 #pragma unroll
@@ -687,16 +680,18 @@ detect_kernel(const __grid_constant__ DetectParams p) {
             float2 x[32];
             if (use_raw) {
 #pragma unroll
-                for (int n1 = 0; n1 < 32; ++n1) x[n1] = rawconv(rawt[n1 * M + j]);
+                for (int n1 = 0; n1 < 32; ++n1) x[brev(n1, 5)] = rawconv(rawt[n1 * M + j]);
             } else {
 #pragma unroll
-                for (int n1 = 0; n1 < 32; ++n1) x[n1] = __ldg(&iqb[n1 * M + j]);
+                for (int n1 = 0; n1 < 32; ++n1) x[brev(n1, 5)] = __ldg(&iqb[n1 * M + j]);
             }
             if (mix) {
+                // row phasor here; the per-thread phasor ph0 is common to the whole item and is
+                // folded into the twiddle seeds below (the DFT is linear)
 #pragma unroll
-                for (int n1 = 0; n1 < 32; ++n1) x[n1] = cmul(x[n1], cmul(ph0[it], rho[n1]));
+                for (int n1 = 1; n1 < 32; ++n1) x[brev(n1, 5)] = cmul(x[brev(n1, 5)], rho[n1]);
             }
-            fft_dif<32, false>(x);
+            fft_dit<32, false>(x);
             // Twiddles W_N^{j k1} are regenerated per block from two per-thread seeds.  The opaque
             // asm keeps the compiler from hoisting all 31 powers out of the block loop, which
             // would turn them into a 124 KB per-CTA local-memory table (L2 traffic + latency).
@@ -708,15 +703,17 @@ detect_kernel(const __grid_constant__ DetectParams p) {
             cur[2] = cmul(cur[1], ws);
             cur[3] = ws4;
             const uint32_t ab = a1_base(j);
-            if constexpr (FAST_ADDR) st8(ab, x[0]);
-            else st8(pos_generic(j), x[0]);
+            if (mix) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) cur[c] = cmul(cur[c], ph0[it]);
+                st8(ab, cmul(x[0], ph0[it]));
+            } else {
+                st8(ab, x[0]);
+            }
 #pragma unroll
             for (int k1 = 1; k1 < 32; ++k1) {
-                const int r = brev(k1, 5);
                 if (k1 > 4) cur[(k1 - 1) & 3] = cmul(cur[(k1 - 1) & 3], ws4);
-                const float2 v = cmul(x[r], cur[(k1 - 1) & 3]);
-                if constexpr (FAST_ADDR) st8(ab + (uint32_t)k1 * (M * 8u), v);
-                else st8(pos_generic(k1 * M + j), v);
+                st8(ab + (uint32_t)k1 * A1_STEP, cmul(x[k1], cur[(k1 - 1) & 3]));
             }
         }
         bar_sync(BAR_MAIN, T);
@@ -732,14 +729,13 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 const uint32_t ab = a2_base(k1, n3);
                 float2 x[R2];
 #pragma unroll
-                for (int n2 = 0; n2 < R2; ++n2) x[n2] = ld8(a2(ab, n2));
-                fft_dif<R2, false>(x);
+                for (int n2 = 0; n2 < R2; ++n2) x[brev(n2, LOG2R2)] = ld8(ab + (uint32_t)n2 * A2_STEP);
+                fft_dit<R2, false>(x);
 #pragma unroll
                 for (int k2 = 0; k2 < R2; ++k2) {
-                    const int r = brev(k2, LOG2R2);
-                    float2 v = x[r];
+                    float2 v = x[k2];
                     if (k2 > 0) v = cmul(v, tw2[k2 * R3 + n3]);
-                    st8(a2(ab, k2), v);
+                    st8(ab + (uint32_t)k2 * A2_STEP, v);
                 }
             }
             bar_sync(BAR_MAIN, T);
@@ -770,12 +766,12 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 const uint32_t ab = a3_base(g);
                 float2 x[R3];
 #pragma unroll
-                for (int n3 = 0; n3 < R3; ++n3) x[n3] = ld8(a3(ab, n3));
-                fft_dif<R3, false>(x);
+                for (int n3 = 0; n3 < R3; ++n3) x[brev(n3, LOG2R3)] = ld8(ab + (uint32_t)n3 * 8u);
+                fft_dit<R3, false>(x);
                 const int kb = (g >> LOG2R2) + 32 * (g & (R2 - 1));     // k1 + 32 k2
 #pragma unroll
                 for (int k3 = 0; k3 < R3; ++k3) {
-                    const int r = brev(k3, LOG2R3);
+                    const int r = k3;
                     const float pv = x[r].x * x[r].x + x[r].y * x[r].y;
                     pw[it][k3] = pv;
                     esum += pv;
@@ -911,48 +907,32 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                     float2 x[R3];
                     if (tpl == 0) {
 #pragma unroll
-                        for (int n3 = 0; n3 < R3; ++n3) x[n3] = ld8(a3(ab, n3));
-                        fft_dif<R3, false>(x);
+                        for (int n3 = 0; n3 < R3; ++n3) x[brev(n3, LOG2R3)] = ld8(ab + (uint32_t)n3 * 8u);
+                        fft_dit<R3, false>(x);
 #pragma unroll
-                        for (int k3 = 0; k3 < R3; ++k3) {
-                            const int r = brev(k3, LOG2R3);
-                            e2sum += x[r].x * x[r].x + x[r].y * x[r].y;
-                        }
+                        for (int k3 = 0; k3 < R3; ++k3) e2sum += x[k3].x * x[k3].x + x[k3].y * x[k3].y;
                         if (p.n_templates > 1) {
 #pragma unroll
-                            for (int k3 = 0; k3 < R3; ++k3) {
-                                const int r = brev(k3, LOG2R3);
-                                p.xsave[(size_t)blockIdx.x * N + (size_t)(it * R3 + k3) * T + tid] = x[r];
-                            }
+                            for (int k3 = 0; k3 < R3; ++k3)
+                                p.xsave[(size_t)blockIdx.x * N + (size_t)(it * R3 + k3) * T + tid] = x[k3];
                         }
                         if (dbg && p.dbg_shifted_fft) {
                             const int kb = (g >> LOG2R2) + 32 * (g & (R2 - 1));
 #pragma unroll
-                            for (int k3 = 0; k3 < R3; ++k3) {
-                                const int r = brev(k3, LOG2R3);
-                                p.dbg_shifted_fft[kb + S * k3] = x[r];
-                            }
+                            for (int k3 = 0; k3 < R3; ++k3) p.dbg_shifted_fft[kb + S * k3] = x[k3];
                         }
                     } else {
 #pragma unroll
-                        for (int k3 = 0; k3 < R3; ++k3) {
-                            const int r = brev(k3, LOG2R3);
-                            x[r] = p.xsave[(size_t)blockIdx.x * N + (size_t)(it * R3 + k3) * T + tid];
-                        }
+                        for (int k3 = 0; k3 < R3; ++k3)
+                            x[k3] = p.xsave[(size_t)blockIdx.x * N + (size_t)(it * R3 + k3) * T + tid];
                     }
                     // multiply by conj(T)/N (soa_estimator.py:99) and run the inverse radix-R3 DFT
                     float2 y[R3];
 #pragma unroll
-                    for (int k3 = 0; k3 < R3; ++k3) {
-                        const int r = brev(k3, LOG2R3);
-                        y[k3] = cmul(x[r], tv[k3]);
-                    }
-                    fft_dif<R3, true>(y);
+                    for (int k3 = 0; k3 < R3; ++k3) y[brev(k3, LOG2R3)] = cmul(x[k3], tv[k3]);
+                    fft_dit<R3, true>(y);
 #pragma unroll
-                    for (int n3 = 0; n3 < R3; ++n3) {
-                        const int r = brev(n3, LOG2R3);
-                        st8(a3(ab, n3), y[r]);
-                    }
+                    for (int n3 = 0; n3 < R3; ++n3) st8(ab + (uint32_t)n3 * 8u, y[n3]);
                 }
                 bar_sync(BAR_MAIN, T);
                 // inverse pass 2': conj twiddle on load, radix-R2 over k2
@@ -965,16 +945,13 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                         float2 x[R2];
 #pragma unroll
                         for (int k2 = 0; k2 < R2; ++k2) {
-                            float2 v = ld8(a2(ab, k2));
+                            float2 v = ld8(ab + (uint32_t)k2 * A2_STEP);
                             if (k2 > 0) v = cmulc(v, tw2[k2 * R3 + n3]);
-                            x[k2] = v;
+                            x[brev(k2, LOG2R2)] = v;
                         }
-                        fft_dif<R2, true>(x);
+                        fft_dit<R2, true>(x);
 #pragma unroll
-                        for (int n2 = 0; n2 < R2; ++n2) {
-                            const int r = brev(n2, LOG2R2);
-                            st8(a2(ab, n2), x[r]);
-                        }
+                        for (int n2 = 0; n2 < R2; ++n2) st8(ab + (uint32_t)n2 * A2_STEP, x[n2]);
                     }
                     bar_sync(BAR_MAIN, T);
                 }
@@ -995,25 +972,20 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                     cur[1] = cmul(ws, ws);
                     cur[2] = cmul(cur[1], ws);
                     cur[3] = ws4;
-                    if constexpr (FAST_ADDR) x[0] = ld8(ab);
-                    else x[0] = ld8(pos_generic(j));
+                    x[0] = ld8(ab);
 #pragma unroll
                     for (int k1 = 1; k1 < 32; ++k1) {
                         if (k1 > 4) cur[(k1 - 1) & 3] = cmul(cur[(k1 - 1) & 3], ws4);
-                        float2 v;
-                        if constexpr (FAST_ADDR) v = ld8(ab + (uint32_t)k1 * (M * 8u));
-                        else v = ld8(pos_generic(k1 * M + j));
-                        x[k1] = cmulc(v, cur[(k1 - 1) & 3]);
+                        x[brev(k1, 5)] = cmulc(ld8(ab + (uint32_t)k1 * A1_STEP), cur[(k1 - 1) & 3]);
                     }
-                    fft_dif<32, true>(x);
+                    fft_dit<32, true>(x);
                     // |c|^2 and windowed arg-max over [corr_start, corr_stop) (soa_estimator.py:137-143);
                     // n = n1*M + j grows with n1, so '>' keeps the first maximum
                     const uint32_t wlen = (uint32_t)(p.corr_stop - p.corr_start);
                     const uint32_t jrel = (uint32_t)(j - p.corr_start);
 #pragma unroll
                     for (int n1 = 0; n1 < 32; ++n1) {
-                        const int r = brev(n1, 5);
-                        const float pv = x[r].x * x[r].x + x[r].y * x[r].y;
+                        const float pv = x[n1].x * x[n1].x + x[n1].y * x[n1].y;
                         cp[it][n1] = pv;
                         if (jrel + (uint32_t)(n1 * M) < wlen && pv > cbestv) {
                             cbestv = pv;
@@ -1031,10 +1003,8 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                     }
                     if (dbg && p.dbg_corr && tpl == 0) {
 #pragma unroll
-                        for (int n1 = 0; n1 < 32; ++n1) {
-                            const int r = brev(n1, 5);
-                            if (n1 * M + j < p.corr_len) p.dbg_corr[n1 * M + j] = x[r];
-                        }
+                        for (int n1 = 0; n1 < 32; ++n1)
+                            if (n1 * M + j < p.corr_len) p.dbg_corr[n1 * M + j] = x[n1];
                     }
                 }
                 // reduce: (energy of X' | sum|c|), sum|c|^2, arg-max
