@@ -223,7 +223,7 @@ def run_ours(args):
     n, batch = args.block_len, args.batch
     tpl, uniq = make_unique_blocks(args.unique, args.p_signal, synth.SEED0 + 100003 * rank)
     det = NativeDetector(n, HISTORY, tpl, len(tpl), WINDOW, THRESH, THRESH, device=local_rank,
-                         max_batch=batch)
+                         max_batch=batch, overlap_launches=True)
     info = det.info()
 
     # device-resident pool of raw blocks, larger than L2 (126 MB): pool_blocks * 32 KiB
@@ -233,7 +233,8 @@ def run_ours(args):
     reps = (pool_blocks + len(uniq) - 1) // len(uniq)
     pool = uniq_d.repeat(reps, 1)[:pool_blocks].contiguous()
     idx = torch.arange(pool_blocks, dtype=torch.int64, device=dev) + rank * (1 << 40)
-    rec = torch.zeros(batch * 64, dtype=torch.uint8, device=dev)
+    # two record buffers, alternated: consecutive launches may overlap at their edges (PDL)
+    recs2 = [torch.zeros(batch * 64, dtype=torch.uint8, device=dev) for _ in range(2)]
     gathered = torch.zeros(world * batch * 64, dtype=torch.uint8, device=dev) if world > 1 else None
     # a real (non-legacy) stream: handle 0 would mean "the detector's own stream" to thr_set_stream
     stream = torch.cuda.Stream(device=dev)
@@ -243,6 +244,7 @@ def run_ours(args):
 
     def step(i, gather=True):
         w = i % n_windows
+        rec = recs2[i & 1]
         det.detect_device(pool[w * batch].data_ptr(), idx[w * batch].data_ptr(), batch, rec.data_ptr())
         if gather and world > 1:
             dist.all_gather_into_tensor(gathered, rec)
@@ -294,7 +296,8 @@ def run_ours(args):
     ms_kernel = timed(args.steps, gather=False) / args.steps if world > 1 else ms_per_step
 
     # records sanity: every block of the last batch must carry a decision
-    recs = np.frombuffer(rec.cpu().numpy().tobytes(), dtype=RECORD_DTYPE)
+    torch.cuda.synchronize()
+    recs = np.frombuffer(recs2[(args.steps - 1) & 1].cpu().numpy().tobytes(), dtype=RECORD_DTYPE)
     n_det = int(((recs["flags"] & 2) != 0).sum())
     n_car = int(((recs["flags"] & 1) != 0).sum())
 

@@ -41,6 +41,13 @@ extern "C" {
 #define THR_ERR_NOMEM     -3
 #define THR_ERR_NO_DEVICE -4   /* no usable sm_100 device                    */
 
+/* thr_config.flags */
+#define THR_CFG_OVERLAP_LAUNCHES 1u    /* consecutive *_device launches on one stream may overlap at their
+                                          edges (programmatic dependent launch): the next batch starts on SMs
+                                          the previous batch has drained.  Launches are independent, so this is
+                                          safe as long as consecutive launches do not write the same output
+                                          buffer (alternate two record buffers).                              */
+
 /* thr_record.flags */
 #define THR_FLAG_CARRIER_DETECTED 1u   /* carrier peak above threshold (carrier_sync.py:69)      */
 #define THR_FLAG_CORR_DETECTED    2u   /* correlation peak above threshold (soa_estimator.py:85) */
@@ -64,7 +71,7 @@ typedef struct thr_config {
     double corr_thresh[3];    /* (constant, snr, stddev)                                 */
     int32_t device;           /* CUDA device ordinal                                     */
     int32_t max_batch;        /* max blocks per launch (device staging is sized for it)  */
-    uint32_t flags;           /* reserved, must be 0                                     */
+    uint32_t flags;           /* THR_CFG_* bits                                          */
     int32_t reserved;
 } thr_config;
 

@@ -150,7 +150,7 @@ class NativeDetector(object):
     """Thin owner of a thr_detector handle."""
 
     def __init__(self, block_len, history_len, templates, carrier_len, carrier_window,
-                 carrier_thresh, corr_thresh, device=0, max_batch=4096):
+                 carrier_thresh, corr_thresh, device=0, max_batch=4096, overlap_launches=False):
         self._lib = load_library()
         self._h = c_void_p()
         tpl = np.ascontiguousarray(np.atleast_2d(np.asarray(templates, dtype=np.float64)))
@@ -172,7 +172,7 @@ class NativeDetector(object):
         cfg.corr_thresh = (c_double * 3)(*[float(v) for v in corr_thresh])
         cfg.device = self.device
         cfg.max_batch = self.max_batch
-        cfg.flags = 0
+        cfg.flags = 1 if overlap_launches else 0      # THR_CFG_OVERLAP_LAUNCHES
         rc = self._lib.thr_create(byref(cfg), byref(self._h))
         if rc != THR_OK:
             msg = self._lib.thr_last_error(None).decode()

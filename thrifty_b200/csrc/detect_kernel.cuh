@@ -418,7 +418,7 @@ struct FitSlot {            // written by main after FFT#1 (A stage), completed 
 struct TailSlot {           // written by main at the end of the correlation stage
     float peak_cp;          // |c|^2 at the peak
     int   s;                // peak lag
-    float e2tot;            // sum |X'|^2
+    float unused0;
     float pa, pc;           // |c|^2 at s-1, s+1
     float c1, c2;           // sum |c|, sum |c|^2 over [0, corr_len) (stddev threshold term only)
     float pad;
@@ -431,38 +431,51 @@ struct TailHdr {            // carrier fields copied for the record
 
 static_assert(sizeof(FitSlot) == 320 && sizeof(TailSlot) == 32 && sizeof(TailHdr) == 32, "mailbox layout");
 
-template <int T>
-struct MainReduce {
-    // block-wide reduction over the T main threads only (two BAR_MAIN syncs)
-    __device__ __forceinline__ static RedOut run(float s0, float s1, unsigned long long best, uint32_t *red,
-                                                 int tid) {
-        constexpr int NW = T / 32;
+// Block-wide arg-max (+ optional sums) over the T worker threads; two BAR_MAIN syncs.
+//   vbits: bit pattern of this thread's best (non-negative) value, 0 if it has none
+//   find_key(gbits): called only by threads whose vbits equals the block maximum; returns the
+//                    smallest key (bin / lag) at which this thread holds that value
+// Returns the maximum and the smallest key over all threads holding it (numpy's first-max rule).
+struct ArgOut {
+    uint32_t vbits, key;
+    float s0, s1;
+};
+template <int T, bool SUMS, class F>
+__device__ __forceinline__ ArgOut main_argmax(uint32_t vbits, float s0, float s1, uint32_t *red, int tid,
+                                              F &&find_key) {
+    constexpr int NW = T / 32;
+    const uint32_t wmax = __reduce_max_sync(0xffffffffu, vbits);
+    if (SUMS) {
         s0 = warp_sum(s0);
         s1 = warp_sum(s1);
-        best = warp_max_u64(best);
-        const int w = tid >> 5;
-        if ((tid & 31) == 0) {
-            red[w * 4 + 0] = __float_as_uint(s0);
-            red[w * 4 + 1] = __float_as_uint(s1);
-            red[w * 4 + 2] = (uint32_t)(best >> 32);
-            red[w * 4 + 3] = (uint32_t)best;
-        }
-        bar_sync(BAR_MAIN, T);
-        RedOut r;
-        r.s0 = 0.f;
-        r.s1 = 0.f;
-        r.best = 0ull;
-#pragma unroll
-        for (int i = 0; i < NW; ++i) {
-            r.s0 += __uint_as_float(red[i * 4 + 0]);
-            r.s1 += __uint_as_float(red[i * 4 + 1]);
-            unsigned long long b = ((unsigned long long)red[i * 4 + 2] << 32) | red[i * 4 + 3];
-            r.best = b > r.best ? b : r.best;
-        }
-        bar_sync(BAR_MAIN, T);
-        return r;
     }
-};
+    const int w = tid >> 5;
+    if ((tid & 31) == 0) {
+        red[w] = wmax;
+        if (SUMS) {
+            red[16 + w] = __float_as_uint(s0);
+            red[32 + w] = __float_as_uint(s1);
+        }
+        if (tid == 0) red[48] = 0xffffffffu;
+    }
+    bar_sync(BAR_MAIN, T);
+    ArgOut r;
+    r.vbits = 0u;
+    r.s0 = 0.f;
+    r.s1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+        r.vbits = max(r.vbits, red[i]);
+        if (SUMS) {
+            r.s0 += __uint_as_float(red[16 + i]);
+            r.s1 += __uint_as_float(red[32 + i]);
+        }
+    }
+    if (vbits == r.vbits) atomicMin(&red[48], find_key(r.vbits));
+    bar_sync(BAR_MAIN, T);
+    r.key = red[48];
+    return r;
+}
 
 // ------------------------------------------------------------------ the kernel
 // Launched with T + 32 threads: warps 0..T/32-1 are the FFT workers, the last warp is the
@@ -515,6 +528,9 @@ detect_kernel(const __grid_constant__ DetectParams p) {
     // blocks of this CTA: blockIdx.x + i * gridDim.x, i in [0, nb)
     const int nb = ((int)blockIdx.x < p.n_blocks) ? (p.n_blocks - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
+    // Launches are independent of each other: let a dependent (next-batch) launch start as soon as
+    // SMs drain (no-op unless the launch carries the programmatic-serialization attribute).
+    asm volatile("griddepcontrol.launch_dependents;");
     if (tid == 0) {
         mbar_init(&mbar[0], 1);
         mbar_init(&mbar[1], 1);
@@ -570,7 +586,9 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 // scalar tail (soa_estimator.py:78-134,159-170); float32 except the SoA itself
                 const TailSlot &ts = tailslot[q * C::MAX_TPL + tpl];
                 const float peak_mag_k = sqrtf(ts.peak_cp);
-                const float sig_energy = ts.e2tot / (float)N;
+                // mean |X'|^2 (soa_estimator.py:111) == sum |x|^2 == mean |X|^2 of FFT#1: the mix is a
+                // unit-modulus rotation and both FFTs are unitary up to N (Parseval)
+                const float sig_energy = h.sig_energy1;
                 const float noise_pw = (sig_energy * p.tpl_energy[tpl] - ts.peak_cp) / (float)N;
                 const float noise_k = sqrtf(noise_pw);                 // NaN if negative
                 float var_k = 0.f;
@@ -758,8 +776,8 @@ detect_kernel(const __grid_constant__ DetectParams p) {
             // pass 3 + power spectrum (Signal.mag, signal_utils.py:99-107) + windowed arg-max
             float pw[I3][R3];
             float esum = 0.f, msum = 0.f;
-            float bestv = -1.f;
-            uint32_t bestrel = 0;
+            float bestv = 0.f;                       // best in-window power of this thread
+            const bool all_in = (p.win_len >= N);    // default window '0--1': every bin qualifies
 #pragma unroll
             for (int it = 0; it < I3; ++it) {
                 const int g = tid + T * it;
@@ -783,14 +801,14 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 // window test: bin k = kb + S*k3, rel = (k - win_start) mod N must be < win_len.
                 // rel mod S does not depend on k3, so a narrow window rejects most items at once.
                 const uint32_t relb = (uint32_t)(kb - p.win_start) & (uint32_t)(N - 1);
-                if ((relb & (uint32_t)(S - 1)) < (uint32_t)p.win_len) {
+                if (all_in) {
+#pragma unroll
+                    for (int k3 = 0; k3 < R3; ++k3) bestv = fmaxf(bestv, pw[it][k3]);
+                } else if ((relb & (uint32_t)(S - 1)) < (uint32_t)p.win_len) {
 #pragma unroll
                     for (int k3 = 0; k3 < R3; ++k3) {
                         const uint32_t rel = (relb + (uint32_t)(S * k3)) & (uint32_t)(N - 1);
-                        if (rel < (uint32_t)p.win_len && pw[it][k3] > bestv) {
-                            bestv = pw[it][k3];
-                            bestrel = rel;
-                        }
+                        if (rel < (uint32_t)p.win_len) bestv = fmaxf(bestv, pw[it][k3]);
                     }
                 }
                 if (dbg && p.dbg_fft_mag) {
@@ -798,11 +816,26 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                     for (int k3 = 0; k3 < R3; ++k3) p.dbg_fft_mag[kb + S * k3] = sqrtf(pw[it][k3]);
                 }
             }
-            const RedOut ra = MainReduce<T>::run(esum, msum, bestv >= 0.f ? pack_cand(bestv, bestrel) : 0ull, red, tid);
+            // first maximum in window order (np.argmax over the wrapped window, carrier_detect.py:138-149)
+            const ArgOut ra = main_argmax<T, true>(__float_as_uint(bestv), esum, msum, red, tid, [&](uint32_t gb) {
+                uint32_t key = 0xffffffffu;
+#pragma unroll
+                for (int it = 0; it < I3; ++it) {
+                    const int g = tid + T * it;
+                    const int kb = (g >> LOG2R2) + 32 * (g & (R2 - 1));
+                    const uint32_t relb = (uint32_t)(kb - p.win_start) & (uint32_t)(N - 1);
+#pragma unroll
+                    for (int k3 = 0; k3 < R3; ++k3) {
+                        const uint32_t rel = (relb + (uint32_t)(S * k3)) & (uint32_t)(N - 1);
+                        if (rel < (uint32_t)p.win_len && __float_as_uint(pw[it][k3]) == gb) key = min(key, rel);
+                    }
+                }
+                return key;
+            });
 
             // ---- carrier decision in float32 (carrier_detect.py:99-115)
-            const float peak_pw = __uint_as_float((uint32_t)(ra.best >> 32));
-            const uint32_t peak_rel = 0xffffffffu - (uint32_t)ra.best;
+            const float peak_pw = __uint_as_float(ra.vbits);
+            const uint32_t peak_rel = ra.key;
             const int kpeak = (p.win_start + (int)peak_rel) & (N - 1);
             const float peak_mag = sqrtf(peak_pw);
             const float noise_pw_c = (ra.s0 - 2.f * (peak_mag * peak_mag)) / (float)(N - 1);
@@ -894,7 +927,6 @@ detect_kernel(const __grid_constant__ DetectParams p) {
             fwd_pass12(i, true, ph0, fs.rho);
 
             // ---- pass 3 of FFT#2, energy of X', then per template: x conj(T)/N and inverse pass 3'
-            float e2sum = 0.f;
             for (int tpl = 0; tpl < p.n_templates; ++tpl) {
                 const float2 *tsp = p.tpl_spec + (size_t)tpl * N;
 #pragma unroll
@@ -909,8 +941,6 @@ detect_kernel(const __grid_constant__ DetectParams p) {
 #pragma unroll
                         for (int n3 = 0; n3 < R3; ++n3) x[brev(n3, LOG2R3)] = ld8(ab + (uint32_t)n3 * 8u);
                         fft_dit<R3, false>(x);
-#pragma unroll
-                        for (int k3 = 0; k3 < R3; ++k3) e2sum += x[k3].x * x[k3].x + x[k3].y * x[k3].y;
                         if (p.n_templates > 1) {
 #pragma unroll
                             for (int k3 = 0; k3 < R3; ++k3)
@@ -958,8 +988,8 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 // inverse pass 1': conj twiddle on load, radix-32 over k1 -> c[n1*M + j]
                 float cp[I1][32];
                 float c1sum = 0.f, c2sum = 0.f;
-                float cbestv = -1.f;
-                int cbestn = 0;
+                float cbestv = 0.f;                  // best in-window |c|^2 of this thread
+                uint32_t inmask[I1];                 // bit n1: lag n1*M + j lies in [corr_start, corr_stop)
 #pragma unroll
                 for (int it = 0; it < I1; ++it) {
                     const int j = tid + T * it;
@@ -981,16 +1011,18 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                     fft_dit<32, true>(x);
                     // |c|^2 and windowed arg-max over [corr_start, corr_stop) (soa_estimator.py:137-143);
                     // n = n1*M + j grows with n1, so '>' keeps the first maximum
-                    const uint32_t wlen = (uint32_t)(p.corr_stop - p.corr_start);
-                    const uint32_t jrel = (uint32_t)(j - p.corr_start);
+                    {
+                        // rows n1 in [lo, hi] are inside the window for this thread's column j
+                        const int lo = max(0, (p.corr_start - j + M - 1) >> LOG2M);
+                        const int hi = min(31, (p.corr_stop - 1 - j) >> LOG2M);    // -1 if j >= corr_stop
+                        const uint32_t upto_hi = hi >= 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u);
+                        inmask[it] = (hi >= lo) ? (upto_hi & ~((1u << lo) - 1u)) : 0u;
+                    }
 #pragma unroll
                     for (int n1 = 0; n1 < 32; ++n1) {
                         const float pv = x[n1].x * x[n1].x + x[n1].y * x[n1].y;
                         cp[it][n1] = pv;
-                        if (jrel + (uint32_t)(n1 * M) < wlen && pv > cbestv) {
-                            cbestv = pv;
-                            cbestn = n1 * M + j;
-                        }
+                        if (inmask[it] & (1u << n1)) cbestv = fmaxf(cbestv, pv);
                     }
                     if (need_std_k) {
 #pragma unroll
@@ -1007,22 +1039,26 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                             if (n1 * M + j < p.corr_len) p.dbg_corr[n1 * M + j] = x[n1];
                     }
                 }
-                // reduce: (energy of X' | sum|c|), sum|c|^2, arg-max
-                const unsigned long long ccand = cbestv >= 0.f ? pack_cand(cbestv, (uint32_t)cbestn) : 0ull;
-                const RedOut rb = MainReduce<T>::run(need_std_k ? c1sum : e2sum, need_std_k ? c2sum : 0.f, ccand, red, tid);
-                float e2tot;
-                if (need_std_k) {
-                    const RedOut rc = MainReduce<T>::run(e2sum, 0.f, 0ull, red, tid);
-                    e2tot = rc.s0;
-                } else {
-                    e2tot = rb.s0;
-                }
-                const int s = (int)(0xffffffffu - (uint32_t)rb.best);
+                // block arg-max: first maximum of |c|^2 over the window (soa_estimator.py:137-143)
+                auto find_lag = [&](uint32_t gb) {
+                    uint32_t key = 0xffffffffu;
+#pragma unroll
+                    for (int it = 0; it < I1; ++it) {
+#pragma unroll
+                        for (int n1 = 31; n1 >= 0; --n1)
+                            if ((inmask[it] & (1u << n1)) && __float_as_uint(cp[it][n1]) == gb)
+                                key = min(key, (uint32_t)(n1 * M + tid + T * it));
+                    }
+                    return key;
+                };
+                ArgOut rb;
+                if (need_std_k) rb = main_argmax<T, true>(__float_as_uint(cbestv), c1sum, c2sum, red, tid, find_lag);
+                else rb = main_argmax<T, false>(__float_as_uint(cbestv), 0.f, 0.f, red, tid, find_lag);
+                const int s = (int)rb.key;
                 TailSlot &ts = tailslot[q * C::MAX_TPL + tpl];
                 if (tid == 0) {
-                    ts.peak_cp = __uint_as_float((uint32_t)(rb.best >> 32));
+                    ts.peak_cp = __uint_as_float(rb.vbits);
                     ts.s = s;
-                    ts.e2tot = e2tot;
                     ts.c1 = rb.s0;
                     ts.c2 = rb.s1;
                 }

@@ -155,7 +155,8 @@ bool range_index(int start, int stop, int length, int *s, int *e) {
 }
 
 int launch(thr_detector *d, cudaStream_t st, const uint8_t *d_raw, const float *d_iq, const int64_t *d_idx,
-           int n_blocks, thr_record *d_out, float2 *dbg_sfft, float2 *dbg_corr, float *dbg_mag) {
+           int n_blocks, thr_record *d_out, float2 *dbg_sfft, float2 *dbg_corr, float *dbg_mag,
+           bool allow_overlap = false) {
     if (n_blocks <= 0) return THR_OK;
     DetectParams p = d->base;
     p.raw = d_raw;
@@ -168,8 +169,20 @@ int launch(thr_detector *d, cudaStream_t st, const uint8_t *d_raw, const float *
     p.dbg_fft_mag = dbg_mag;
     const int grid = n_blocks < d->grid ? n_blocks : d->grid;
     void *args[] = {&p};
-    // T worker threads + one service warp (see detect_kernel.cuh)
-    CU(d, cudaLaunchKernel(d->var.fn, dim3(grid), dim3(d->var.launch_threads), args, d->var.smem, st));
+    cudaLaunchConfig_t lc;
+    std::memset(&lc, 0, sizeof lc);
+    lc.gridDim = dim3(grid);
+    lc.blockDim = dim3(d->var.launch_threads);     // workers (+ service warpgroup), see detect_kernel.cuh
+    lc.dynamicSmemBytes = d->var.smem;
+    lc.stream = st;
+    cudaLaunchAttribute attr[1];
+    if (allow_overlap && (d->cfg.flags & THR_CFG_OVERLAP_LAUNCHES) && !d->var.gmem && d->cfg.n_templates == 1) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = attr;
+        lc.numAttrs = 1;
+    }
+    CU(d, cudaLaunchKernelExC(&lc, d->var.fn, args));
     d->launches++;
     return THR_OK;
 }
@@ -222,7 +235,7 @@ int thr_create(const thr_config *cfg, thr_detector **out) {
         return fail(nullptr, THR_ERR_INVALID, "history_len %d must satisfy template_len-1 <= H < block_len", H);
     if (cfg->carrier_len < 1) return fail(nullptr, THR_ERR_INVALID, "carrier_len must be positive");
     if (cfg->max_batch < 1) return fail(nullptr, THR_ERR_INVALID, "max_batch must be positive");
-    if (cfg->flags != 0) return fail(nullptr, THR_ERR_INVALID, "flags must be 0");
+    if (cfg->flags & ~THR_CFG_OVERLAP_LAUNCHES) return fail(nullptr, THR_ERR_INVALID, "unknown flags 0x%x", cfg->flags);
     int ws, we;
     if (!range_index(cfg->window_start, cfg->window_stop, N, &ws, &we))   // carrier_detect.py:47-49
         return fail(nullptr, THR_ERR_INVALID, "Frequency window out of range: %d - %d", cfg->window_start,
@@ -409,7 +422,7 @@ int thr_detect_batch_device(thr_detector *d, const uint8_t *d_raw, const int64_t
     if (n_blocks > d->cfg.max_batch) return fail(d, THR_ERR_INVALID, "n_blocks %d exceeds max_batch %d", n_blocks, d->cfg.max_batch);
     if (((uintptr_t)d_raw & 15) != 0) return fail(d, THR_ERR_INVALID, "d_raw must be 16-byte aligned (TMA bulk copy)");
     CU(d, cudaSetDevice(d->device));
-    return launch(d, d->stream, d_raw, nullptr, d_idx, n_blocks, d_out, nullptr, nullptr, nullptr);
+    return launch(d, d->stream, d_raw, nullptr, d_idx, n_blocks, d_out, nullptr, nullptr, nullptr, true);
 }
 
 int thr_detect_batch_device_c64(thr_detector *d, const float *d_iq, const int64_t *d_idx, int32_t n_blocks,
@@ -418,7 +431,7 @@ int thr_detect_batch_device_c64(thr_detector *d, const float *d_iq, const int64_
     if (n_blocks > d->cfg.max_batch) return fail(d, THR_ERR_INVALID, "n_blocks %d exceeds max_batch %d", n_blocks, d->cfg.max_batch);
     if (((uintptr_t)d_iq & 7) != 0) return fail(d, THR_ERR_INVALID, "d_iq must be 8-byte aligned");
     CU(d, cudaSetDevice(d->device));
-    return launch(d, d->stream, nullptr, d_iq, d_idx, n_blocks, d_out, nullptr, nullptr, nullptr);
+    return launch(d, d->stream, nullptr, d_iq, d_idx, n_blocks, d_out, nullptr, nullptr, nullptr, true);
 }
 
 static int detect_host(thr_detector *d, const uint8_t *raw, const float *iq, const int64_t *block_idx,
