@@ -42,6 +42,7 @@ struct DetectParams {
     float k_const, k_snr, k_std;   // correlation threshold coefficients
     int corr_start, corr_stop, corr_len;
     int new_len;               // N - H
+    int zoom;                  // 1: carrier window (+-3 bins) lies in [0,128) and no stddev term -> pruned FFT#1
     float fit_tab[7][4];       // per fit point x=-3..3: sin(aWx), cos(aWx), sin(ax), cos(ax), a = pi/N
     float fit_W;               // carrier_len
     float fit_WoverN;          // W / N
@@ -82,7 +83,7 @@ struct Cfg {
     static constexpr int MAX_TPL = 32;               // templates per detector (tail mailbox size)
     static constexpr size_t smem_bytes() {           // must cover the carve-up in detect_kernel
         return BUF_BYTES + 2 * (size_t)(2 * N) + (size_t)M * 8
-               + 2 * 320 + 2 * 32 + 2 * MAX_TPL * 32 + 256 + 64;
+               + 2 * 320 + 2 * 32 + 2 * MAX_TPL * 32 + 256 + 512 + 64;
     }
 };
 
@@ -161,6 +162,21 @@ __host__ __device__ __forceinline__ constexpr float sin32(int q) {
         case 14: return 0.38268343236508989f;
         case 15: return 0.19509032201612861f;
         default: return 0.0f;
+    }
+}
+
+// acc + v * W_32^q (forward, q in [0,32)): 2 packed FMAs, the rotation is an operand swizzle
+template <int Q>
+__device__ __forceinline__ float2 fma_tw32(float2 acc, float2 v) {
+    constexpr int q = Q & 31;
+    if constexpr (q == 0) return f2add(acc, v);
+    else if constexpr (q == 8) return f2add(acc, rot_mj(v));
+    else if constexpr (q == 16) return f2sub(acc, v);
+    else if constexpr (q == 24) return f2add(acc, rot_pj(v));
+    else {
+        constexpr float sg = q >= 16 ? -1.0f : 1.0f;           // W^(q) = -W^(q-16)
+        constexpr float c = sg * cos32(q & 15), sn = sg * sin32(q & 15);
+        return __ffma2_rn(rot_mj(v), make_float2(sn, sn), __ffma2_rn(v, make_float2(c, c), acc));
     }
 }
 
@@ -519,6 +535,8 @@ detect_kernel(const __grid_constant__ DetectParams p) {
     off += 2 * (size_t)C::MAX_TPL * sizeof(TailSlot);
     uint32_t *red = reinterpret_cast<uint32_t *>(smem + off);        // 64 words reduction scratch
     off += 256;
+    float *zpow = reinterpret_cast<float *>(smem + off);             // |X[k]|^2, k < 128 (zoom path)
+    off += 512;
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + off);       // 2 barriers
 
     const bool use_raw = (p.raw != nullptr);
@@ -687,7 +705,10 @@ detect_kernel(const __grid_constant__ DetectParams p) {
     uint32_t par0 = 0, par1 = 0;    // phase parity of the two tile barriers
 
     // forward passes 1 and 2 of block i (shared by FFT#1 and FFT#2)
-    auto fwd_pass12 = [&](int i, bool mix, const float2 (&ph0)[I1], const float2 *rho) {
+    // zoom (pruned FFT#1): only bins [0,128) are needed, i.e. k3 == 0 and k2 < 4, so pass 2 computes
+    // 4 of its R2 outputs and pass 3 degenerates to a sum; the spectrum energy comes from Parseval
+    const bool zoom = (p.zoom != 0) && (p.dbg_fft_mag == nullptr) && (R2 == 32);
+    auto fwd_pass12 = [&](int i, bool mix, const float2 (&ph0)[I1], const float2 *rho, float &energy) {
         const uint16_t *rawt = reinterpret_cast<const uint16_t *>(raw_s + (size_t)(i & 1) * RAW_BYTES);
         const float2 *iqb = use_raw ? nullptr : p.iq + (size_t)((int)blockIdx.x + i * (int)gridDim.x) * N;
         // pass 1: samples (rawconv or complex64) [* mix phasor] -> radix-32 over n1 (stride M)
@@ -702,6 +723,10 @@ detect_kernel(const __grid_constant__ DetectParams p) {
             } else {
 #pragma unroll
                 for (int n1 = 0; n1 < 32; ++n1) x[brev(n1, 5)] = __ldg(&iqb[n1 * M + j]);
+            }
+            if (!mix && zoom) {                  // sum |x|^2 (Parseval: sum_k |X[k]|^2 = N sum_n |x[n]|^2)
+#pragma unroll
+                for (int n1 = 0; n1 < 32; ++n1) energy = fmaf(x[n1].x, x[n1].x, fmaf(x[n1].y, x[n1].y, energy));
             }
             if (mix) {
                 // row phasor here; the per-thread phasor ph0 is common to the whole item and is
@@ -738,6 +763,49 @@ detect_kernel(const __grid_constant__ DetectParams p) {
         // after the pass-1 barrier of the mix pass nobody reads this raw stage any more:
         // prefetch the tile of block i+2 into it
         if (mix && use_raw && tid == 0 && i + 2 < nb) issue_tile(i + 2);
+        if constexpr (R2 == 32) {
+            if (!mix && zoom) {
+                // pruned pass 2: outputs k2 = 0..3 of the 32-point DFT over n2 = 8m + r:
+                //   c_r[k] = sum_m a[8m+r] W_4^{mk}   (radix-4, no multiplications)
+                //   B[k]   = sum_r W_32^{rk} c_r[k]   (2 packed FMAs per term)
+#pragma unroll
+                for (int it = 0; it < I2; ++it) {
+                    const int w = tid + T * it;
+                    const int k1 = w >> LOG2R3, n3 = w & (R3 - 1);
+                    const uint32_t ab = a2_base(k1, n3);
+                    float2 b0, b1, b2, b3;
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        const float2 a0 = ld8(ab + (uint32_t)(r) * A2_STEP);
+                        const float2 a1 = ld8(ab + (uint32_t)(8 + r) * A2_STEP);
+                        const float2 a2 = ld8(ab + (uint32_t)(16 + r) * A2_STEP);
+                        const float2 a3 = ld8(ab + (uint32_t)(24 + r) * A2_STEP);
+                        const float2 s0 = f2add(a0, a2), s1 = f2sub(a0, a2);
+                        const float2 s2 = f2add(a1, a3), s3 = f2sub(a1, a3);
+                        const float2 c0 = f2add(s0, s2), c2 = f2sub(s0, s2);
+                        const float2 c1 = f2add(s1, rot_mj(s3)), c3 = f2add(s1, rot_pj(s3));
+                        if (r == 0) {
+                            b0 = c0; b1 = c1; b2 = c2; b3 = c3;
+                        } else {
+                            b0 = f2add(b0, c0);
+                            if (r == 1) { b1 = fma_tw32<1>(b1, c1); b2 = fma_tw32<2>(b2, c2); b3 = fma_tw32<3>(b3, c3); }
+                            if (r == 2) { b1 = fma_tw32<2>(b1, c1); b2 = fma_tw32<4>(b2, c2); b3 = fma_tw32<6>(b3, c3); }
+                            if (r == 3) { b1 = fma_tw32<3>(b1, c1); b2 = fma_tw32<6>(b2, c2); b3 = fma_tw32<9>(b3, c3); }
+                            if (r == 4) { b1 = fma_tw32<4>(b1, c1); b2 = fma_tw32<8>(b2, c2); b3 = fma_tw32<12>(b3, c3); }
+                            if (r == 5) { b1 = fma_tw32<5>(b1, c1); b2 = fma_tw32<10>(b2, c2); b3 = fma_tw32<15>(b3, c3); }
+                            if (r == 6) { b1 = fma_tw32<6>(b1, c1); b2 = fma_tw32<12>(b2, c2); b3 = fma_tw32<18>(b3, c3); }
+                            if (r == 7) { b1 = fma_tw32<7>(b1, c1); b2 = fma_tw32<14>(b2, c2); b3 = fma_tw32<21>(b3, c3); }
+                        }
+                    }
+                    st8(ab, b0);
+                    st8(ab + 1u * A2_STEP, cmul(b1, tw2[1 * R3 + n3]));
+                    st8(ab + 2u * A2_STEP, cmul(b2, tw2[2 * R3 + n3]));
+                    st8(ab + 3u * A2_STEP, cmul(b3, tw2[3 * R3 + n3]));
+                }
+                bar_sync(BAR_MAIN, T);
+                return;
+            }
+        }
         // pass 2: radix-R2 over n2 (stride R3) inside each k1 slab, twiddle W_M^{n3 k2}
         if (R2 > 1) {
 #pragma unroll
@@ -771,67 +839,118 @@ detect_kernel(const __grid_constant__ DetectParams p) {
             float2 ph_unused[I1];
 #pragma unroll
             for (int it = 0; it < I1; ++it) ph_unused[it] = make_float2(1.f, 0.f);
-            fwd_pass12(ia, false, ph_unused, nullptr);
+            float tenergy = 0.f;
+            fwd_pass12(ia, false, ph_unused, nullptr, tenergy);
 
-            // pass 3 + power spectrum (Signal.mag, signal_utils.py:99-107) + windowed arg-max
+            ArgOut ra;
             float pw[I3][R3];
-            float esum = 0.f, msum = 0.f;
-            float bestv = 0.f;                       // best in-window power of this thread
-            const bool all_in = (p.win_len >= N);    // default window '0--1': every bin qualifies
+            if (zoom) {
+                // pass 3 (pruned): X[k1 + 32 k2] = sum_n3 B[k1,k2;n3] for the 128 bins k < 128;
+                // 4 threads per bin, R3/4 terms each, then two shuffles
+                constexpr int PER = R3 / 4;
+#pragma unroll 1
+                for (int pzb = 0; pzb < 128; pzb += T / 4) {
+                    const int pz = pzb + (tid >> 2), sub = tid & 3;
+                    const int k1 = pz & 31, k2 = pz >> 5;
+                    float2 acc = make_float2(0.f, 0.f);
+                    if (pz < 128) {
 #pragma unroll
-            for (int it = 0; it < I3; ++it) {
-                const int g = tid + T * it;
-                const uint32_t ab = a3_base(g);
-                float2 x[R3];
-#pragma unroll
-                for (int n3 = 0; n3 < R3; ++n3) x[brev(n3, LOG2R3)] = ld8(ab + (uint32_t)n3 * 8u);
-                fft_dit<R3, false>(x);
-                const int kb = (g >> LOG2R2) + 32 * (g & (R2 - 1));     // k1 + 32 k2
-#pragma unroll
-                for (int k3 = 0; k3 < R3; ++k3) {
-                    const int r = k3;
-                    const float pv = x[r].x * x[r].x + x[r].y * x[r].y;
-                    pw[it][k3] = pv;
-                    esum += pv;
-                }
-                if (need_std_c) {
-#pragma unroll
-                    for (int k3 = 0; k3 < R3; ++k3) msum += sqrtf(pw[it][k3]);
-                }
-                // window test: bin k = kb + S*k3, rel = (k - win_start) mod N must be < win_len.
-                // rel mod S does not depend on k3, so a narrow window rejects most items at once.
-                const uint32_t relb = (uint32_t)(kb - p.win_start) & (uint32_t)(N - 1);
-                if (all_in) {
-#pragma unroll
-                    for (int k3 = 0; k3 < R3; ++k3) bestv = fmaxf(bestv, pw[it][k3]);
-                } else if ((relb & (uint32_t)(S - 1)) < (uint32_t)p.win_len) {
-#pragma unroll
-                    for (int k3 = 0; k3 < R3; ++k3) {
-                        const uint32_t rel = (relb + (uint32_t)(S * k3)) & (uint32_t)(N - 1);
-                        if (rel < (uint32_t)p.win_len) bestv = fmaxf(bestv, pw[it][k3]);
+                        for (int t = 0; t < PER; ++t)
+                            acc = f2add(acc, ld8(a2_base(k1, sub * PER + t) + (uint32_t)k2 * A2_STEP));
                     }
+                    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 1);
+                    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 1);
+                    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 2);
+                    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 2);
+                    if (sub == 0 && pz < 128) zpow[k1 + 32 * k2] = acc.x * acc.x + acc.y * acc.y;
                 }
-                if (dbg && p.dbg_fft_mag) {
+                const float wsum = warp_sum(tenergy);
+                if (lane == 0) red[16 + (tid >> 5)] = __float_as_uint(wsum);
+                bar_sync(BAR_MAIN, T);
+                // every warp finds the window maximum of the 128 powers on its own (no extra barrier)
+                uint32_t vb = 0u;
 #pragma unroll
-                    for (int k3 = 0; k3 < R3; ++k3) p.dbg_fft_mag[kb + S * k3] = sqrtf(pw[it][k3]);
+                for (int c = 0; c < 4; ++c) {
+                    const int k = lane + 32 * c;
+                    const uint32_t rel = (uint32_t)(k - p.win_start);
+                    vb = max(vb, rel < (uint32_t)p.win_len ? __float_as_uint(zpow[k]) : 0u);
                 }
-            }
-            // first maximum in window order (np.argmax over the wrapped window, carrier_detect.py:138-149)
-            const ArgOut ra = main_argmax<T, true>(__float_as_uint(bestv), esum, msum, red, tid, [&](uint32_t gb) {
+                const uint32_t gb = __reduce_max_sync(0xffffffffu, vb);
                 uint32_t key = 0xffffffffu;
 #pragma unroll
+                for (int c = 3; c >= 0; --c) {
+                    const int k = lane + 32 * c;
+                    const uint32_t rel = (uint32_t)(k - p.win_start);
+                    if (rel < (uint32_t)p.win_len && __float_as_uint(zpow[k]) == gb) key = rel;
+                }
+                ra.vbits = gb;
+                ra.key = __reduce_min_sync(0xffffffffu, key);
+                float esum = 0.f;
+#pragma unroll
+                for (int w = 0; w < T / 32; ++w) esum += __uint_as_float(red[16 + w]);
+                ra.s0 = esum * (float)N;
+                ra.s1 = 0.f;
+            } else {
+                // pass 3 + power spectrum (Signal.mag, signal_utils.py:99-107) + windowed arg-max
+                float esum = 0.f, msum = 0.f;
+                float bestv = 0.f;                       // best in-window power of this thread
+                const bool all_in = (p.win_len >= N);    // default window '0--1': every bin qualifies
+    #pragma unroll
                 for (int it = 0; it < I3; ++it) {
                     const int g = tid + T * it;
-                    const int kb = (g >> LOG2R2) + 32 * (g & (R2 - 1));
-                    const uint32_t relb = (uint32_t)(kb - p.win_start) & (uint32_t)(N - 1);
-#pragma unroll
+                    const uint32_t ab = a3_base(g);
+                    float2 x[R3];
+    #pragma unroll
+                    for (int n3 = 0; n3 < R3; ++n3) x[brev(n3, LOG2R3)] = ld8(ab + (uint32_t)n3 * 8u);
+                    fft_dit<R3, false>(x);
+                    const int kb = (g >> LOG2R2) + 32 * (g & (R2 - 1));     // k1 + 32 k2
+    #pragma unroll
                     for (int k3 = 0; k3 < R3; ++k3) {
-                        const uint32_t rel = (relb + (uint32_t)(S * k3)) & (uint32_t)(N - 1);
-                        if (rel < (uint32_t)p.win_len && __float_as_uint(pw[it][k3]) == gb) key = min(key, rel);
+                        const int r = k3;
+                        const float pv = x[r].x * x[r].x + x[r].y * x[r].y;
+                        pw[it][k3] = pv;
+                        esum += pv;
+                    }
+                    if (need_std_c) {
+    #pragma unroll
+                        for (int k3 = 0; k3 < R3; ++k3) msum += sqrtf(pw[it][k3]);
+                    }
+                    // window test: bin k = kb + S*k3, rel = (k - win_start) mod N must be < win_len.
+                    // rel mod S does not depend on k3, so a narrow window rejects most items at once.
+                    const uint32_t relb = (uint32_t)(kb - p.win_start) & (uint32_t)(N - 1);
+                    if (all_in) {
+    #pragma unroll
+                        for (int k3 = 0; k3 < R3; ++k3) bestv = fmaxf(bestv, pw[it][k3]);
+                    } else if ((relb & (uint32_t)(S - 1)) < (uint32_t)p.win_len) {
+    #pragma unroll
+                        for (int k3 = 0; k3 < R3; ++k3) {
+                            const uint32_t rel = (relb + (uint32_t)(S * k3)) & (uint32_t)(N - 1);
+                            if (rel < (uint32_t)p.win_len) bestv = fmaxf(bestv, pw[it][k3]);
+                        }
+                    }
+                    if (dbg && p.dbg_fft_mag) {
+    #pragma unroll
+                        for (int k3 = 0; k3 < R3; ++k3) p.dbg_fft_mag[kb + S * k3] = sqrtf(pw[it][k3]);
                     }
                 }
-                return key;
-            });
+                // first maximum in window order (np.argmax over the wrapped window, carrier_detect.py:138-149)
+                ra = main_argmax<T, true>(__float_as_uint(bestv), esum, msum, red, tid, [&](uint32_t gb) {
+                    uint32_t key = 0xffffffffu;
+    #pragma unroll
+                    for (int it = 0; it < I3; ++it) {
+                        const int g = tid + T * it;
+                        const int kb = (g >> LOG2R2) + 32 * (g & (R2 - 1));
+                        const uint32_t relb = (uint32_t)(kb - p.win_start) & (uint32_t)(N - 1);
+    #pragma unroll
+                        for (int k3 = 0; k3 < R3; ++k3) {
+                            const uint32_t rel = (relb + (uint32_t)(S * k3)) & (uint32_t)(N - 1);
+                            if (rel < (uint32_t)p.win_len && __float_as_uint(pw[it][k3]) == gb) key = min(key, rel);
+                        }
+                    }
+                    return key;
+                });
+
+            }
 
             // ---- carrier decision in float32 (carrier_detect.py:99-115)
             const float peak_pw = __uint_as_float(ra.vbits);
@@ -859,7 +978,9 @@ detect_kernel(const __grid_constant__ DetectParams p) {
             }
             // ---- the 7 magnitudes around the peak for the Dirichlet fit (compare-select, no
             //      dynamic register indexing)
-            if (carrier) {
+            if (carrier && zoom) {
+                if (tid < 7) fs.mags[tid] = sqrtf(zpow[kpeak - 3 + tid]);
+            } else if (carrier) {
 #pragma unroll
                 for (int it = 0; it < I3; ++it) {
                     const int g = tid + T * it;
@@ -924,7 +1045,8 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 turns += 0.5f * (float)(kpeak & 1) + 0.5f * delta;
                 ph0[it] = cispi(2.f * turns);
             }
-            fwd_pass12(i, true, ph0, fs.rho);
+            float unused_energy = 0.f;
+            fwd_pass12(i, true, ph0, fs.rho, unused_energy);
 
             // ---- pass 3 of FFT#2, energy of X', then per template: x conj(T)/N and inverse pass 3'
             for (int tpl = 0; tpl < p.n_templates; ++tpl) {
