@@ -158,6 +158,29 @@ def test_fresh_seeds_vs_oracle(block_len, n_blocks, seed):
     det.close()
 
 
+@pytest.mark.parametrize("window,cthresh,kthresh", [
+    ((7, 300), (0., 15., 0.), (0., 15., 0.)),         # window beyond bin 124: full FFT#1 path
+    ((7, 110), (1., 12., 2.), (0.5, 10., 3.)),        # stddev terms: full FFT#1 path, extra reductions
+    ((-300, -7), (0., 15., 0.), (0., 15., 0.)),       # negative-frequency window
+    ((3, 124), (0., 15., 0.), (0., 15., 0.)),         # widest window the pruned FFT#1 path accepts
+])
+def test_n16384_carrier_paths(window, cthresh, kthresh):
+    """N=16384: the pruned ('zoom') and the full FFT#1 carrier paths both match the oracle."""
+    from thrifty_b200._native import NativeDetector
+    tpl = np.load(os.path.join(parity.GOLDEN, "template_example.npy"))
+    n, hist, nblk = 16384, 4920, 96
+    lo, hi = (window[0] + 1.0, window[1] - 1.0)
+    raw, _ = synth.make_blocks(nblk, n, hist, tpl, 0.6, seed=31337 + abs(window[0]), bin_range=(lo, hi))
+    st = orc.DetectorSettings(n, hist, len(tpl), cthresh, window, tpl, kthresh)
+    ref = orc.detect_blocks(st, raw)
+    det = NativeDetector(n, hist, tpl, len(tpl), window, cthresh, kthresh, max_batch=128)
+    got = det.detect_raw(raw)[:, 0]
+    stats = parity.compare_records(got, ref, what="N=16384 window %s" % (window,))
+    print(window, stats)
+    assert stats["carrier"] >= nblk // 3
+    det.close()
+
+
 def test_whole_spectrum_window_and_degenerate_blocks():
     """Default window '0--1' (all bins) and degenerate inputs: constant, saturated, DC-only."""
     from thrifty_b200._native import NativeDetector

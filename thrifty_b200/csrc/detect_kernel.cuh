@@ -842,9 +842,33 @@ detect_kernel(const __grid_constant__ DetectParams p) {
             float tenergy = 0.f;
             fwd_pass12(ia, false, ph_unused, nullptr, tenergy);
 
-            ArgOut ra;
-            float pw[I3][R3];
+            FitSlot &fs = fitslot[q];
+            // carrier decision in float32 (carrier_detect.py:99-115); returns the peak bin or -1
+            auto decide = [&](const ArgOut &ra) -> int {
+                const float peak_pw = __uint_as_float(ra.vbits);
+                const int kpeak = (p.win_start + (int)ra.key) & (N - 1);
+                const float peak_mag = sqrtf(peak_pw);
+                const float noise_pw_c = (ra.s0 - 2.f * (peak_mag * peak_mag)) / (float)(N - 1);
+                const float noise_c = sqrtf(noise_pw_c);
+                float var_c = 0.f;
+                if (need_std_c) {
+                    const float mean = ra.s1 / (float)N;
+                    var_c = fmaxf(ra.s0 / (float)N - mean * mean, 0.f);
+                }
+                const float thr_c = sqrtf(p.c_const + p.c_snr * (noise_c * noise_c) + p.c_std * var_c);
+                const bool carrier = peak_mag > thr_c;
+                if (tid == 0) {
+                    fs.kpeak = kpeak;
+                    fs.carrier = carrier ? 1 : 0;
+                    fs.peak_mag = peak_mag;
+                    fs.noise_c = noise_c;
+                    fs.sig_energy1 = ra.s0 / (float)N;
+                    fs.delta = 0.f;
+                }
+                return carrier ? kpeak : -1;
+            };
             if (zoom) {
+                ArgOut ra;
                 // pass 3 (pruned): X[k1 + 32 k2] = sum_n3 B[k1,k2;n3] for the 128 bins k < 128;
                 // 4 threads per bin, R3/4 terms each, then two shuffles
                 constexpr int PER = R3 / 4;
@@ -890,8 +914,12 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 for (int w = 0; w < T / 32; ++w) esum += __uint_as_float(red[16 + w]);
                 ra.s0 = esum * (float)N;
                 ra.s1 = 0.f;
+                const int kpeak = decide(ra);
+                // the 7 magnitudes around the peak for the Dirichlet fit
+                if (kpeak >= 0 && tid < 7) fs.mags[tid] = sqrtf(zpow[kpeak - 3 + tid]);
             } else {
                 // pass 3 + power spectrum (Signal.mag, signal_utils.py:99-107) + windowed arg-max
+                float pw[I3][R3];
                 float esum = 0.f, msum = 0.f;
                 float bestv = 0.f;                       // best in-window power of this thread
                 const bool all_in = (p.win_len >= N);    // default window '0--1': every bin qualifies
@@ -934,7 +962,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                     }
                 }
                 // first maximum in window order (np.argmax over the wrapped window, carrier_detect.py:138-149)
-                ra = main_argmax<T, true>(__float_as_uint(bestv), esum, msum, red, tid, [&](uint32_t gb) {
+                const ArgOut ra = main_argmax<T, true>(__float_as_uint(bestv), esum, msum, red, tid, [&](uint32_t gb) {
                     uint32_t key = 0xffffffffu;
     #pragma unroll
                     for (int it = 0; it < I3; ++it) {
@@ -949,50 +977,23 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                     }
                     return key;
                 });
-
-            }
-
-            // ---- carrier decision in float32 (carrier_detect.py:99-115)
-            const float peak_pw = __uint_as_float(ra.vbits);
-            const uint32_t peak_rel = ra.key;
-            const int kpeak = (p.win_start + (int)peak_rel) & (N - 1);
-            const float peak_mag = sqrtf(peak_pw);
-            const float noise_pw_c = (ra.s0 - 2.f * (peak_mag * peak_mag)) / (float)(N - 1);
-            const float noise_c = sqrtf(noise_pw_c);
-            float var_c = 0.f;
-            if (need_std_c) {
-                const float mean = ra.s1 / (float)N;
-                var_c = fmaxf(ra.s0 / (float)N - mean * mean, 0.f);
-            }
-            const float thr_c = sqrtf(p.c_const + p.c_snr * (noise_c * noise_c) + p.c_std * var_c);
-            const bool carrier = peak_mag > thr_c;
-
-            FitSlot &fs = fitslot[q];
-            if (tid == 0) {
-                fs.kpeak = kpeak;
-                fs.carrier = carrier ? 1 : 0;
-                fs.peak_mag = peak_mag;
-                fs.noise_c = noise_c;
-                fs.sig_energy1 = ra.s0 / (float)N;
-                fs.delta = 0.f;
-            }
-            // ---- the 7 magnitudes around the peak for the Dirichlet fit (compare-select, no
-            //      dynamic register indexing)
-            if (carrier && zoom) {
-                if (tid < 7) fs.mags[tid] = sqrtf(zpow[kpeak - 3 + tid]);
-            } else if (carrier) {
+                const int kpeak = decide(ra);
+                // the 7 magnitudes around the peak for the Dirichlet fit (compare-select, no dynamic
+                // register indexing)
+                if (kpeak >= 0) {
 #pragma unroll
-                for (int it = 0; it < I3; ++it) {
-                    const int g = tid + T * it;
-                    const int kb = (g >> LOG2R2) + 32 * (g & (R2 - 1));
-                    const uint32_t u = (uint32_t)(kb - kpeak + 3) & (uint32_t)(N - 1);
-                    const uint32_t lo = u & (uint32_t)(S - 1);
-                    if (lo < 7u) {
-                        const int k3s = (R3 - (int)(u >> LOG2S)) & (R3 - 1);
-                        float v = 0.f;
+                    for (int it = 0; it < I3; ++it) {
+                        const int g = tid + T * it;
+                        const int kb = (g >> LOG2R2) + 32 * (g & (R2 - 1));
+                        const uint32_t u = (uint32_t)(kb - kpeak + 3) & (uint32_t)(N - 1);
+                        const uint32_t lo = u & (uint32_t)(S - 1);
+                        if (lo < 7u) {
+                            const int k3s = (R3 - (int)(u >> LOG2S)) & (R3 - 1);
+                            float v = 0.f;
 #pragma unroll
-                        for (int k3 = 0; k3 < R3; ++k3) v = (k3 == k3s) ? pw[it][k3] : v;
-                        fs.mags[lo] = sqrtf(v);
+                            for (int k3 = 0; k3 < R3; ++k3) v = (k3 == k3s) ? pw[it][k3] : v;
+                            fs.mags[lo] = sqrtf(v);
+                        }
                     }
                 }
             }
