@@ -34,6 +34,7 @@ HISTORY = 4920
 WINDOW = (7, 110)
 THRESH = (0.0, 15.0, 0.0)
 TEMPLATE_PATH = os.path.join(ROOT, "tests", "golden", "template_example.npy")
+GATHER_EVERY = 8     # steps per all-gather of the record ring (multi-GPU)
 
 
 def workload_name(args):
@@ -217,7 +218,19 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL / c10d print their version banner on stdout when the communicator is created:
+        # send it to stderr so that stdout carries exactly one JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node %d" % args.gpus
 
     n, batch = args.block_len, args.batch
@@ -233,21 +246,25 @@ def run_ours(args):
     reps = (pool_blocks + len(uniq) - 1) // len(uniq)
     pool = uniq_d.repeat(reps, 1)[:pool_blocks].contiguous()
     idx = torch.arange(pool_blocks, dtype=torch.int64, device=dev) + rank * (1 << 40)
-    # two record buffers, alternated: consecutive launches may overlap at their edges (PDL)
-    recs2 = [torch.zeros(batch * 64, dtype=torch.uint8, device=dev) for _ in range(2)]
-    gathered = torch.zeros(world * batch * 64, dtype=torch.uint8, device=dev) if world > 1 else None
+    # ring of record buffers: consecutive launches may overlap at their edges (PDL), so each step
+    # writes its own slot; with several ranks the ring is all-gathered once per GATHER_EVERY steps
+    # (one 2 MiB collective instead of eight 256 KiB ones: NCCL launch latency, not bandwidth, is
+    # what a 64-byte-per-block gather costs)
+    ring = torch.zeros(GATHER_EVERY * batch * 64, dtype=torch.uint8, device=dev)
+    recs2 = [ring[k * batch * 64:(k + 1) * batch * 64] for k in range(GATHER_EVERY)]
+    gathered = torch.zeros(world * GATHER_EVERY * batch * 64, dtype=torch.uint8, device=dev) if world > 1 else None
     # a real (non-legacy) stream: handle 0 would mean "the detector's own stream" to thr_set_stream
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     det.set_stream(stream.cuda_stream)
     n_windows = pool_blocks // batch
 
-    def step(i, gather=True):
+    def step(i, gather=True, last=False):
         w = i % n_windows
-        rec = recs2[i & 1]
+        rec = recs2[i % GATHER_EVERY]
         det.detect_device(pool[w * batch].data_ptr(), idx[w * batch].data_ptr(), batch, rec.data_ptr())
-        if gather and world > 1:
-            dist.all_gather_into_tensor(gathered, rec)
+        if gather and world > 1 and (i % GATHER_EVERY == GATHER_EVERY - 1 or last):
+            dist.all_gather_into_tensor(gathered, ring)
 
     def barrier():
         if world > 1:
@@ -259,7 +276,7 @@ def run_ours(args):
         barrier()
         e0.record(stream)
         for i in range(k):
-            step(i, gather)
+            step(i, gather, last=(i == k - 1))
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
@@ -297,7 +314,7 @@ def run_ours(args):
 
     # records sanity: every block of the last batch must carry a decision
     torch.cuda.synchronize()
-    recs = np.frombuffer(recs2[(args.steps - 1) & 1].cpu().numpy().tobytes(), dtype=RECORD_DTYPE)
+    recs = np.frombuffer(recs2[(args.steps - 1) % GATHER_EVERY].cpu().numpy().tobytes(), dtype=RECORD_DTYPE)
     n_det = int(((recs["flags"] & 2) != 0).sum())
     n_car = int(((recs["flags"] & 1) != 0).sum())
 
@@ -353,7 +370,7 @@ def run_ours(args):
                        "pool_blocks_per_gpu": pool_blocks,
                        "l2_policy": "inputs larger than L2: %d MiB raw pool cycled per GPU" % (pool_blocks * 2 * n >> 20),
                        "kernel": info["kernel"], "grid": info["grid"], "threads": info["threads"],
-                       "smem_bytes": info["smem_bytes"], "parallelism": "stripe%d" % world,
+                       "smem_bytes": info["smem_bytes"], "parallelism": "stripe%d" % world, "record_gather": ("all_gather of the 64-B record ring every %d steps" % GATHER_EVERY) if world > 1 else "none (1 GPU)",
                        "carrier_detected_last_batch": n_car, "corr_detected_last_batch": n_det,
                        "blocks_per_s": world * batch / (ms_per_step * 1e-3)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
