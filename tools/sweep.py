@@ -1,0 +1,91 @@
+#!/usr/bin/env python
+"""Secondary measurements (BASELINE.json configs 3 and 5, signal mixes), device-resident inputs.
+
+    python tools/sweep.py            # prints one JSON line per configuration
+
+Uses only the C ABI (device pool allocated through thr_device_alloc, timing with the library's
+CUDA-event timer on the launch stream).  The headline number is bench.py's; this is the table
+quoted in DESIGN.md section 7."""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from thrifty_b200 import synth  # noqa: E402
+from thrifty_b200._native import NativeDetector, RECORD_DTYPE, load_library  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def run(block_len, templates, history, batch, p_signal, steps=64, warmup=4, window=(7, 110), unique=256,
+        label=""):
+    lib = load_library()
+    tpl0 = templates[0] if templates.ndim == 2 else templates
+    raw, _ = synth.make_blocks(unique, block_len, history, tpl0, p_signal, seed=424242)
+    n_tpl = templates.shape[0] if templates.ndim == 2 else 1
+    det = NativeDetector(block_len, history, templates, len(tpl0), window, (0., 15., 0.), (0., 15., 0.),
+                         max_batch=batch, overlap_launches=True)
+    # pool > L2 (126 MB): at least 160 MiB of raw blocks, a multiple of the batch
+    pool_blocks = max(2 * batch, ((160 << 20) // (2 * block_len) + batch - 1) // batch * batch)
+    host = np.ascontiguousarray(raw[np.arange(pool_blocks) % unique])
+    d_raw = lib.thr_device_alloc(0, host.nbytes)
+    d_out = [lib.thr_device_alloc(0, batch * n_tpl * 64) for _ in range(2)]
+    assert d_raw and all(d_out)
+    assert lib.thr_memcpy_h2d(0, d_raw, host.ctypes.data, host.nbytes) == 0
+    windows = pool_blocks // batch
+
+    def step(i):
+        off = (i % windows) * batch * 2 * block_len
+        det.detect_device(d_raw + off, None, batch, d_out[i & 1])
+
+    for i in range(warmup):
+        step(i)
+    det.synchronize()
+    det.timer_start()
+    for i in range(steps):
+        step(i)
+    ms = det.timer_stop() / steps
+    out = np.zeros(batch * n_tpl, dtype=RECORD_DTYPE)
+    lib.thr_memcpy_d2h(0, out.ctypes.data, d_out[(steps - 1) & 1], out.nbytes)
+    info = det.info()
+    blocks_per_s = batch / (ms * 1e-3)
+    alg = batch * (2 * block_len + 64 * n_tpl)
+    peak = 6533.2
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peak = float(json.load(open(pk))["hbm_gbs"])
+    line = dict(label=label, block_len=block_len, n_templates=n_tpl, batch=batch, p_signal=p_signal,
+                ms_per_launch=ms, blocks_per_s=blocks_per_s, msamples_per_s=blocks_per_s * block_len / 1e6,
+                hbm_gbs_algorithmic=alg / (ms * 1e-3) / 1e9, hbm_frac_of_measured_peak=alg / (ms * 1e-3) / 1e9 / peak,
+                kernel=info["kernel"], grid=info["grid"], threads=info["threads"], ctas_per_sm=info["ctas_per_sm"],
+                smem_bytes=info["smem_bytes"], carrier=int(((out["flags"] & 1) != 0).sum()),
+                detected=int(((out["flags"] & 2) != 0).sum()))
+    print(json.dumps(line), flush=True)
+    for ptr in [d_raw] + d_out:
+        lib.thr_device_free(0, ptr)
+    det.close()
+
+
+def main():
+    example = np.load(os.path.join(GOLDEN, "template_example.npy"))
+    t9, t10 = synth.gold_template(9), synth.gold_template(10)
+    # config 3: block_len sweep, batch 4096, 100 % burst blocks
+    run(4096, t9, len(t9) + 6, 4096, 1.0, label="cfg3 N=4096")
+    run(8192, t10, len(t10) + 6, 4096, 1.0, label="cfg3 N=8192")
+    run(16384, example, 4920, 4096, 1.0, label="cfg3 N=16384 (headline, pruned FFT#1)")
+    run(16384, example, 4920, 4096, 1.0, window=(7, 300), label="N=16384 full FFT#1 (window 7-300)")
+    run(32768, example, 4920, 2048, 1.0, steps=16, label="cfg3 N=32768 (global-scratch variant)")
+    # signal mixes at N=16384
+    run(16384, example, 4920, 4096, 0.5, label="N=16384 50% burst blocks")
+    run(16384, example, 4920, 4096, 0.0, label="N=16384 noise only")
+    # config 5: 4 Gold templates jointly
+    t11 = np.stack([synth.gold_template(11, i) for i in range(4)])
+    run(16384, t11, t11.shape[1] + 6, 4096, 1.0, steps=32, label="cfg5 N=16384, 4 Gold templates")
+
+
+if __name__ == "__main__":
+    main()
