@@ -133,6 +133,21 @@ int thr_detect_batch(thr_detector *det, const uint8_t *raw, const int64_t *block
 int thr_detect_batch_c64(thr_detector *det, const float *iq, const int64_t *block_idx,
                          int64_t n_blocks, thr_record *out);
 
+/* ---- `.card` text ingest (thrifty/block_data.py:101-131 card_reader, fastcard/card_reader.c:22-78) ----
+ * thr_card_scan: host-side line scan of a chunk of `.card` text.  Comment ('#'), blank and the
+ *   'Using Volk machine:' / 'linux;' noise lines are skipped; for each data line
+ *   "<time> <block_idx> <base64>" the two numbers are parsed and the byte offset of the payload is
+ *   returned.  A payload whose length is not 4*ceil(2N/3) is an error (*bad_line = 1-based line number).
+ *   With final_chunk == 0 an unterminated last line is left unconsumed (*consumed = bytes used).
+ * thr_detect_card: scan + copy the text to the device + base64 decode ON THE GPU + detect, pipelined
+ *   in chunks; timestamps / block_idx / out must hold max_blocks entries (out: max_blocks * n_templates). */
+int thr_card_scan(const char *text, size_t len, int32_t block_len, int32_t final_chunk, int64_t max_blocks,
+                  double *timestamps, int64_t *block_idx, int64_t *payload_off, int64_t *n_found,
+                  int64_t *consumed, int64_t *bad_line);
+int thr_detect_card(thr_detector *det, const char *text, size_t len, int32_t final_chunk, int64_t max_blocks,
+                    double *timestamps, int64_t *block_idx, thr_record *out, int64_t *n_blocks,
+                    int64_t *consumed);
+
 /* ---- detection, device-resident buffers (async on the handle's stream) ----
  * n_blocks <= max_batch.  Pointers are device pointers. */
 int thr_detect_batch_device(thr_detector *det, const uint8_t *d_raw, const int64_t *d_block_idx,

@@ -103,6 +103,48 @@ def test_fft_mag_debug_output():
     det.close()
 
 
+def test_card_ingest_gpu_decode():
+    """thr_detect_card: `.card` text scanned on the host, base64 decoded on the GPU == detect_raw."""
+    from thrifty_b200._native import NativeDetector, NativeError
+    from thrifty_b200.detect import Detector
+    for name in ("n4096_gold9", "n16384_example"):
+        cfg, raw, block_idx, ref, _ = parity.load_golden(name)
+        text = io.StringIO()
+        block_data.write_card(text, raw, block_indices=block_idx, t0=1000.0, dt=0.0047767)
+        data = ("linux; GNU C++ version\n" + text.getvalue()).encode()
+        det = NativeDetector(cfg["block_len"], cfg["history_len"], cfg["template"], len(cfg["template"]),
+                             cfg["window"], cfg["cthresh"], cfg["kthresh"], max_batch=20)
+        want = det.detect_raw(raw, block_idx)
+        ts, idx, got, consumed = det.detect_card(data)
+        assert consumed == len(data) and len(ts) == len(raw)
+        np.testing.assert_array_equal(idx, block_idx)
+        np.testing.assert_allclose(ts, 1000.0 + 0.0047767 * np.arange(len(raw)), atol=2e-6)
+        assert got.tobytes() == want.tobytes()            # decoded payloads are bit-identical
+        parity.compare_records(got[:, 0], ref, what=name + "/card")
+        # CRLF line ends and a chunk boundary in the middle of a line
+        crlf = data.replace(b"\n", b"\r\n")
+        cut = len(crlf) // 2 + 123
+        t1, i1, r1, used = det.detect_card(crlf[:cut], final=False)
+        t2, i2, r2, used2 = det.detect_card(crlf[used:], final=True)
+        assert used <= cut and used + used2 == len(crlf)
+        assert np.concatenate([r1, r2]).tobytes() == want.tobytes()
+        # a non-base64 character inside a payload is an error, not silent garbage
+        bad = bytearray(data)
+        bad[len(bad) // 2] = ord("!")
+        with pytest.raises(NativeError):
+            det.detect_card(bytes(bad))
+        det.close()
+    # the Detector front end over a binary stream
+    cfg, raw, block_idx, ref, _ = parity.load_golden("n4096_gold9")
+    text = io.StringIO()
+    block_data.write_card(text, raw, block_indices=block_idx)
+    d = Detector(_settings(cfg), rxid=0, batch=16)
+    results = list(d.detect_card_stream(io.BytesIO(text.getvalue().encode()), chunk_bytes=50000))
+    assert len(results) == len(raw)
+    parity.compare_records(_rows_as_records(_results_to_rows(results)), ref, what="card stream")
+    d.close()
+
+
 def test_cli_card_to_toad(tmp_path):
     """`thrifty_b200 detect x.card -o x.toad` reproduces the reference's .toad lines."""
     cfg, raw, block_idx, ref, lines = parity.load_golden("n4096_gold9")

@@ -178,3 +178,36 @@ def test_gold_templates():
     t = synth.gold_template(9)
     assert len(t) == 1226 and set(np.unique(t)) == {-1.0, 1.0}
     assert len(synth.gold_template(10)) == 2455 and len(synth.gold_template(11)) == 4914
+
+
+def test_card_scan_native():
+    """thr_card_scan (host line scanner of the GPU ingest path) against the reference grammar."""
+    import ctypes
+    from thrifty_b200 import _native
+    lib = _native.load_library()
+    n = 48                                        # 2N = 96 bytes -> 128 base64 characters
+    rng = np.random.default_rng(5)
+    raw = rng.integers(0, 256, size=(4, 2 * n), dtype=np.uint8)
+    buf = io.StringIO()
+    block_data.write_card(buf, raw, block_indices=[7, 8, 20, -3], t0=1000.25, dt=0.5)
+    text = ("Using Volk machine: avx2\n\n" + buf.getvalue()).encode()
+    ts = np.zeros(8); idx = np.zeros(8, dtype=np.int64); off = np.zeros(8, dtype=np.int64)
+    nf, used, bad = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+
+    def scan(data, final, maxb=8):
+        return lib.thr_card_scan(data, len(data), n, final, maxb, ts.ctypes.data, idx.ctypes.data, off.ctypes.data,
+                                 ctypes.byref(nf), ctypes.byref(used), ctypes.byref(bad))
+    assert scan(text, 1) == 0 and nf.value == 4 and used.value == len(text)
+    assert list(idx[:4]) == [7, 8, 20, -3]
+    np.testing.assert_allclose(ts[:4], 1000.25 + 0.5 * np.arange(4))
+    import base64
+    for i in range(4):
+        payload = text[off[i]:off[i] + 128]
+        np.testing.assert_array_equal(np.frombuffer(base64.b64decode(payload), dtype=np.uint8), raw[i])
+    # unterminated last line is left for the next chunk unless final
+    cut = text[:-40]
+    assert scan(cut, 0) == 0 and nf.value == 3 and cut[used.value:].startswith(b"1001.75")
+    assert scan(cut, 1) == -1 and bad.value > 0          # truncated payload at EOF is malformed
+    assert scan(text, 1, maxb=2) == 0 and nf.value == 2   # max_blocks respected
+    assert scan(b"1.0 5 AAAA\n", 1) == -1                 # wrong payload length (card_reader.c:58-66)
+    assert scan(b"garbage line\n", 1) == -1

@@ -59,7 +59,7 @@ EXPORTS = [
     "thr_detect_batch", "thr_detect_batch_c64", "thr_detect_batch_device",
     "thr_detect_batch_device_c64", "thr_detect_block_data", "thr_set_stream", "thr_synchronize",
     "thr_timer_start", "thr_timer_stop", "thr_host_alloc", "thr_host_free", "thr_device_alloc",
-    "thr_device_free", "thr_memcpy_h2d", "thr_memcpy_d2h",
+    "thr_device_free", "thr_memcpy_h2d", "thr_memcpy_d2h", "thr_card_scan", "thr_detect_card",
 ]
 
 _lib = None
@@ -97,6 +97,12 @@ def load_library(path=None):
     lib.thr_detect_block_data.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                                           c_void_p, c_void_p, c_void_p]
     lib.thr_detect_block_data.restype = c_int
+    lib.thr_card_scan.argtypes = [c_char_p, c_size_t, c_int32, c_int32, c_int64, c_void_p, c_void_p, c_void_p,
+                                  POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]
+    lib.thr_card_scan.restype = c_int
+    lib.thr_detect_card.argtypes = [c_void_p, c_char_p, c_size_t, c_int32, c_int64, c_void_p, c_void_p, c_void_p,
+                                    POINTER(c_int64), POINTER(c_int64)]
+    lib.thr_detect_card.restype = c_int
     lib.thr_set_stream.argtypes = [c_void_p, c_void_p]
     lib.thr_set_stream.restype = c_int
     lib.thr_synchronize.argtypes = [c_void_p]
@@ -259,6 +265,26 @@ class NativeDetector(object):
         self._check(self._lib.thr_detect_block_data(self._h, raw_ptr, iq_ptr, int(block_idx), out.ctypes.data,
                                                     sfft.ctypes.data, corr.ctypes.data, mag.ctypes.data))
         return out, sfft, corr, mag
+
+    def detect_card(self, text, final=True, max_blocks=None):
+        """`.card` text (bytes) -> (timestamps f8[B], block_idx i8[B], records [B, n_templates], consumed).
+
+        Lines are scanned on the host, the base64 payloads are decoded on the GPU (thr_detect_card).
+        With final=False an unterminated last line is left for the next call (see `consumed`)."""
+        if not isinstance(text, (bytes, bytearray)):
+            raise TypeError("text must be bytes")
+        line_len = ((2 * self.block_len + 2) // 3) * 4 + 16
+        if max_blocks is None:
+            max_blocks = len(text) // line_len + 1
+        ts = np.zeros(max_blocks, dtype=np.float64)
+        idx = np.zeros(max_blocks, dtype=np.int64)
+        out = np.zeros((max_blocks, self.n_templates), dtype=RECORD_DTYPE)
+        nblk, consumed = c_int64(0), c_int64(0)
+        self._check(self._lib.thr_detect_card(self._h, bytes(text), len(text), 1 if final else 0, max_blocks,
+                                              ts.ctypes.data, idx.ctypes.data, out.ctypes.data,
+                                              byref(nblk), byref(consumed)))
+        n = nblk.value
+        return ts[:n], idx[:n], out[:n], consumed.value
 
     # -- device-buffer API (pointers are integers, e.g. torch.Tensor.data_ptr())
     def detect_device(self, d_raw, d_block_idx, n_blocks, d_out):

@@ -20,6 +20,7 @@
 
 #include "../../include/thrifty_b200.h"
 #include "detect_kernel.cuh"
+#include "card_ingest.cuh"
 
 using thr::DetectParams;
 
@@ -73,6 +74,9 @@ struct Slot {                 // one in-flight chunk of the host-buffer API
     int64_t *d_idx = nullptr;
     thr_record *d_out = nullptr;
     float *d_iq = nullptr;    // complex64 staging (lazily, c64_chunk * N * 8)
+    uint8_t *d_text = nullptr;   // .card text staging (lazily, host_chunk lines)
+    int64_t *d_off = nullptr;    // payload offsets inside d_text
+    size_t text_cap = 0;
 };
 
 }  // namespace
@@ -91,6 +95,7 @@ struct thr_detector {
     float *d_tpl_energy = nullptr;
     float2 *d_scratch = nullptr;
     float2 *d_xsave = nullptr;
+    unsigned int *d_bad = nullptr;       // invalid base64 character counter (.card ingest)
     Slot slot[2];
     int c64_chunk = 0;
     int host_chunk = 0;                  // blocks per pipelined chunk of the host-buffer API
@@ -210,6 +215,8 @@ void thr_destroy(thr_detector *d) {
         cudaFree(s.d_idx);
         cudaFree(s.d_out);
         cudaFree(s.d_iq);
+        cudaFree(s.d_text);
+        cudaFree(s.d_off);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     if (d->own_stream) { cudaStreamSynchronize(d->own_stream); cudaStreamDestroy(d->own_stream); }
@@ -219,6 +226,7 @@ void thr_destroy(thr_detector *d) {
     cudaFree(d->d_tpl_energy);
     cudaFree(d->d_scratch);
     cudaFree(d->d_xsave);
+    cudaFree(d->d_bad);
     delete d;
 }
 
@@ -530,6 +538,124 @@ int thr_detect_block_data(thr_detector *d, const uint8_t *raw, const float *iq, 
     return done(THR_OK);
 #undef CUD
 }
+
+// ---- .card text ingest ------------------------------------------------------------------
+// thrifty/block_data.py:101-131 card_reader / fastcard/card_reader.c:22-78
+static bool starts_with(const char *p, const char *e, const char *lit) {
+    const size_t n = std::strlen(lit);
+    return (size_t)(e - p) >= n && std::memcmp(p, lit, n) == 0;
+}
+
+int thr_card_scan(const char *text, size_t len, int32_t block_len, int32_t final_chunk, int64_t max_blocks,
+                  double *timestamps, int64_t *block_idx, int64_t *payload_off, int64_t *n_found,
+                  int64_t *consumed, int64_t *bad_line) {
+    if (!text || !timestamps || !block_idx || !payload_off || !n_found || !consumed || block_len < 1)
+        return THR_ERR_INVALID;
+    const int64_t want = ((2 * (int64_t)block_len + 2) / 3) * 4;       // base64 characters per payload
+    const char *p = text, *end = text + len;
+    int64_t n = 0, line_no = 0;
+    if (bad_line) *bad_line = -1;
+    while (p < end && n < max_blocks) {
+        const char *nl = (const char *)std::memchr(p, '\n', (size_t)(end - p));
+        if (!nl && !final_chunk) break;                                // incomplete last line: wait for more
+        const char *e = nl ? nl : end;
+        const char *next = nl ? nl + 1 : end;
+        ++line_no;
+        const char *le = e;
+        if (le > p && le[-1] == '\r') --le;
+        if (le == p || *p == '#' || starts_with(p, le, "Using Volk machine:") || starts_with(p, le, "linux;")) {
+            p = next;                                                  // comment / blank / stdout noise
+            continue;
+        }
+        char *q = nullptr;
+        const double ts = std::strtod(p, &q);
+        bool ok = q != p && q < le && *q == ' ';
+        long long idx = 0;
+        if (ok) {
+            const char *r = q + 1;
+            char *q2 = nullptr;
+            idx = std::strtoll(r, &q2, 10);
+            ok = q2 != r && q2 < le && *q2 == ' ';
+            q = q2;
+        }
+        if (ok) ok = (le - (q + 1)) == want;                           // card_reader.c:58-66 length check
+        if (!ok) {
+            if (bad_line) *bad_line = line_no;
+            *n_found = n;
+            *consumed = p - text;
+            return THR_ERR_INVALID;
+        }
+        timestamps[n] = ts;
+        block_idx[n] = idx;
+        payload_off[n] = (q + 1) - text;
+        ++n;
+        p = next;
+    }
+    *n_found = n;
+    *consumed = p - text;
+    return THR_OK;
+}
+
+int thr_detect_card(thr_detector *d, const char *text, size_t len, int32_t final_chunk, int64_t max_blocks,
+                    double *timestamps, int64_t *block_idx, thr_record *out, int64_t *n_blocks,
+                    int64_t *consumed) {
+    if (!d || !text || !timestamps || !block_idx || !out || !n_blocks || !consumed)
+        return d ? fail(d, THR_ERR_INVALID, "null argument") : THR_ERR_INVALID;
+    CU(d, cudaSetDevice(d->device));
+    const int N = d->cfg.block_len, NT = d->cfg.n_templates;
+    const int64_t want = ((2 * (int64_t)N + 2) / 3) * 4;
+    std::vector<int64_t> off((size_t)max_blocks);
+    int64_t bad_line = -1;
+    int rc = thr_card_scan(text, len, N, final_chunk, max_blocks, timestamps, block_idx, off.data(), n_blocks,
+                           consumed, &bad_line);
+    if (rc != THR_OK)
+        return fail(d, rc, ".card data line %lld is malformed (expected '<time> <index> <%lld base64 chars>')",
+                    (long long)bad_line, (long long)want);
+    const int64_t nb_total = *n_blocks;
+    if (!d->d_bad) {
+        CU(d, cudaMalloc(&d->d_bad, sizeof(unsigned int)));
+    }
+    CU(d, cudaMemsetAsync(d->d_bad, 0, sizeof(unsigned int), d->slot[0].stream));
+    CU(d, cudaStreamSynchronize(d->slot[0].stream));
+    const int64_t chunk = d->host_chunk;
+    int c = 0;
+    for (int64_t b0 = 0; b0 < nb_total; b0 += chunk, ++c) {
+        Slot &s = d->slot[c & 1];
+        const int nb = (int)((nb_total - b0) < chunk ? (nb_total - b0) : chunk);
+        // byte range of the text that covers the payloads of this chunk (aligned down to 4)
+        const int64_t t0 = off[b0] & ~(int64_t)3, t1 = off[b0 + nb - 1] + want;
+        const size_t bytes = (size_t)(t1 - t0);
+        if (s.text_cap < bytes + 16) {
+            CU(d, cudaStreamSynchronize(s.stream));
+            cudaFree(s.d_text);
+            s.d_text = nullptr;
+            s.text_cap = bytes + bytes / 4 + 4096;
+            CU(d, cudaMalloc(&s.d_text, s.text_cap));
+        }
+        if (!s.d_off) CU(d, cudaMalloc(&s.d_off, (size_t)d->cfg.max_batch * sizeof(int64_t)));
+        std::vector<int64_t> rel(nb);
+        for (int i = 0; i < nb; ++i) rel[i] = off[b0 + i] - t0;
+        CU(d, cudaMemcpyAsync(s.d_text, text + t0, bytes, cudaMemcpyHostToDevice, s.stream));
+        CU(d, cudaMemcpyAsync(s.d_off, rel.data(), (size_t)nb * sizeof(int64_t), cudaMemcpyHostToDevice, s.stream));
+        CU(d, cudaMemcpyAsync(s.d_idx, block_idx + b0, (size_t)nb * sizeof(int64_t), cudaMemcpyHostToDevice, s.stream));
+        const dim3 grid((unsigned)((want + thr::B64_SEG_CHARS - 1) / thr::B64_SEG_CHARS), (unsigned)nb);
+        thr::b64_decode_kernel<<<grid, thr::B64_THREADS, 0, s.stream>>>(s.d_text, s.d_off, (int)want, 2 * N, s.d_in,
+                                                                       d->d_bad);
+        CU(d, cudaGetLastError());
+        d->launches++;
+        rc = launch(d, s.stream, s.d_in, nullptr, s.d_idx, nb, s.d_out, nullptr, nullptr, nullptr);
+        if (rc != THR_OK) return rc;
+        CU(d, cudaMemcpyAsync(out + (size_t)b0 * NT, s.d_out, (size_t)nb * NT * sizeof(thr_record),
+                              cudaMemcpyDeviceToHost, s.stream));
+        // `rel` is pageable: the copy above was staged before cudaMemcpyAsync returned
+    }
+    unsigned int n_bad = 0;
+    for (auto &s : d->slot) CU(d, cudaStreamSynchronize(s.stream));
+    CU(d, cudaMemcpy(&n_bad, d->d_bad, sizeof n_bad, cudaMemcpyDeviceToHost));
+    if (n_bad) return fail(d, THR_ERR_INVALID, ".card payload contains %u group(s) with non-base64 characters", n_bad);
+    return THR_OK;
+}
+
 
 void *thr_host_alloc(size_t bytes) {
     void *p = nullptr;

@@ -126,6 +126,28 @@ class Detector(object):
             recs = self.native.detect_c64(np.stack(conv), idx)
         return [record_to_result(recs[i, 0], items[i][0], self.rxid) for i in range(len(items))]
 
+    # ---- whole `.card` streams: scan on the host, base64 decode + detect on the GPU
+    def detect_card_stream(self, stream, chunk_bytes=64 << 20):
+        """Yield (detected, DetectionResult) for every data line of a binary `.card` stream.
+
+        Same results as iterating Detector(settings, card_reader(stream)) (block_data.py:101-131),
+        but the text goes to the GPU as is (thr_detect_card): no host-side base64 or rawconv."""
+        pending = b""
+        while True:
+            data = getattr(stream, "read1", stream.read)(chunk_bytes)    # read1: do not stall on live pipes
+            final = len(data) == 0
+            if isinstance(data, str):
+                data = data.encode("ascii")
+            text = pending + data
+            if not text:
+                break
+            ts, idx, recs, consumed = self.native.detect_card(text, final=final)
+            for i in range(len(ts)):
+                yield record_to_result(recs[i, 0], float(ts[i]), self.rxid)
+            pending = text[consumed:]
+            if final:
+                break
+
     # ---- iterator protocol (detect.py:80-91)
     def next(self):
         """Process the next block of data."""
@@ -235,6 +257,9 @@ def detector_cli(detector_class, parser=None, extra_args=None, argv=None):
     parser.add_argument("--batch", dest="batch", type=int, default=256,
                         help="blocks per GPU launch (read-ahead) [default: 256]")
     parser.add_argument("--device", dest="device", type=int, default=0, help="CUDA device ordinal")
+    parser.add_argument("--host-decode", dest="host_decode", action="store_true",
+                        help="decode the .card base64 payloads on the host (reference behaviour) "
+                             "instead of on the GPU")
     group = parser.add_mutually_exclusive_group()
     group.add_argument("-o", "--output", dest="output", type=argparse.FileType("w"),
                        help="Output file (.toad) ('-' for stdout)")
@@ -264,6 +289,9 @@ def detector_cli(detector_class, parser=None, extra_args=None, argv=None):
         kwargs.setdefault("batch", args.batch)
         kwargs.setdefault("device", args.device)
     detections = detector_class(settings, blocks, rxid=config.rxid, **kwargs)
+    if detector_class is Detector and not args.raw and not args.host_decode:
+        # fast path: the `.card` text is decoded on the GPU (same records, same order)
+        detections = detections.detect_card_stream(args.input)
     summary_liner = SummaryLineFormatter(config.sample_rate, config.block_size, add_dt=True)
     for detected, result in detections:
         if detected and output_file is not None:

@@ -70,7 +70,43 @@ def run(block_len, templates, history, batch, p_signal, steps=64, warmup=4, wind
     det.close()
 
 
+def run_card(n_blocks=2048, reps=3):
+    """`.card` text -> records: host scan + GPU base64 decode + detect (thr_detect_card) vs the
+    host-side decode a Python card_reader does (base64.b64decode + detect_raw)."""
+    import base64
+    import io
+    import time
+    from thrifty_b200 import block_data
+    example = np.load(os.path.join(GOLDEN, "template_example.npy"))
+    n, hist = 16384, 4920
+    raw, _ = synth.make_blocks(128, n, hist, example, 1.0, seed=99)
+    raw = raw[np.arange(n_blocks) % 128]
+    buf = io.StringIO()
+    block_data.write_card(buf, raw)
+    text = buf.getvalue().encode()
+    det = NativeDetector(n, hist, example, len(example), (7, 110), (0., 15., 0.), (0., 15., 0.), max_batch=4096)
+    det.detect_card(text)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        ts, idx, recs, used = det.detect_card(text)
+    dt_gpu = (time.perf_counter() - t0) / reps
+    t0 = time.perf_counter()
+    blocks = list(block_data.card_reader(io.BytesIO(text), raw=True))
+    recs2 = det.detect_raw(np.stack([b[2] for b in blocks]), np.array([b[1] for b in blocks]))
+    dt_host = time.perf_counter() - t0
+    assert recs2.tobytes() == recs.tobytes()
+    print(json.dumps(dict(label="card ingest N=16384 (text -> records)", n_blocks=n_blocks, text_mb=len(text) / 1e6,
+                          gpu_decode_blocks_per_s=n_blocks / dt_gpu, gpu_decode_msamples_per_s=n_blocks * n / dt_gpu / 1e6,
+                          gpu_decode_text_gbs=len(text) / dt_gpu / 1e9,
+                          host_decode_blocks_per_s=n_blocks / dt_host,
+                          host_decode_msamples_per_s=n_blocks * n / dt_host / 1e6)), flush=True)
+    det.close()
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "card":
+        run_card()
+        return
     example = np.load(os.path.join(GOLDEN, "template_example.npy"))
     t9, t10 = synth.gold_template(9), synth.gold_template(10)
     # config 3: block_len sweep, batch 4096, 100 % burst blocks
