@@ -148,6 +148,18 @@ int thr_detect_card(thr_detector *det, const char *text, size_t len, int32_t fin
                     double *timestamps, int64_t *block_idx, thr_record *out, int64_t *n_blocks,
                     int64_t *consumed);
 
+/* ---- contiguous raw sample streams (thrifty/block_data.py:70-98 block_reader, fastcard/raw_reader.c:15-46) ----
+ * Block b covers samples [b*(N-H) - H, b*(N-H) + N - H) of the stream; the kernel reads these overlapping
+ * windows in place, so only the N-H new samples of a block are ever copied.  `stream` starts with the H
+ * history samples of block `first_block`; the number of whole blocks found is returned in *n_blocks.
+ * Requires 2*(N-H) to be a multiple of 16 bytes (TMA bulk copy alignment).
+ * The very first block of a capture (history = zeros, not representable as bytes) is handled by the caller
+ * through thr_detect_batch_c64 (thrifty_b200.block_data.block_reader does this). */
+int thr_detect_stream(thr_detector *det, const uint8_t *stream, int64_t n_stream_bytes, int64_t first_block,
+                      thr_record *out, int64_t *n_blocks);
+int thr_detect_stream_device(thr_detector *det, const uint8_t *d_stream, int64_t n_stream_bytes,
+                             const int64_t *d_block_idx, int32_t n_blocks, thr_record *d_out);
+
 /* ---- detection, device-resident buffers (async on the handle's stream) ----
  * n_blocks <= max_batch.  Pointers are device pointers. */
 int thr_detect_batch_device(thr_detector *det, const uint8_t *d_raw, const int64_t *d_block_idx,

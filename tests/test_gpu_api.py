@@ -145,6 +145,42 @@ def test_card_ingest_gpu_decode():
     d.close()
 
 
+def test_raw_stream_front_end():
+    """`--raw` streams: overlapping windows read in place on the GPU == the reference block_reader
+    (block_data.py:70-98) followed by Detector.detect on every block, including block 0."""
+    from thrifty_b200.detect import Detector
+    tpl = synth.gold_template(9)
+    n, hist = 4096, len(tpl) + 6
+    new = n - hist
+    nblk = 41
+    rng = np.random.default_rng(2024)
+    total = nblk * new + 77                              # trailing partial block is dropped
+    x = 0.02 * (rng.standard_normal(total) + 1j * rng.standard_normal(total))
+    pos = 500
+    while pos + len(tpl) < total:                        # a burst every ~1.7 blocks
+        f = rng.uniform(8, 109)
+        t = np.arange(len(tpl))
+        x[pos:pos + len(tpl)] += rng.uniform(0.15, 0.4) * (tpl + 1) / 2 * np.exp(2j * np.pi * f * (pos + t) / n)
+        pos += int(rng.uniform(1.2, 2.2) * new)
+    stream = synth.complex_to_raw(x).tobytes()
+    cfg = dict(block_len=n, history_len=hist, template=tpl, cthresh=(0., 15., 0.), window=(7, 110),
+               kthresh=(0., 15., 0.))
+    st = orc.DetectorSettings(n, hist, len(tpl), (0., 15., 0.), (7, 110), tpl, (0., 15., 0.))
+    odet = orc.Detector(st, rxid=0)
+    ref = np.zeros(nblk, dtype=orc.RECORD_DTYPE)
+    blocks = list(orc.block_reader(io.BytesIO(stream), n, hist))
+    assert len(blocks) == nblk
+    for i, (bi, data) in enumerate(blocks):
+        ref[i] = orc.result_to_row(odet.detect(0.0, bi, data))
+    det = Detector(_settings(cfg), rxid=0, batch=16)
+    results = list(det.detect_raw_stream(io.BytesIO(stream), chunk_blocks=7))
+    assert len(results) == nblk
+    assert [r.block for _, r in results] == list(range(nblk))
+    stats = parity.compare_records(_rows_as_records(_results_to_rows(results)), ref, what="raw stream")
+    assert stats["detected"] >= 10
+    det.close()
+
+
 def test_cli_card_to_toad(tmp_path):
     """`thrifty_b200 detect x.card -o x.toad` reproduces the reference's .toad lines."""
     cfg, raw, block_idx, ref, lines = parity.load_golden("n4096_gold9")

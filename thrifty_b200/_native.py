@@ -60,6 +60,7 @@ EXPORTS = [
     "thr_detect_batch_device_c64", "thr_detect_block_data", "thr_set_stream", "thr_synchronize",
     "thr_timer_start", "thr_timer_stop", "thr_host_alloc", "thr_host_free", "thr_device_alloc",
     "thr_device_free", "thr_memcpy_h2d", "thr_memcpy_d2h", "thr_card_scan", "thr_detect_card",
+    "thr_detect_stream", "thr_detect_stream_device",
 ]
 
 _lib = None
@@ -103,6 +104,10 @@ def load_library(path=None):
     lib.thr_detect_card.argtypes = [c_void_p, c_char_p, c_size_t, c_int32, c_int64, c_void_p, c_void_p, c_void_p,
                                     POINTER(c_int64), POINTER(c_int64)]
     lib.thr_detect_card.restype = c_int
+    lib.thr_detect_stream.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_void_p, POINTER(c_int64)]
+    lib.thr_detect_stream.restype = c_int
+    lib.thr_detect_stream_device.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_void_p]
+    lib.thr_detect_stream_device.restype = c_int
     lib.thr_set_stream.argtypes = [c_void_p, c_void_p]
     lib.thr_set_stream.restype = c_int
     lib.thr_synchronize.argtypes = [c_void_p]
@@ -266,6 +271,19 @@ class NativeDetector(object):
                                                     sfft.ctypes.data, corr.ctypes.data, mag.ctypes.data))
         return out, sfft, corr, mag
 
+    def detect_stream(self, stream, first_block):
+        """Contiguous uint8 I/Q stream that starts with the history of block `first_block`.
+        Returns records [B, n_templates] for the B whole blocks it contains (thr_detect_stream)."""
+        stream = np.ascontiguousarray(stream, dtype=np.uint8)
+        new = 2 * (self.block_len - self.history_len)
+        nblk = (len(stream) - 2 * self.block_len) // new + 1 if len(stream) >= 2 * self.block_len else 0
+        out = np.zeros((max(nblk, 0), self.n_templates), dtype=RECORD_DTYPE)
+        got = c_int64(0)
+        self._check(self._lib.thr_detect_stream(self._h, stream.ctypes.data, len(stream), int(first_block),
+                                                out.ctypes.data, byref(got)))
+        assert got.value == len(out)
+        return out
+
     def detect_card(self, text, final=True, max_blocks=None):
         """`.card` text (bytes) -> (timestamps f8[B], block_idx i8[B], records [B, n_templates], consumed).
 
@@ -276,11 +294,20 @@ class NativeDetector(object):
         line_len = ((2 * self.block_len + 2) // 3) * 4 + 16
         if max_blocks is None:
             max_blocks = len(text) // line_len + 1
+        return self.detect_card_ptr(bytes(text), len(text), final, max_blocks)
+
+    def detect_card_ptr(self, ptr, length, final=True, max_blocks=None):
+        """Same as detect_card for text at a raw address (e.g. a PinnedBuffer: full-speed H2D copies)."""
+        line_len = ((2 * self.block_len + 2) // 3) * 4 + 16
+        if max_blocks is None:
+            max_blocks = length // line_len + 1
         ts = np.zeros(max_blocks, dtype=np.float64)
         idx = np.zeros(max_blocks, dtype=np.int64)
         out = np.zeros((max_blocks, self.n_templates), dtype=RECORD_DTYPE)
         nblk, consumed = c_int64(0), c_int64(0)
-        self._check(self._lib.thr_detect_card(self._h, bytes(text), len(text), 1 if final else 0, max_blocks,
+        if not isinstance(ptr, (bytes, bytearray)):
+            ptr = ctypes.cast(ptr, c_char_p)
+        self._check(self._lib.thr_detect_card(self._h, ptr, length, 1 if final else 0, max_blocks,
                                               ts.ctypes.data, idx.ctypes.data, out.ctypes.data,
                                               byref(nblk), byref(consumed)))
         n = nblk.value

@@ -27,7 +27,8 @@
 namespace thr {
 
 struct DetectParams {
-    const uint8_t *raw;        // [n_blocks][2N] u8 interleaved I,Q (or nullptr)
+    const uint8_t *raw;        // u8 interleaved I,Q: block b starts at raw + b*raw_stride (or nullptr)
+    int64_t raw_stride;        // bytes between block starts: 2N (.card blocks) or 2(N-H) (contiguous stream)
     const float2  *iq;         // [n_blocks][N] complex64 (used when raw == nullptr)
     const int64_t *block_idx;  // [n_blocks] or nullptr (-> 0,1,2..)
     thr_record    *out;        // [n_blocks][n_templates]
@@ -696,7 +697,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
     auto issue_tile = [&](int i) {      // thread 0: TMA bulk copy of block i's raw tile into stage i&1
         const int blk = (int)blockIdx.x + i * (int)gridDim.x;
         mbar_expect_tx(&mbar[i & 1], RAW_BYTES);
-        tma_bulk_g2s(raw_s + (size_t)(i & 1) * RAW_BYTES, p.raw + (size_t)blk * RAW_BYTES, RAW_BYTES, &mbar[i & 1]);
+        tma_bulk_g2s(raw_s + (size_t)(i & 1) * RAW_BYTES, p.raw + (size_t)blk * (size_t)p.raw_stride, RAW_BYTES, &mbar[i & 1]);
     };
     if (use_raw && tid == 0) {
         if (nb > 0) issue_tile(0);

@@ -132,20 +132,83 @@ class Detector(object):
 
         Same results as iterating Detector(settings, card_reader(stream)) (block_data.py:101-131),
         but the text goes to the GPU as is (thr_detect_card): no host-side base64 or rawconv."""
-        pending = b""
+        from thrifty_b200._native import PinnedBuffer
+        line_len = ((2 * self.settings.block_len + 2) // 3) * 4 + 64
+        chunk_bytes = max(int(chunk_bytes), 4 * line_len)
+        buf = PinnedBuffer(chunk_bytes)          # page-locked: the text is DMA'd straight from here
+        view = buf.array
+        fill = 0
+        read_into = getattr(stream, "readinto1", None) or getattr(stream, "readinto", None)
+        try:
+            while True:
+                if read_into is not None:
+                    got = read_into(memoryview(view)[fill:]) or 0
+                else:
+                    data = stream.read(chunk_bytes - fill)
+                    if isinstance(data, str):
+                        data = data.encode("ascii")
+                    got = len(data)
+                    view[fill:fill + got] = np.frombuffer(data, dtype=np.uint8)
+                final = got == 0
+                total = fill + got
+                if total == 0:
+                    break
+                ts, idx, recs, consumed = self.native.detect_card_ptr(buf.ptr, total, final=final)
+                for i in range(len(ts)):
+                    yield record_to_result(recs[i, 0], float(ts[i]), self.rxid)
+                fill = total - consumed
+                if fill:
+                    view[:fill] = view[consumed:total].copy()
+                if final:
+                    break
+                if fill >= chunk_bytes:
+                    raise ValueError(".card line longer than the %d-byte chunk buffer" % chunk_bytes)
+        finally:
+            buf.close()
+
+    # ---- raw sample streams (`thrifty detect --raw`): no host-side re-blocking
+    def detect_raw_stream(self, stream, chunk_blocks=4096):
+        """Yield (detected, DetectionResult) for every block of a raw uint8 I/Q stream
+        (block_data.py:70-98 semantics: block b = H samples of history + N-H new samples; the first
+        block's history is zeros; a trailing partial block is dropped).  The overlapping windows are
+        read in place on the GPU (thr_detect_stream), only new samples are copied."""
+        import time
+        n, h = self.settings.block_len, self.settings.history_len
+        new = 2 * (n - h)
+        read = getattr(stream, "read1", stream.read)
+
+        def read_exact(nbytes):
+            parts, got = [], 0
+            while got < nbytes:
+                data = read(nbytes - got)
+                if not data:
+                    break
+                parts.append(data)
+                got += len(data)
+            return b"".join(parts)
+
+        first = read_exact(new)
+        if len(first) < new:
+            return
+        from thrifty_b200.block_data import raw_to_complex
+        block0 = np.concatenate([np.zeros(h, dtype=np.complex64),
+                                 raw_to_complex(np.frombuffer(first, dtype=np.uint8))])
+        yield self.detect(time.time(), 0, block0)[:2]
+        tail = np.frombuffer(first, dtype=np.uint8)[new - 2 * h:] if h else np.zeros(0, dtype=np.uint8)
+        next_block = 1
         while True:
-            data = getattr(stream, "read1", stream.read)(chunk_bytes)    # read1: do not stall on live pipes
-            final = len(data) == 0
-            if isinstance(data, str):
-                data = data.encode("ascii")
-            text = pending + data
-            if not text:
+            data = read_exact(chunk_blocks * new)
+            nblk = len(data) // new
+            if nblk == 0:
                 break
-            ts, idx, recs, consumed = self.native.detect_card(text, final=final)
-            for i in range(len(ts)):
-                yield record_to_result(recs[i, 0], float(ts[i]), self.rxid)
-            pending = text[consumed:]
-            if final:
+            buf = np.concatenate([tail, np.frombuffer(data[:nblk * new], dtype=np.uint8)])
+            recs = self.native.detect_stream(buf, next_block)
+            now = time.time()
+            for i in range(nblk):
+                yield record_to_result(recs[i, 0], now, self.rxid)
+            tail = buf[len(buf) - 2 * h:] if h else np.zeros(0, dtype=np.uint8)
+            next_block += nblk
+            if len(data) < chunk_blocks * new:
                 break
 
     # ---- iterator protocol (detect.py:80-91)
@@ -292,6 +355,10 @@ def detector_cli(detector_class, parser=None, extra_args=None, argv=None):
     if detector_class is Detector and not args.raw and not args.host_decode:
         # fast path: the `.card` text is decoded on the GPU (same records, same order)
         detections = detections.detect_card_stream(args.input)
+    elif detector_class is Detector and args.raw and not args.host_decode \
+            and (2 * (config.block_size - config.block_history)) % 16 == 0:
+        # fast path: overlapping windows are read in place from the contiguous stream
+        detections = detections.detect_raw_stream(args.input, chunk_blocks=max(args.batch, 1))
     summary_liner = SummaryLineFormatter(config.sample_rate, config.block_size, add_dt=True)
     for detected, result in detections:
         if detected and output_file is not None:
