@@ -71,7 +71,8 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    path = path or LIB_PATH
+    # THRIFTY_B200_LIB: alternative build of the same library (kernel experiments, tools/variants.sh)
+    path = path or os.environ.get("THRIFTY_B200_LIB") or LIB_PATH
     if not os.path.exists(path):
         raise NativeError(
             "libthrifty_b200.so not found at %s: build it (python -c 'import __graft_entry__ as g; "

@@ -24,6 +24,21 @@
 
 #include "../../include/thrifty_b200.h"
 
+// experiment switches (compile-time; defaults are the measured-best configuration)
+#ifndef THR_WL23
+#define THR_WL23 1          // warp-local hand-over between passes 2 and 3 (no CTA barrier)
+#endif
+#ifndef THR_RHO128
+#define THR_RHO128 1        // mix phasor table read two entries per LDS.128 (broadcast)
+#endif
+#ifndef THR_PACKRAW
+#define THR_PACKRAW 1       // rawconv and the Parseval energy on packed FP32x2 instructions
+#endif
+#ifndef THR_ARGMAX1
+#define THR_ARGMAX1 0       // block arg-max with one CTA barrier (per-warp first index) instead of two:
+                            // measured 4 % slower (every warp pays the index scan), kept for reference
+#endif
+
 namespace thr {
 
 struct DetectParams {
@@ -82,6 +97,18 @@ struct Cfg {
     static constexpr int LAUNCH_THREADS = SERVICE ? T + 128 : T;
     static constexpr int MIN_CTAS = T >= 512 ? 1 : (T >= 256 ? 2 : (T >= 128 ? 4 : 8));
     static constexpr int MAX_TPL = 32;               // templates per detector (tail mailbox size)
+    // Passes 2 and 3 both work inside one k1 slab (M consecutive elements).  When every warp owns the
+    // same slabs in both passes the hand-over 2 -> 3 (and 3' -> 2') only needs __syncwarp(): the warps
+    // of a CTA then run the whole stretch  pass 2 -> 3 -> x conj(T) -> 3' -> 2'  without a CTA barrier
+    // and drift apart, so the LDS/STS phases of one warp overlap the FMA phases of another.
+    //   R2 == R3: the natural item order already matches.   T == 512, R2 == 32: pass-3 items are
+    //   re-assigned per warp (P3_REMAP); the template spectrum is stored in the matching order.
+    static constexpr bool P3_REMAP = THR_WL23 && (T_ == 512 && R2 == 32 && R3 == 16);
+    static constexpr bool WL23 = THR_WL23 && (P3_REMAP || (R2 == R3 && I2 == I3));
+    // pass-3 item (row of R3 elements) of thread `tid`, iteration `it`
+    __host__ __device__ static constexpr int p3_item(int tid, int it) {
+        return P3_REMAP ? (((tid >> 5) * I3 + it) << 5) + (tid & 31) : tid + T_ * it;
+    }
     static constexpr size_t smem_bytes() {           // must cover the carve-up in detect_kernel
         return BUF_BYTES + 2 * (size_t)(2 * N) + (size_t)M * 8
                + 2 * 320 + 2 * 32 + 2 * MAX_TPL * 32 + 256 + 512 + 64;
@@ -403,10 +430,17 @@ __device__ __forceinline__ float dirichlet_fit(float y, int lane, const DetectPa
 // 0x4B000000 | b is the float 2^23 + b; subtracting 2^23 is exact, and the fused multiply-add
 // rounds the exact value (b - 127.4f) * 2^-7, which is representable.
 __device__ __forceinline__ float2 rawconv(uint32_t w16) {
+    constexpr float c = -127.4f * 0.0078125f;
+#if THR_PACKRAW
+    const float2 f = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(w16, 0x4B000000u, 0x7650)),
+                                            __uint_as_float(__byte_perm(w16, 0x4B000000u, 0x7651))),
+                                make_float2(-8388608.0f, -8388608.0f));
+    return __ffma2_rn(f, make_float2(0.0078125f, 0.0078125f), make_float2(c, c));
+#else
     const float fx = __uint_as_float(__byte_perm(w16, 0x4B000000u, 0x7650)) - 8388608.0f;
     const float fy = __uint_as_float(__byte_perm(w16, 0x4B000000u, 0x7651)) - 8388608.0f;
-    constexpr float c = -127.4f * 0.0078125f;
     return make_float2(fmaf(fx, 0.0078125f, c), fmaf(fy, 0.0078125f, c));
+#endif
 }
 
 // ------------------------------------------------------------------ named barriers
@@ -467,6 +501,42 @@ __device__ __forceinline__ ArgOut main_argmax(uint32_t vbits, float s0, float s1
         s1 = warp_sum(s1);
     }
     const int w = tid >> 5;
+#if THR_ARGMAX1
+    if (NW <= 16) {
+        // one barrier: every warp resolves the first index of its own maximum, the (value, key) pairs
+        // of the NW warps are then combined by every thread
+        uint32_t key = 0xffffffffu;
+        if (vbits == wmax) key = find_key(wmax);
+        key = __reduce_min_sync(0xffffffffu, key);
+        if ((tid & 31) == 0) {
+            red[w] = wmax;
+            red[48 + w] = key;
+            if (SUMS) {
+                red[16 + w] = __float_as_uint(s0);
+                red[32 + w] = __float_as_uint(s1);
+            }
+        }
+        bar_sync(BAR_MAIN, T);
+        ArgOut r;
+        r.vbits = 0u;
+        r.key = 0xffffffffu;
+        r.s0 = 0.f;
+        r.s1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+            const uint32_t v = red[i], k = red[48 + i];
+            if (v > r.vbits || (v == r.vbits && k < r.key)) {
+                r.vbits = v;
+                r.key = k;
+            }
+            if (SUMS) {
+                r.s0 += __uint_as_float(red[16 + i]);
+                r.s1 += __uint_as_float(red[32 + i]);
+            }
+        }
+        return r;
+    }
+#endif
     if ((tid & 31) == 0) {
         red[w] = wmax;
         if (SUMS) {
@@ -726,14 +796,31 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 for (int n1 = 0; n1 < 32; ++n1) x[brev(n1, 5)] = __ldg(&iqb[n1 * M + j]);
             }
             if (!mix && zoom) {                  // sum |x|^2 (Parseval: sum_k |X[k]|^2 = N sum_n |x[n]|^2)
+#if THR_PACKRAW
+                float2 e2 = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int n1 = 0; n1 < 32; ++n1) e2 = __ffma2_rn(x[n1], x[n1], e2);
+                energy += e2.x + e2.y;
+#else
 #pragma unroll
                 for (int n1 = 0; n1 < 32; ++n1) energy = fmaf(x[n1].x, x[n1].x, fmaf(x[n1].y, x[n1].y, energy));
+#endif
             }
             if (mix) {
                 // row phasor here; the per-thread phasor ph0 is common to the whole item and is
                 // folded into the twiddle seeds below (the DFT is linear)
+#if THR_RHO128
+                const float4 *rho4 = reinterpret_cast<const float4 *>(rho);
+#pragma unroll
+                for (int n1 = 0; n1 < 32; n1 += 2) {
+                    const float4 r = rho4[n1 >> 1];
+                    if (n1 > 0) x[brev(n1, 5)] = cmul(x[brev(n1, 5)], make_float2(r.x, r.y));
+                    x[brev(n1 + 1, 5)] = cmul(x[brev(n1 + 1, 5)], make_float2(r.z, r.w));
+                }
+#else
 #pragma unroll
                 for (int n1 = 1; n1 < 32; ++n1) x[brev(n1, 5)] = cmul(x[brev(n1, 5)], rho[n1]);
+#endif
             }
             fft_dit<32, false>(x);
             // Twiddles W_N^{j k1} are regenerated per block from two per-thread seeds.  The opaque
@@ -803,7 +890,8 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                     st8(ab + 2u * A2_STEP, cmul(b2, tw2[2 * R3 + n3]));
                     st8(ab + 3u * A2_STEP, cmul(b3, tw2[3 * R3 + n3]));
                 }
-                bar_sync(BAR_MAIN, T);
+                if constexpr (C::P3_REMAP) __syncwarp();   // pruned pass 3 reads this warp's own slabs
+                else bar_sync(BAR_MAIN, T);
                 return;
             }
         }
@@ -825,7 +913,8 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                     st8(ab + (uint32_t)k2 * A2_STEP, v);
                 }
             }
-            bar_sync(BAR_MAIN, T);
+            if constexpr (C::WL23) __syncwarp();           // pass 3 reads this warp's own slabs
+            else bar_sync(BAR_MAIN, T);
         }
     };
 
@@ -873,21 +962,35 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 // pass 3 (pruned): X[k1 + 32 k2] = sum_n3 B[k1,k2;n3] for the 128 bins k < 128;
                 // 4 threads per bin, R3/4 terms each, then two shuffles
                 constexpr int PER = R3 / 4;
-#pragma unroll 1
-                for (int pzb = 0; pzb < 128; pzb += T / 4) {
-                    const int pz = pzb + (tid >> 2), sub = tid & 3;
-                    const int k1 = pz & 31, k2 = pz >> 5;
+                if constexpr (C::P3_REMAP) {
+                    // warp w owns slabs k1 = 2w, 2w+1 (written by its own pruned pass 2): 8 bins x 4 lanes
+                    const int k1 = 2 * (tid >> 5) + (lane >> 4), k2 = (lane >> 2) & 3, sub = lane & 3;
                     float2 acc = make_float2(0.f, 0.f);
-                    if (pz < 128) {
 #pragma unroll
-                        for (int t = 0; t < PER; ++t)
-                            acc = f2add(acc, ld8(a2_base(k1, sub * PER + t) + (uint32_t)k2 * A2_STEP));
-                    }
+                    for (int t = 0; t < PER; ++t)
+                        acc = f2add(acc, ld8(a2_base(k1, sub * PER + t) + (uint32_t)k2 * A2_STEP));
                     acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 1);
                     acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 1);
                     acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 2);
                     acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 2);
-                    if (sub == 0 && pz < 128) zpow[k1 + 32 * k2] = acc.x * acc.x + acc.y * acc.y;
+                    if (sub == 0) zpow[k1 + 32 * k2] = acc.x * acc.x + acc.y * acc.y;
+                } else {
+#pragma unroll 1
+                    for (int pzb = 0; pzb < 128; pzb += T / 4) {
+                        const int pz = pzb + (tid >> 2), sub = tid & 3;
+                        const int k1 = pz & 31, k2 = pz >> 5;
+                        float2 acc = make_float2(0.f, 0.f);
+                        if (pz < 128) {
+#pragma unroll
+                            for (int t = 0; t < PER; ++t)
+                                acc = f2add(acc, ld8(a2_base(k1, sub * PER + t) + (uint32_t)k2 * A2_STEP));
+                        }
+                        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 1);
+                        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 1);
+                        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 2);
+                        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 2);
+                        if (sub == 0 && pz < 128) zpow[k1 + 32 * k2] = acc.x * acc.x + acc.y * acc.y;
+                    }
                 }
                 const float wsum = warp_sum(tenergy);
                 if (lane == 0) red[16 + (tid >> 5)] = __float_as_uint(wsum);
@@ -926,7 +1029,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 const bool all_in = (p.win_len >= N);    // default window '0--1': every bin qualifies
     #pragma unroll
                 for (int it = 0; it < I3; ++it) {
-                    const int g = tid + T * it;
+                    const int g = C::p3_item(tid, it);
                     const uint32_t ab = a3_base(g);
                     float2 x[R3];
     #pragma unroll
@@ -967,7 +1070,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                     uint32_t key = 0xffffffffu;
     #pragma unroll
                     for (int it = 0; it < I3; ++it) {
-                        const int g = tid + T * it;
+                        const int g = C::p3_item(tid, it);
                         const int kb = (g >> LOG2R2) + 32 * (g & (R2 - 1));
                         const uint32_t relb = (uint32_t)(kb - p.win_start) & (uint32_t)(N - 1);
     #pragma unroll
@@ -984,7 +1087,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 if (kpeak >= 0) {
 #pragma unroll
                     for (int it = 0; it < I3; ++it) {
-                        const int g = tid + T * it;
+                        const int g = C::p3_item(tid, it);
                         const int kb = (g >> LOG2R2) + 32 * (g & (R2 - 1));
                         const uint32_t u = (uint32_t)(kb - kpeak + 3) & (uint32_t)(N - 1);
                         const uint32_t lo = u & (uint32_t)(S - 1);
@@ -1055,7 +1158,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 const float2 *tsp = p.tpl_spec + (size_t)tpl * N;
 #pragma unroll
                 for (int it = 0; it < I3; ++it) {
-                    const int g = tid + T * it;
+                    const int g = C::p3_item(tid, it);
                     const uint32_t ab = a3_base(g);
                     float2 tv[R3];                                    // template spectrum, issued early
 #pragma unroll
@@ -1088,7 +1191,8 @@ detect_kernel(const __grid_constant__ DetectParams p) {
 #pragma unroll
                     for (int n3 = 0; n3 < R3; ++n3) st8(ab + (uint32_t)n3 * 8u, y[n3]);
                 }
-                bar_sync(BAR_MAIN, T);
+                if constexpr (C::WL23 && R2 > 1) __syncwarp();   // pass 2' reads this warp's own slabs
+                else bar_sync(BAR_MAIN, T);
                 // inverse pass 2': conj twiddle on load, radix-R2 over k2
                 if (R2 > 1) {
 #pragma unroll

@@ -33,6 +33,7 @@ struct Variant {
     int threads;
     bool gmem;
     int r2, r3, i3;
+    int (*p3_item)(int tid, int it);   // pass-3 item owned by (thread, iteration): fixes the template order
     int launch_threads;
     size_t smem;
     const void *fn;
@@ -49,6 +50,7 @@ Variant make_variant(const char *name) {
     v.r2 = C::R2;
     v.r3 = C::R3;
     v.i3 = C::I3;
+    v.p3_item = [](int tid, int it) { return C::p3_item(tid, it); };
     v.launch_threads = C::LAUNCH_THREADS;
     v.smem = C::smem_bytes();
     v.fn = (const void *)&thr::detect_kernel<LOG2N, T, GMEM>;
@@ -58,12 +60,14 @@ Variant make_variant(const char *name) {
 
 bool pick_variant(int n, Variant *out) {
     switch (n) {
+#ifndef THR_ONLY_N16384     // experiment builds (tools/variants.sh) carry the headline size only
         case 1024:  *out = make_variant<10, 32, false>("detect_kernel<N=1024,T=32,smem>"); return true;
         case 2048:  *out = make_variant<11, 64, false>("detect_kernel<N=2048,T=64,smem>"); return true;
         case 4096:  *out = make_variant<12, 128, false>("detect_kernel<N=4096,T=128,smem>"); return true;
         case 8192:  *out = make_variant<13, 256, false>("detect_kernel<N=8192,T=256,smem>"); return true;
-        case 16384: *out = make_variant<14, 512, false>("detect_kernel<N=16384,T=512,smem>"); return true;
         case 32768: *out = make_variant<15, 512, true>("detect_kernel<N=32768,T=512,gmem>"); return true;
+#endif
+        case 16384: *out = make_variant<14, 512, false>("detect_kernel<N=16384,T=512,smem>"); return true;
         default: return false;
     }
 }
@@ -314,7 +318,7 @@ int thr_create(const thr_config *cfg, thr_detector **out) {
             for (int i = 0; i < I3; ++i)
                 for (int k3 = 0; k3 < R3; ++k3)
                     for (int tid = 0; tid < T; ++tid) {
-                        const int g = tid + T * i;
+                        const int g = var.p3_item(tid, i);
                         const int k = (g / R2) + 32 * (g % R2) + 32 * R2 * k3;
                         perm[(size_t)t * N + (size_t)(i * R3 + k3) * T + tid] =
                             make_float2((float)(a[k].real() / N), (float)(-a[k].imag() / N));
