@@ -570,7 +570,8 @@ __device__ __forceinline__ ArgOut main_argmax(uint32_t vbits, float s0, float s1
 // pipeline per CTA:   A(b+1) || fit(b)   ->   B(b) || tail(b-1)
 //   A(b): raw tile -> FFT#1 -> |X|^2, arg-max, carrier decision, 7 magnitudes posted
 //   B(b): mix + FFT#2 -> x conj(T)/N -> IFFT -> |c|^2 arg-max, neighbours posted
-template <int LOG2N, int T, bool GMEM>
+// MULTI = false: exactly one template (no template loop, no X' save area).
+template <int LOG2N, int T, bool GMEM, bool MULTI>
 __global__ void __launch_bounds__(Cfg<LOG2N, T, GMEM>::LAUNCH_THREADS, Cfg<LOG2N, T, GMEM>::MIN_CTAS)
 detect_kernel(const __grid_constant__ DetectParams p) {
     using C = Cfg<LOG2N, T, GMEM>;
@@ -610,12 +611,15 @@ detect_kernel(const __grid_constant__ DetectParams p) {
     off += 512;
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + off);       // 2 barriers
 
-    const bool use_raw = (p.raw != nullptr);
-    const bool dbg = (p.dbg_fft_mag != nullptr) || (p.dbg_shifted_fft != nullptr) || (p.dbg_corr != nullptr);
-    const bool need_std_c = (p.c_std != 0.f);
-    const bool need_std_k = (p.k_std != 0.f);
-    // blocks of this CTA: blockIdx.x + i * gridDim.x, i in [0, nb)
-    const int nb = ((int)blockIdx.x < p.n_blocks) ? (p.n_blocks - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    // Launch-invariant switches are re-read from the kernel parameters (constant bank, uniform
+    // datapath) wherever they are used: held in registers they get spilled, and a spill reload
+    // misses the small L1 that is left next to 207 KB of shared memory (long-scoreboard stalls).
+#define use_raw (p.raw != nullptr)
+#define need_std_c (p.c_std != 0.f)
+#define need_std_k (p.k_std != 0.f)
+    // blocks of this CTA: blockIdx.x + i * gridDim.x for i >= 0 while that is < n_blocks
+    auto has_block = [&](int i) -> bool { return (int)blockIdx.x + i * (int)gridDim.x < p.n_blocks; };
+    const int n_tpl = MULTI ? p.n_templates : 1;
 
     // Launches are independent of each other: let a dependent (next-batch) launch start as soon as
     // SMs drain (no-op unless the launch carries the programmatic-serialization attribute).
@@ -652,7 +656,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
     auto do_tail = [&](int i, int q) {
         const TailHdr &h = tailhdr[q];
         const int blk = (int)blockIdx.x + i * (int)gridDim.x;
-        if (lane < p.n_templates) {
+        if (lane < n_tpl) {
             const int tpl = lane;
             const int64_t bidx = p.block_idx ? p.block_idx[blk] : (int64_t)blk;
             thr_record rec;
@@ -703,7 +707,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 rec.flags = THR_FLAG_CARRIER_DETECTED | (detected ? THR_FLAG_CORR_DETECTED : 0u);
                 rec.signal_energy = sig_energy;
             }
-            p.out[(size_t)blk * p.n_templates + tpl] = rec;
+            p.out[(size_t)blk * n_tpl + tpl] = rec;
         }
     };
 
@@ -712,8 +716,8 @@ detect_kernel(const __grid_constant__ DetectParams p) {
             // service warpgroup: hand registers to the workers; only its first warp works
             asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
             if (tid >= T + 32) return;
-            for (int i = -1; i < nb; ++i) {
-                if (i + 1 < nb) {
+            for (int i = -1; has_block(i < 0 ? 0 : i); ++i) {
+                if (has_block(i + 1)) {
                     const int q = (i + 1) & 1;
                     bar_sync(BAR_FITREQ + q, NTHREADS);               // A(i+1) posted
                     do_fit(q);
@@ -770,8 +774,8 @@ detect_kernel(const __grid_constant__ DetectParams p) {
         tma_bulk_g2s(raw_s + (size_t)(i & 1) * RAW_BYTES, p.raw + (size_t)blk * (size_t)p.raw_stride, RAW_BYTES, &mbar[i & 1]);
     };
     if (use_raw && tid == 0) {
-        if (nb > 0) issue_tile(0);
-        if (nb > 1) issue_tile(1);
+        if (has_block(0)) issue_tile(0);
+        if (has_block(1)) issue_tile(1);
     }
     uint32_t par0 = 0, par1 = 0;    // phase parity of the two tile barriers
 
@@ -850,7 +854,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
         bar_sync(BAR_MAIN, T);
         // after the pass-1 barrier of the mix pass nobody reads this raw stage any more:
         // prefetch the tile of block i+2 into it
-        if (mix && use_raw && tid == 0 && i + 2 < nb) issue_tile(i + 2);
+        if (mix && use_raw && tid == 0 && has_block(i + 2)) issue_tile(i + 2);
         if constexpr (R2 == 32) {
             if (!mix && zoom) {
                 // pruned pass 2: outputs k2 = 0..3 of the 32-point DFT over n2 = 8m + r:
@@ -918,9 +922,9 @@ detect_kernel(const __grid_constant__ DetectParams p) {
         }
     };
 
-    for (int i = -1; i < nb; ++i) {
+    for (int i = -1; has_block(i < 0 ? 0 : i); ++i) {
         // ================================================================= A(i+1): FFT #1
-        if (i + 1 < nb) {
+        if (has_block(i + 1)) {
             const int ia = i + 1, q = ia & 1;
             if (use_raw) {
                 mbar_wait(&mbar[q], q ? par1 : par0);
@@ -1060,7 +1064,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                             if (rel < (uint32_t)p.win_len) bestv = fmaxf(bestv, pw[it][k3]);
                         }
                     }
-                    if (dbg && p.dbg_fft_mag) {
+                    if (p.dbg_fft_mag) {
     #pragma unroll
                         for (int k3 = 0; k3 < R3; ++k3) p.dbg_fft_mag[kb + S * k3] = sqrtf(pw[it][k3]);
                     }
@@ -1128,7 +1132,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
             }
             if (!carrier) {
                 // raw stage i&1 is free (A(i) finished long ago): prefetch block i+2 into it
-                if (use_raw && tid == 0 && i + 2 < nb) issue_tile(i + 2);
+                if (use_raw && tid == 0 && has_block(i + 2)) issue_tile(i + 2);
                 if constexpr (SERVICE) {
                     bar_arrive(BAR_TAILREQ + q, NTHREADS);
                 } else {
@@ -1154,7 +1158,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
             fwd_pass12(i, true, ph0, fs.rho, unused_energy);
 
             // ---- pass 3 of FFT#2, energy of X', then per template: x conj(T)/N and inverse pass 3'
-            for (int tpl = 0; tpl < p.n_templates; ++tpl) {
+            for (int tpl = 0; tpl < n_tpl; ++tpl) {
                 const float2 *tsp = p.tpl_spec + (size_t)tpl * N;
 #pragma unroll
                 for (int it = 0; it < I3; ++it) {
@@ -1168,12 +1172,12 @@ detect_kernel(const __grid_constant__ DetectParams p) {
 #pragma unroll
                         for (int n3 = 0; n3 < R3; ++n3) x[brev(n3, LOG2R3)] = ld8(ab + (uint32_t)n3 * 8u);
                         fft_dit<R3, false>(x);
-                        if (p.n_templates > 1) {
+                        if (MULTI && p.n_templates > 1) {
 #pragma unroll
                             for (int k3 = 0; k3 < R3; ++k3)
                                 p.xsave[(size_t)blockIdx.x * N + (size_t)(it * R3 + k3) * T + tid] = x[k3];
                         }
-                        if (dbg && p.dbg_shifted_fft) {
+                        if (p.dbg_shifted_fft) {
                             const int kb = (g >> LOG2R2) + 32 * (g & (R2 - 1));
 #pragma unroll
                             for (int k3 = 0; k3 < R3; ++k3) p.dbg_shifted_fft[kb + S * k3] = x[k3];
@@ -1261,7 +1265,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                             }
                         }
                     }
-                    if (dbg && p.dbg_corr && tpl == 0) {
+                    if (p.dbg_corr && tpl == 0) {
 #pragma unroll
                         for (int n1 = 0; n1 < 32; ++n1)
                             if (n1 * M + j < p.corr_len) p.dbg_corr[n1 * M + j] = x[n1];
@@ -1316,6 +1320,9 @@ detect_kernel(const __grid_constant__ DetectParams p) {
             }
         }
     }
+#undef use_raw
+#undef need_std_c
+#undef need_std_k
 }
 
 }  // namespace thr

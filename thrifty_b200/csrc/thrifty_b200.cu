@@ -20,57 +20,15 @@
 
 #include "../../include/thrifty_b200.h"
 #include "detect_kernel.cuh"
+#include "variants.h"
 #include "card_ingest.cuh"
 
 using thr::DetectParams;
+using thr::Variant;
 
 namespace {
 
 thread_local std::string g_create_error;
-
-struct Variant {
-    int log2n;
-    int threads;
-    bool gmem;
-    int r2, r3, i3;
-    int (*p3_item)(int tid, int it);   // pass-3 item owned by (thread, iteration): fixes the template order
-    int launch_threads;
-    size_t smem;
-    const void *fn;
-    const char *name;
-};
-
-template <int LOG2N, int T, bool GMEM>
-Variant make_variant(const char *name) {
-    using C = thr::Cfg<LOG2N, T, GMEM>;
-    Variant v;
-    v.log2n = LOG2N;
-    v.threads = T;
-    v.gmem = GMEM;
-    v.r2 = C::R2;
-    v.r3 = C::R3;
-    v.i3 = C::I3;
-    v.p3_item = [](int tid, int it) { return C::p3_item(tid, it); };
-    v.launch_threads = C::LAUNCH_THREADS;
-    v.smem = C::smem_bytes();
-    v.fn = (const void *)&thr::detect_kernel<LOG2N, T, GMEM>;
-    v.name = name;
-    return v;
-}
-
-bool pick_variant(int n, Variant *out) {
-    switch (n) {
-#ifndef THR_ONLY_N16384     // experiment builds (tools/variants.sh) carry the headline size only
-        case 1024:  *out = make_variant<10, 32, false>("detect_kernel<N=1024,T=32,smem>"); return true;
-        case 2048:  *out = make_variant<11, 64, false>("detect_kernel<N=2048,T=64,smem>"); return true;
-        case 4096:  *out = make_variant<12, 128, false>("detect_kernel<N=4096,T=128,smem>"); return true;
-        case 8192:  *out = make_variant<13, 256, false>("detect_kernel<N=8192,T=256,smem>"); return true;
-        case 32768: *out = make_variant<15, 512, true>("detect_kernel<N=32768,T=512,gmem>"); return true;
-#endif
-        case 16384: *out = make_variant<14, 512, false>("detect_kernel<N=16384,T=512,smem>"); return true;
-        default: return false;
-    }
-}
 
 struct Slot {                 // one in-flight chunk of the host-buffer API
     cudaStream_t stream = nullptr;
@@ -240,9 +198,11 @@ int thr_create(const thr_config *cfg, thr_detector **out) {
     *out = nullptr;
     const int N = cfg->block_len, H = cfg->history_len, L = cfg->template_len, NT = cfg->n_templates;
     Variant var;
-    if (!pick_variant(N, &var))
+    if (!thr::pick_variant_single(N, &var))
         return fail(nullptr, THR_ERR_INVALID, "unsupported block_len %d (power of two 1024..32768)", N);
     if (NT < 1 || NT > 32) return fail(nullptr, THR_ERR_INVALID, "n_templates must be 1..32");
+    if (NT > 1 && !thr::pick_variant_multi(N, &var))
+        return fail(nullptr, THR_ERR_INVALID, "no multi-template kernel for block_len %d in this build", N);
     if (!cfg->templates || L < 1 || L > N) return fail(nullptr, THR_ERR_INVALID, "bad template (len %d)", L);
     if (H < L - 1 || H >= N)   // soa_estimator.py:33 assert history_len >= template_len - 1
         return fail(nullptr, THR_ERR_INVALID, "history_len %d must satisfy template_len-1 <= H < block_len", H);
@@ -278,7 +238,7 @@ int thr_create(const thr_config *cfg, thr_detector **out) {
     CUC(cudaSetDevice(d->device));
     cudaDeviceProp prop;
     CUC(cudaGetDeviceProperties(&prop, d->device));
-    std::snprintf(d->device_name, sizeof d->device_name, "%s", prop.name);
+    std::snprintf(d->device_name, sizeof d->device_name, "%.63s", prop.name);
     if (prop.major != 10) {
         fail(d, THR_ERR_NO_DEVICE, "device %d (%s, sm_%d%d) is not sm_100: this library only carries sm_100a code",
              d->device, prop.name, prop.major, prop.minor);

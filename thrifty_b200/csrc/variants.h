@@ -1,0 +1,25 @@
+// variants.h -- table of compiled detect_kernel instantiations (one per block length), built in two
+// translation units so that they compile in parallel: detect_single.cu (one template, no template
+// loop) and detect_multi.cu (several templates per detector).
+#pragma once
+
+#include <stddef.h>
+
+namespace thr {
+
+struct Variant {
+    int log2n;
+    int threads;
+    bool gmem;
+    int r2, r3, i3;
+    int (*p3_item)(int tid, int it);   // pass-3 item owned by (thread, iteration): fixes the template order
+    int launch_threads;
+    size_t smem;
+    const void *fn;
+    const char *name;
+};
+
+bool pick_variant_single(int block_len, Variant *out);   // n_templates == 1
+bool pick_variant_multi(int block_len, Variant *out);    // n_templates >= 1
+
+}  // namespace thr
