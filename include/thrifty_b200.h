@@ -48,6 +48,16 @@ extern "C" {
                                           safe as long as consecutive launches do not write the same output
                                           buffer (alternate two record buffers).                              */
 
+#define THR_CFG_FASTDET_SEMANTICS 2u    /* semantics of the reference's native twin instead of the Python path:
+                                          fastcard/cardet.c:7-41 + fastdet/corr_detector.cpp:88-197.  Decisions
+                                          on powers (threshold = c + s*noise_power, stddev terms must be 0),
+                                          integer-bin carrier shift (the spectrum roll is folded into the
+                                          template: 2 transforms per block instead of 3), 3-point parabolic
+                                          carrier offset (reporting only), Gaussian correlation offset clipped
+                                          to +-0.5, noise clamped at 0, no zero-straddling carrier window, one
+                                          template.  Record fields keep their meaning (magnitudes = sqrt of the
+                                          powers, as fastdet prints them, fastdet.cpp:191-206).               */
+
 /* thr_record.flags */
 #define THR_FLAG_CARRIER_DETECTED 1u   /* carrier peak above threshold (carrier_sync.py:69)      */
 #define THR_FLAG_CORR_DETECTED    2u   /* correlation peak above threshold (soa_estimator.py:85) */

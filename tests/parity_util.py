@@ -96,3 +96,79 @@ def compare_records(got, ref, what=""):
             np.testing.assert_allclose(g["soa"], r["soa"], rtol=0, atol=ATOL_OFFSET, err_msg=tag + " soa")
             stats["max_abs_soa"] = max(stats["max_abs_soa"], abs(float(g["soa"]) - r["soa"]))
     return stats
+
+
+# ------------------------------------------------------------------ fastdet (native twin) semantics
+FASTDET_GOLDEN_NAMES = ["n16384_example", "n8192_gold10_const", "n4096_gold9_negwin", "n4096_gold9_stream",
+                        "n32768_example"]
+
+
+def fastdet_stream_blocks(raw, block_len, history_len):
+    """(stream bytes, blocks) the reference's raw_reader forms from the NEW parts of `raw`
+    (fastcard/raw_reader.c:15-46; the first block's history is uint16 127 per sample, reader.c:56-59)."""
+    new = block_len - history_len
+    stream = np.concatenate([r[2 * history_len:] for r in raw])
+    blocks = np.zeros((len(raw), 2 * block_len), dtype=np.uint8)
+    cur = np.zeros(2 * block_len, dtype=np.uint8)
+    cur[0::2] = 127
+    for b in range(len(raw)):
+        cur = np.concatenate([cur[2 * new:], stream[2 * new * b:2 * new * (b + 1)]])
+        blocks[b] = cur
+    return stream, blocks
+
+
+def load_fastdet_golden(name):
+    """-> (cfg, blocks uint8[B,2N], block_idx, reference records, toad lines, stream or None)."""
+    g = np.load(os.path.join(GOLDEN, "fastdet_%s.npz" % name))
+    cfg = dict(name=name, block_len=int(g["block_len"]), history_len=int(g["history_len"]),
+               template=template_by_id(str(g["template_id"])), window=tuple(int(v) for v in g["window"]),
+               n_blocks=int(g["n_blocks"]), thresh=tuple(float(v) for v in g["thresh"]),
+               corr_thresh=tuple(float(v) for v in g["corr_thresh"]), mode=str(g["mode"]))
+    raw, _ = synth.make_blocks(cfg["n_blocks"], cfg["block_len"], cfg["history_len"], cfg["template"],
+                               float(g["p_signal"]), seed=int(g["seed"]),
+                               bin_range=tuple(float(v) for v in g["bin_range"]))
+    assert np.uint32(zlib.crc32(raw.tobytes())) == g["raw_crc32"], "synthetic generator drifted"
+    stream = None
+    if cfg["mode"] == "raw":
+        stream, raw = fastdet_stream_blocks(raw, cfg["block_len"], cfg["history_len"])
+        block_idx = np.arange(cfg["n_blocks"], dtype=np.int64)
+    else:
+        block_idx = 10 + 3 * np.arange(cfg["n_blocks"], dtype=np.int64)
+    return cfg, raw, block_idx, g["records"], [str(s) for s in g["toad_lines"]], stream
+
+
+def compare_fastdet(got, ref, what="", rtol=RTOL_MAG, atol_off=ATOL_OFFSET):
+    """got: thr_record array [B] from a THR_CFG_FASTDET_SEMANTICS detector; ref: fastdet_oracle
+    REF_RECORD_DTYPE array [B] (powers; thr_record carries their square roots)."""
+    assert len(got) == len(ref)
+    stats = dict(n=len(ref), carrier=0, detected=0, marginal=0, max_rel_power=0.0, max_abs_offset=0.0)
+    for i in range(len(ref)):
+        r, g = ref[i], got[i]
+        tag = "%s block %d" % (what, i)
+        assert int(g["block_idx"]) == int(r["block_idx"]), tag
+        assert bool(g["flags"] & 1) == bool(r["carrier_detected"]), tag + ": carrier flag"
+        if not r["carrier_detected"]:
+            assert not (g["flags"] & 2), tag
+            continue
+        stats["carrier"] += 1
+        assert int(g["carrier_bin"]) == int(r["carrier_argmax"]), tag + ": carrier bin"
+        assert int(g["corr_sample"]) == int(r["corr_peak_idx"]), tag + ": corr sample"
+        marginal = r["corr_threshold"] > 0 and abs(r["corr_peak_power"] / r["corr_threshold"] - 1) < 1e-3
+        if marginal:
+            stats["marginal"] += 1
+        else:
+            assert bool(g["flags"] & 2) == bool(r["corr_detected"]), tag + ": corr flag"
+        for gf, rf in (("carrier_energy", "carrier_max"), ("carrier_noise", "carrier_noise"),
+                       ("corr_energy", "corr_peak_power"), ("corr_noise", "corr_noise_power")):
+            gv, rv = float(g[gf]) ** 2, float(r[rf])
+            rel = abs(gv - rv) / max(abs(rv), 1e-30) if rv != 0 else abs(gv)
+            assert rel <= 2 * rtol, "%s: %s^2 %g vs %g" % (tag, gf, gv, rv)      # squares: twice the magnitude bar
+            stats["max_rel_power"] = max(stats["max_rel_power"], rel)
+        assert abs(float(g["carrier_offset"]) - float(r["carrier_offset"])) <= atol_off, tag + ": carrier offset"
+        if bool(g["flags"] & 2) == bool(r["corr_detected"]):
+            d = abs(float(g["corr_offset"]) - float(r["corr_offset"]))
+            assert d <= atol_off, tag + ": corr offset %g" % d
+            stats["max_abs_offset"] = max(stats["max_abs_offset"], d)
+            assert abs(float(g["soa"]) - float(r["soa"])) <= atol_off, tag + ": soa"
+            stats["detected"] += int(bool(r["corr_detected"]))
+    return stats

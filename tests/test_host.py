@@ -211,3 +211,66 @@ def test_card_scan_native():
     assert scan(text, 1, maxb=2) == 0 and nf.value == 2   # max_blocks respected
     assert scan(b"1.0 5 AAAA\n", 1) == -1                 # wrong payload length (card_reader.c:58-66)
     assert scan(b"garbage line\n", 1) == -1
+
+
+# ---------------------------------------------------------------- fastdet-compatible front end (host parts)
+def test_fastdet_threshold_parser():
+    # fastcard/parse.c:54-99
+    from thrifty_b200 import fastdet
+    assert fastdet.parse_threshold("100c2s") == (100.0, 2.0)
+    assert fastdet.parse_threshold("15s") == (0.0, 15.0)
+    assert fastdet.parse_threshold("2s100c") == (100.0, 2.0)
+    assert fastdet.parse_threshold("42") == (42.0, 0.0)
+    assert fastdet.parse_threshold("1.5e2c") == (150.0, 0.0)
+    for bad in ("1c2c", "1s2s", "3x", "c"):
+        with pytest.raises(ValueError):
+            fastdet.parse_threshold(bad)
+
+
+def test_fastdet_window_parser():
+    # fastcard/parse.c:38-52 (sscanf "%d-%d")
+    from thrifty_b200 import fastdet
+    assert fastdet.parse_carrier_window("7-110") == (7, 110)
+    assert fastdet.parse_carrier_window("0--1") == (0, -1)
+    assert fastdet.parse_carrier_window("-110--7") == (-110, -7)
+    assert fastdet.parse_carrier_window("55") == (55, 55)
+    with pytest.raises(ValueError):
+        fastdet.parse_carrier_window("a-b")
+
+
+def test_fastdet_tpl_round_trip(tmp_path):
+    # fastdet/corr_detector.cpp:200-228, scripts/npy_to_tpl.py:18-22
+    from thrifty_b200 import fastdet
+    tpl = np.load(os.path.join(os.path.dirname(__file__), "golden", "template_example.npy"))
+    path = str(tmp_path / "t.tpl")
+    fastdet.save_template(path, tpl)
+    back = fastdet.load_template(path)
+    assert back.dtype == np.float32 and len(back) == len(tpl)
+    assert np.array_equal(back, tpl.astype(np.float32))
+    assert os.path.getsize(path) == 2 + 4 * len(tpl)
+    with open(path, "r+b") as f:
+        f.truncate(100)
+    with pytest.raises(RuntimeError):
+        fastdet.load_template(path)
+
+
+def test_fastdet_toad_line_matches_native_format():
+    # fastdet/fastdet.cpp:191-206 vs the compiled reference's records (goldens)
+    import parity_util as parity
+    from thrifty_b200 import fastdet
+    from thrifty_b200._native import RECORD_DTYPE
+    cfg, raw, block_idx, ref, toads, _ = parity.load_fastdet_golden("n16384_example")
+    r = ref[ref["corr_detected"] != 0][0]
+    rec = np.zeros((), dtype=RECORD_DTYPE)
+    rec["block_idx"], rec["soa"] = r["block_idx"], r["soa"]
+    rec["corr_sample"], rec["corr_offset"] = r["corr_peak_idx"], r["corr_offset"]
+    rec["corr_energy"], rec["corr_noise"] = np.sqrt(r["corr_peak_power"]), np.sqrt(r["corr_noise_power"])
+    rec["carrier_bin"], rec["carrier_offset"] = r["carrier_argmax"], r["carrier_offset"]
+    rec["carrier_energy"], rec["carrier_noise"] = np.sqrt(r["carrier_max"]), np.sqrt(r["carrier_noise"])
+    rec["flags"] = 3
+    line = fastdet.toad_line(rec, r["ts_sec"] + r["ts_usec"] * 1e-6, 0)
+    mine, gold = line.split(" "), toads[0].split(" ")
+    assert len(mine) == 12 and mine[0] == gold[0] and mine[2] == gold[2] and mine[4] == gold[4] and mine[8 + 0] == gold[8]
+    for a, b in zip(mine[5:], gold[5:]):
+        assert abs(float(a) - float(b)) <= 1e-4 * max(1.0, abs(float(b)))
+    assert "carrier @" in fastdet.info_line(rec, (0., 15.), (0., 15.))

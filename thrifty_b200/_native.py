@@ -162,7 +162,8 @@ class NativeDetector(object):
     """Thin owner of a thr_detector handle."""
 
     def __init__(self, block_len, history_len, templates, carrier_len, carrier_window,
-                 carrier_thresh, corr_thresh, device=0, max_batch=4096, overlap_launches=False):
+                 carrier_thresh, corr_thresh, device=0, max_batch=4096, overlap_launches=False,
+                 fastdet=False):
         self._lib = load_library()
         self._h = c_void_p()
         tpl = np.ascontiguousarray(np.atleast_2d(np.asarray(templates, dtype=np.float64)))
@@ -184,12 +185,15 @@ class NativeDetector(object):
         cfg.corr_thresh = (c_double * 3)(*[float(v) for v in corr_thresh])
         cfg.device = self.device
         cfg.max_batch = self.max_batch
-        cfg.flags = 1 if overlap_launches else 0      # THR_CFG_OVERLAP_LAUNCHES
+        # THR_CFG_OVERLAP_LAUNCHES | THR_CFG_FASTDET_SEMANTICS (the native twin's semantics:
+        # thresholds (constant, snr) apply to POWERS, fastcard/parse.c:54-99 '<c>c<s>s')
+        cfg.flags = (1 if overlap_launches else 0) | (2 if fastdet else 0)
+        self.fastdet = bool(fastdet)
         rc = self._lib.thr_create(byref(cfg), byref(self._h))
         if rc != THR_OK:
             msg = self._lib.thr_last_error(None).decode()
             self._h = c_void_p()
-            if "out of range" in msg and "window" in msg:
+            if ("out of range" in msg and "window" in msg) or "window range not supported" in msg:
                 raise ValueError(msg)            # carrier_detect.py:47-49 raises ValueError
             raise NativeError("thr_create failed (%d): %s" % (rc, msg))
 

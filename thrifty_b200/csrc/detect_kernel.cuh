@@ -63,6 +63,11 @@ struct DetectParams {
     float fit_W;               // carrier_len
     float fit_WoverN;          // W / N
     float fit_invN;            // 1 / N
+    // fastdet-semantics kernels (FASTDET = true) only:
+    const float2 *tpl_shift;   // [win_len][N]: conj(T)[(k - kpeak) mod N]/N per carrier bin of the window, kernel
+                               // order (the integer roll of fastdet/corr_detector.cpp:13-17,179 folded into the
+                               // template), or nullptr -> gather from tpl_nat
+    const float2 *tpl_nat;     // [N] conj(FFT(template))/N in natural order
     float2 *dbg_shifted_fft;   // optional [N], natural order (single-block debug launches)
     float2 *dbg_corr;          // optional [corr_len]
     float  *dbg_fft_mag;       // optional [N]
@@ -571,7 +576,10 @@ __device__ __forceinline__ ArgOut main_argmax(uint32_t vbits, float s0, float s1
 //   A(b): raw tile -> FFT#1 -> |X|^2, arg-max, carrier decision, 7 magnitudes posted
 //   B(b): mix + FFT#2 -> x conj(T)/N -> IFFT -> |c|^2 arg-max, neighbours posted
 // MULTI = false: exactly one template (no template loop, no X' save area).
-template <int LOG2N, int T, bool GMEM, bool MULTI>
+// FASTDET = true: the semantics of the reference's native twin (fastcard + fastdet): decisions on powers,
+// integer-bin carrier shift folded into the template spectrum (so FFT #2 disappears: 2 transforms per
+// block), parabolic carrier offset, +-0.5 clip -- see the FASTDET section below.
+template <int LOG2N, int T, bool GMEM, bool MULTI, bool FASTDET = false>
 __global__ void __launch_bounds__(Cfg<LOG2N, T, GMEM>::LAUNCH_THREADS, Cfg<LOG2N, T, GMEM>::MIN_CTAS)
 detect_kernel(const __grid_constant__ DetectParams p) {
     using C = Cfg<LOG2N, T, GMEM>;
@@ -711,12 +719,74 @@ detect_kernel(const __grid_constant__ DetectParams p) {
         }
     };
 
+    // scalar tail of the fastdet semantics (fastcard/cardet.c:22-40, fastdet/corr_detector.cpp:88-175,
+    // fastdet/fastdet.cpp:184-206).  TailHdr carries POWERS here: peak_mag = max |X|^2, noise_c = noise power,
+    // sig_energy1 = fft_sum / N, pad[0..1] = |X|^2 at the bins next to the peak.
+    auto do_tail_fd = [&](int i, int q) {
+        const TailHdr &h = tailhdr[q];
+        const int blk = (int)blockIdx.x + i * (int)gridDim.x;
+        if (lane == 0) {
+            const int64_t bidx = p.block_idx ? p.block_idx[blk] : (int64_t)blk;
+            thr_record rec;
+            rec.block_idx = bidx;
+            rec.carrier_bin = h.kpeak;
+            rec.carrier_energy = sqrtf(h.peak_mag);                 // fastdet.cpp:204 prints sqrt(max)
+            rec.carrier_noise = sqrtf(h.noise_c);
+            rec.template_idx = 0;
+            rec.reserved = 0.f;
+            rec.signal_energy = h.sig_energy1;
+            if (!h.carrier) {
+                rec.soa = __longlong_as_double(0x7ff8000000000000ll);
+                rec.carrier_offset = 0.f;
+                rec.corr_sample = -1;
+                rec.corr_offset = __int_as_float(0x7fc00000);
+                rec.corr_energy = __int_as_float(0x7fc00000);
+                rec.corr_noise = __int_as_float(0x7fc00000);
+                rec.flags = 0u;
+            } else {
+                // corr_detector.cpp:88-101 parabolic interpolation on sqrt(power), clipped to +-0.5
+                const float ca = sqrtf(h.pad[0]), cb = sqrtf(h.peak_mag), cc = sqrtf(h.pad[1]);
+                const float coff = fminf(fmaxf((cc - ca) / (4.f * cb - 2.f * ca - 2.f * cc), -0.5f), 0.5f);
+                const TailSlot &ts = tailslot[q * C::MAX_TPL];
+                // corr_detector.cpp:118-125: the peak power arrives as size_t (truncated), noise clamped at 0
+                float noise_pw = (h.sig_energy1 * p.tpl_energy[0] - truncf(ts.peak_cp)) / (float)N;
+                noise_pw = noise_pw < 0.f ? 0.f : noise_pw;
+                const float thr_k = p.k_const + p.k_snr * noise_pw;                      // :158
+                const bool detected = ts.peak_cp > thr_k;
+                float offset = 0.f;
+                if (detected && ts.s > 0 && ts.s < p.corr_len - 1) {
+                    // :103-116 Gaussian interpolation on ln sqrt(power), clipped to +-0.5
+                    const float num = logf(ts.pc / ts.pa);
+                    const float den = logf((ts.peak_cp / ts.pa) * (ts.peak_cp / ts.pc));
+                    offset = fminf(fmaxf(0.5f * num / den, -0.5f), 0.5f);
+                }
+                rec.soa = (double)p.new_len * (double)bidx + (double)ts.s + (double)offset;   // fastdet.cpp:184
+                rec.carrier_offset = coff;
+                rec.corr_sample = ts.s;
+                rec.corr_offset = offset;
+                rec.corr_energy = sqrtf(ts.peak_cp);
+                rec.corr_noise = sqrtf(noise_pw);
+                rec.flags = THR_FLAG_CARRIER_DETECTED | (detected ? THR_FLAG_CORR_DETECTED : 0u);
+            }
+            p.out[blk] = rec;
+        }
+    };
+
     if constexpr (SERVICE) {
         if (tid >= T) {
             // service warpgroup: hand registers to the workers; only its first warp works
             asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
             if (tid >= T + 32) return;
-            for (int i = -1; has_block(i < 0 ? 0 : i); ++i) {
+            if constexpr (FASTDET) {
+                for (int i = 0; has_block(i); ++i) {
+                    const int q = i & 1;
+                    bar_sync(BAR_TAILREQ + q, NTHREADS);                  // block i posted
+                    do_tail_fd(i, q);
+                    bar_arrive(BAR_FITDONE + q, NTHREADS);                // mailbox q may be reused
+                }
+                return;
+            }
+            if constexpr (!FASTDET) for (int i = -1; has_block(i < 0 ? 0 : i); ++i) {
                 if (has_block(i + 1)) {
                     const int q = (i + 1) & 1;
                     bar_sync(BAR_FITREQ + q, NTHREADS);               // A(i+1) posted
@@ -782,7 +852,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
     // forward passes 1 and 2 of block i (shared by FFT#1 and FFT#2)
     // zoom (pruned FFT#1): only bins [0,128) are needed, i.e. k3 == 0 and k2 < 4, so pass 2 computes
     // 4 of its R2 outputs and pass 3 degenerates to a sum; the spectrum energy comes from Parseval
-    const bool zoom = (p.zoom != 0) && (p.dbg_fft_mag == nullptr) && (R2 == 32);
+    const bool zoom = !FASTDET && (p.zoom != 0) && (p.dbg_fft_mag == nullptr) && (R2 == 32);
     auto fwd_pass12 = [&](int i, bool mix, const float2 (&ph0)[I1], const float2 *rho, float &energy) {
         const uint16_t *rawt = reinterpret_cast<const uint16_t *>(raw_s + (size_t)(i & 1) * RAW_BYTES);
         const float2 *iqb = use_raw ? nullptr : p.iq + (size_t)((int)blockIdx.x + i * (int)gridDim.x) * N;
@@ -854,7 +924,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
         bar_sync(BAR_MAIN, T);
         // after the pass-1 barrier of the mix pass nobody reads this raw stage any more:
         // prefetch the tile of block i+2 into it
-        if (mix && use_raw && tid == 0 && has_block(i + 2)) issue_tile(i + 2);
+        if ((mix || FASTDET) && use_raw && tid == 0 && has_block(i + 2)) issue_tile(i + 2);
         if constexpr (R2 == 32) {
             if (!mix && zoom) {
                 // pruned pass 2: outputs k2 = 0..3 of the 32-point DFT over n2 = 8m + r:
@@ -922,7 +992,262 @@ detect_kernel(const __grid_constant__ DetectParams p) {
         }
     };
 
-    for (int i = -1; has_block(i < 0 ? 0 : i); ++i) {
+    // ---- correlation stage for one template (soa_estimator.py:97-143): this thread's pass-3 outputs X'
+    // (supplied by get_x) x conj(T)/N -> inverse passes 3', 2', 1' -> |c|^2 windowed arg-max -> TailSlot
+    auto corr_stage = [&](int q, int tpl, auto &&get_tv, auto &&get_x) {
+#pragma unroll
+        for (int it = 0; it < I3; ++it) {
+            const int g = C::p3_item(tid, it);
+            const uint32_t ab = a3_base(g);
+            float2 tv[R3];                                    // template spectrum, issued early
+#pragma unroll
+            for (int k3 = 0; k3 < R3; ++k3) tv[k3] = get_tv(it, g, k3);
+            float2 x[R3];
+            get_x(it, g, ab, x);
+            // multiply by conj(T)/N (soa_estimator.py:99) and run the inverse radix-R3 DFT
+            float2 y[R3];
+#pragma unroll
+            for (int k3 = 0; k3 < R3; ++k3) y[brev(k3, LOG2R3)] = cmul(x[k3], tv[k3]);
+            fft_dit<R3, true>(y);
+#pragma unroll
+            for (int n3 = 0; n3 < R3; ++n3) st8(ab + (uint32_t)n3 * 8u, y[n3]);
+        }
+        if constexpr (C::WL23 && R2 > 1) __syncwarp();   // pass 2' reads this warp's own slabs
+        else bar_sync(BAR_MAIN, T);
+        // inverse pass 2': conj twiddle on load, radix-R2 over k2
+        if (R2 > 1) {
+#pragma unroll
+            for (int it = 0; it < I2; ++it) {
+                const int w = tid + T * it;
+                const int k1 = w >> LOG2R3, n3 = w & (R3 - 1);
+                const uint32_t ab = a2_base(k1, n3);
+                float2 x[R2];
+#pragma unroll
+                for (int k2 = 0; k2 < R2; ++k2) {
+                    float2 v = ld8(ab + (uint32_t)k2 * A2_STEP);
+                    if (k2 > 0) v = cmulc(v, tw2[k2 * R3 + n3]);
+                    x[brev(k2, LOG2R2)] = v;
+                }
+                fft_dit<R2, true>(x);
+#pragma unroll
+                for (int n2 = 0; n2 < R2; ++n2) st8(ab + (uint32_t)n2 * A2_STEP, x[n2]);
+            }
+            bar_sync(BAR_MAIN, T);
+        }
+        // inverse pass 1': conj twiddle on load, radix-32 over k1 -> c[n1*M + j]
+        float cp[I1][32];
+        float c1sum = 0.f, c2sum = 0.f;
+        float cbestv = 0.f;                  // best in-window |c|^2 of this thread
+        uint32_t inmask[I1];                 // bit n1: lag n1*M + j lies in [corr_start, corr_stop)
+#pragma unroll
+        for (int it = 0; it < I1; ++it) {
+            const int j = tid + T * it;
+            const uint32_t ab = a1_base(j);
+            float2 x[32];
+            float2 ws = w1[it], ws4 = w4[it];
+            asm volatile("" : "+f"(ws.x), "+f"(ws.y), "+f"(ws4.x), "+f"(ws4.y));
+            float2 cur[4];
+            cur[0] = ws;
+            cur[1] = cmul(ws, ws);
+            cur[2] = cmul(cur[1], ws);
+            cur[3] = ws4;
+            x[0] = ld8(ab);
+#pragma unroll
+            for (int k1 = 1; k1 < 32; ++k1) {
+                if (k1 > 4) cur[(k1 - 1) & 3] = cmul(cur[(k1 - 1) & 3], ws4);
+                x[brev(k1, 5)] = cmulc(ld8(ab + (uint32_t)k1 * A1_STEP), cur[(k1 - 1) & 3]);
+            }
+            fft_dit<32, true>(x);
+            // |c|^2 and windowed arg-max over [corr_start, corr_stop) (soa_estimator.py:137-143);
+            // n = n1*M + j grows with n1, so '>' keeps the first maximum
+            {
+                // rows n1 in [lo, hi] are inside the window for this thread's column j
+                const int lo = max(0, (p.corr_start - j + M - 1) >> LOG2M);
+                const int hi = min(31, (p.corr_stop - 1 - j) >> LOG2M);    // -1 if j >= corr_stop
+                const uint32_t upto_hi = hi >= 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u);
+                inmask[it] = (hi >= lo) ? (upto_hi & ~((1u << lo) - 1u)) : 0u;
+            }
+#pragma unroll
+            for (int n1 = 0; n1 < 32; ++n1) {
+                const float pv = x[n1].x * x[n1].x + x[n1].y * x[n1].y;
+                cp[it][n1] = pv;
+                if (inmask[it] & (1u << n1)) cbestv = fmaxf(cbestv, pv);
+            }
+            if (need_std_k) {
+#pragma unroll
+                for (int n1 = 0; n1 < 32; ++n1) {
+                    if (n1 * M + j < p.corr_len) {
+                        c1sum += sqrtf(cp[it][n1]);
+                        c2sum += cp[it][n1];
+                    }
+                }
+            }
+            if (p.dbg_corr && tpl == 0) {
+#pragma unroll
+                for (int n1 = 0; n1 < 32; ++n1)
+                    if (n1 * M + j < p.corr_len) p.dbg_corr[n1 * M + j] = x[n1];
+            }
+        }
+        // block arg-max: first maximum of |c|^2 over the window (soa_estimator.py:137-143)
+        auto find_lag = [&](uint32_t gb) {
+            uint32_t key = 0xffffffffu;
+#pragma unroll
+            for (int it = 0; it < I1; ++it) {
+#pragma unroll
+                for (int n1 = 31; n1 >= 0; --n1)
+                    if ((inmask[it] & (1u << n1)) && __float_as_uint(cp[it][n1]) == gb)
+                        key = min(key, (uint32_t)(n1 * M + tid + T * it));
+            }
+            return key;
+        };
+        ArgOut rb;
+        if (need_std_k) rb = main_argmax<T, true>(__float_as_uint(cbestv), c1sum, c2sum, red, tid, find_lag);
+        else rb = main_argmax<T, false>(__float_as_uint(cbestv), 0.f, 0.f, red, tid, find_lag);
+        const int s = (int)rb.key;
+        TailSlot &ts = tailslot[q * C::MAX_TPL + tpl];
+        if (tid == 0) {
+            ts.peak_cp = __uint_as_float(rb.vbits);
+            ts.s = s;
+            ts.c1 = rb.s0;
+            ts.c2 = rb.s1;
+        }
+        // neighbours of the peak for the Gaussian interpolation
+#pragma unroll
+        for (int it = 0; it < I1; ++it) {
+            const int j = tid + T * it;
+#pragma unroll
+            for (int dd = -1; dd <= 1; dd += 2) {
+                const int nt = s + dd;
+                if (nt >= 0 && nt < N && (nt & (M - 1)) == j) {
+                    const int n1s = nt >> LOG2M;
+                    float v = 0.f;
+#pragma unroll
+                    for (int n1 = 0; n1 < 32; ++n1) v = (n1 == n1s) ? cp[it][n1] : v;
+                    if (dd < 0) ts.pa = v; else ts.pc = v;
+                }
+            }
+        }
+    };
+
+    // =====================================================================================
+    // FASTDET: the reference's native semantics (fastcard/fastcard.c:177-189, cardet.c:7-41,
+    // fastdet/corr_detector.cpp:127-197).  Per block: FFT#1 (full) -> |X|^2, sum, windowed arg-max,
+    // power-domain threshold -> X x conj(T)[k - kpeak]/N -> inverse transform -> |c|^2 arg-max -> tail.
+    // The integer roll of the spectrum is a re-indexing of the template, so X never leaves the registers
+    // between the forward pass 3 and the inverse pass 3'.
+    // =====================================================================================
+    if constexpr (FASTDET) {
+        for (int i = 0; has_block(i); ++i) {
+            const int q = i & 1;
+            if (use_raw) {
+                mbar_wait(&mbar[q], q ? par1 : par0);
+                if (q) par1 ^= 1; else par0 ^= 1;
+            }
+            float2 ph_unused[I1];
+#pragma unroll
+            for (int it = 0; it < I1; ++it) ph_unused[it] = make_float2(1.f, 0.f);
+            float tenergy = 0.f;
+            fwd_pass12(i, false, ph_unused, nullptr, tenergy);
+            // pass 3, power spectrum (fastcard.c:180), sum (cardet.c:12) and windowed maximum (cardet.c:15-19)
+            float2 xk[I3][R3];
+            float esum = 0.f, bestv = 0.f;
+            const bool all_in = (p.win_len >= N);
+#pragma unroll
+            for (int it = 0; it < I3; ++it) {
+                const int g = C::p3_item(tid, it);
+                const uint32_t ab = a3_base(g);
+#pragma unroll
+                for (int n3 = 0; n3 < R3; ++n3) xk[it][brev(n3, LOG2R3)] = ld8(ab + (uint32_t)n3 * 8u);
+                fft_dit<R3, false>(xk[it]);
+                const int kb = (g >> LOG2R2) + 32 * (g & (R2 - 1));
+                const uint32_t relb = (uint32_t)(kb - p.win_start) & (uint32_t)(N - 1);
+                const bool item_in = all_in || ((relb & (uint32_t)(S - 1)) < (uint32_t)p.win_len);
+#pragma unroll
+                for (int k3 = 0; k3 < R3; ++k3) {
+                    const float pv = xk[it][k3].x * xk[it][k3].x + xk[it][k3].y * xk[it][k3].y;
+                    esum += pv;
+                    if (item_in) {
+                        const uint32_t rel = (relb + (uint32_t)(S * k3)) & (uint32_t)(N - 1);
+                        if (rel < (uint32_t)p.win_len) bestv = fmaxf(bestv, pv);
+                    }
+                    if (p.dbg_fft_mag) p.dbg_fft_mag[kb + S * k3] = sqrtf(pv);
+                }
+            }
+            const ArgOut ra = main_argmax<T, true>(__float_as_uint(bestv), esum, 0.f, red, tid, [&](uint32_t gb) {
+                uint32_t key = 0xffffffffu;
+#pragma unroll
+                for (int it = 0; it < I3; ++it) {
+                    const int g = C::p3_item(tid, it);
+                    const int kb = (g >> LOG2R2) + 32 * (g & (R2 - 1));
+                    const uint32_t relb = (uint32_t)(kb - p.win_start) & (uint32_t)(N - 1);
+#pragma unroll
+                    for (int k3 = 0; k3 < R3; ++k3) {
+                        const float pv = xk[it][k3].x * xk[it][k3].x + xk[it][k3].y * xk[it][k3].y;
+                        const uint32_t rel = (relb + (uint32_t)(S * k3)) & (uint32_t)(N - 1);
+                        if (rel < (uint32_t)p.win_len && __float_as_uint(pv) == gb) key = min(key, rel);
+                    }
+                }
+                return key;
+            });
+            // cardet.c:21-29: noise power, power-domain threshold
+            const float peak_pw = __uint_as_float(ra.vbits), fsum = ra.s0;
+            const int kpeak = (p.win_start + (int)ra.key) & (N - 1);
+            const float noise_pw = (fsum != 0.f) ? (fsum - 2.f * peak_pw) / (float)(N - 1) : 0.f;
+            const bool carrier = peak_pw > p.c_const + p.c_snr * noise_pw;
+            // mailbox q was last used by block i-2: wait until its tail has been written out
+            if constexpr (SERVICE) {
+                if (i >= 2) bar_sync(BAR_FITDONE + q, NTHREADS);
+            }
+            TailHdr &h = tailhdr[q];
+            if (tid == 0) {
+                h.kpeak = kpeak;
+                h.carrier = carrier ? 1 : 0;
+                h.peak_mag = peak_pw;
+                h.noise_c = noise_pw;
+                h.sig_energy1 = fsum / (float)N;          // corr_detector.cpp:184
+                h.delta = 0.f;
+            }
+            if (carrier) {
+                // |X|^2 next to the peak for the parabolic carrier offset (corr_detector.cpp:191)
+#pragma unroll
+                for (int it = 0; it < I3; ++it) {
+                    const int g = C::p3_item(tid, it);
+                    const int kb = (g >> LOG2R2) + 32 * (g & (R2 - 1));
+                    const uint32_t u = (uint32_t)(kb - kpeak + 1) & (uint32_t)(N - 1);
+                    const uint32_t lo = u & (uint32_t)(S - 1);
+                    if (lo < 3u && lo != 1u) {
+                        const int k3s = (R3 - (int)(u >> LOG2S)) & (R3 - 1);
+                        float v = 0.f;
+#pragma unroll
+                        for (int k3 = 0; k3 < R3; ++k3)
+                            v = (k3 == k3s) ? xk[it][k3].x * xk[it][k3].x + xk[it][k3].y * xk[it][k3].y : v;
+                        h.pad[lo >> 1] = v;
+                    }
+                }
+                const int rel = (int)ra.key;
+                const float2 *tsp = p.tpl_shift ? p.tpl_shift + (size_t)rel * N : nullptr;
+                corr_stage(q, 0,
+                           [&](int it, int g, int k3) {
+                               if (tsp) return __ldg(&tsp[(size_t)(it * R3 + k3) * T + tid]);
+                               const int k = (g >> LOG2R2) + 32 * (g & (R2 - 1)) + S * k3;
+                               return __ldg(&p.tpl_nat[(k - kpeak) & (N - 1)]);
+                           },
+                           [&](int it, int, uint32_t, float2 (&x)[R3]) {
+#pragma unroll
+                               for (int k3 = 0; k3 < R3; ++k3) x[k3] = xk[it][k3];
+                           });
+            }
+            if constexpr (SERVICE) {
+                bar_arrive(BAR_TAILREQ + q, NTHREADS);
+            } else {
+                bar_sync(BAR_MAIN, T);
+                if (tid < 32) do_tail_fd(i, q);
+            }
+        }
+        return;
+    }
+
+    if constexpr (!FASTDET) for (int i = -1; has_block(i < 0 ? 0 : i); ++i) {
         // ================================================================= A(i+1): FFT #1
         if (has_block(i + 1)) {
             const int ia = i + 1, q = ia & 1;
@@ -1157,159 +1482,31 @@ detect_kernel(const __grid_constant__ DetectParams p) {
             float unused_energy = 0.f;
             fwd_pass12(i, true, ph0, fs.rho, unused_energy);
 
-            // ---- pass 3 of FFT#2, energy of X', then per template: x conj(T)/N and inverse pass 3'
+            // ---- pass 3 of FFT#2, then per template: x conj(T)/N and the inverse transform
             for (int tpl = 0; tpl < n_tpl; ++tpl) {
                 const float2 *tsp = p.tpl_spec + (size_t)tpl * N;
+                corr_stage(q, tpl, [&](int it, int, int k3) { return __ldg(&tsp[(size_t)(it * R3 + k3) * T + tid]); },
+                           [&](int it, int g, uint32_t ab, float2 (&x)[R3]) {
+                if (tpl == 0) {
 #pragma unroll
-                for (int it = 0; it < I3; ++it) {
-                    const int g = C::p3_item(tid, it);
-                    const uint32_t ab = a3_base(g);
-                    float2 tv[R3];                                    // template spectrum, issued early
-#pragma unroll
-                    for (int k3 = 0; k3 < R3; ++k3) tv[k3] = __ldg(&tsp[(size_t)(it * R3 + k3) * T + tid]);
-                    float2 x[R3];
-                    if (tpl == 0) {
-#pragma unroll
-                        for (int n3 = 0; n3 < R3; ++n3) x[brev(n3, LOG2R3)] = ld8(ab + (uint32_t)n3 * 8u);
-                        fft_dit<R3, false>(x);
-                        if (MULTI && p.n_templates > 1) {
-#pragma unroll
-                            for (int k3 = 0; k3 < R3; ++k3)
-                                p.xsave[(size_t)blockIdx.x * N + (size_t)(it * R3 + k3) * T + tid] = x[k3];
-                        }
-                        if (p.dbg_shifted_fft) {
-                            const int kb = (g >> LOG2R2) + 32 * (g & (R2 - 1));
-#pragma unroll
-                            for (int k3 = 0; k3 < R3; ++k3) p.dbg_shifted_fft[kb + S * k3] = x[k3];
-                        }
-                    } else {
+                    for (int n3 = 0; n3 < R3; ++n3) x[brev(n3, LOG2R3)] = ld8(ab + (uint32_t)n3 * 8u);
+                    fft_dit<R3, false>(x);
+                    if (MULTI && p.n_templates > 1) {
 #pragma unroll
                         for (int k3 = 0; k3 < R3; ++k3)
-                            x[k3] = p.xsave[(size_t)blockIdx.x * N + (size_t)(it * R3 + k3) * T + tid];
+                            p.xsave[(size_t)blockIdx.x * N + (size_t)(it * R3 + k3) * T + tid] = x[k3];
                     }
-                    // multiply by conj(T)/N (soa_estimator.py:99) and run the inverse radix-R3 DFT
-                    float2 y[R3];
+                    if (p.dbg_shifted_fft) {
+                        const int kb = (g >> LOG2R2) + 32 * (g & (R2 - 1));
 #pragma unroll
-                    for (int k3 = 0; k3 < R3; ++k3) y[brev(k3, LOG2R3)] = cmul(x[k3], tv[k3]);
-                    fft_dit<R3, true>(y);
+                        for (int k3 = 0; k3 < R3; ++k3) p.dbg_shifted_fft[kb + S * k3] = x[k3];
+                    }
+                } else {
 #pragma unroll
-                    for (int n3 = 0; n3 < R3; ++n3) st8(ab + (uint32_t)n3 * 8u, y[n3]);
+                    for (int k3 = 0; k3 < R3; ++k3)
+                        x[k3] = p.xsave[(size_t)blockIdx.x * N + (size_t)(it * R3 + k3) * T + tid];
                 }
-                if constexpr (C::WL23 && R2 > 1) __syncwarp();   // pass 2' reads this warp's own slabs
-                else bar_sync(BAR_MAIN, T);
-                // inverse pass 2': conj twiddle on load, radix-R2 over k2
-                if (R2 > 1) {
-#pragma unroll
-                    for (int it = 0; it < I2; ++it) {
-                        const int w = tid + T * it;
-                        const int k1 = w >> LOG2R3, n3 = w & (R3 - 1);
-                        const uint32_t ab = a2_base(k1, n3);
-                        float2 x[R2];
-#pragma unroll
-                        for (int k2 = 0; k2 < R2; ++k2) {
-                            float2 v = ld8(ab + (uint32_t)k2 * A2_STEP);
-                            if (k2 > 0) v = cmulc(v, tw2[k2 * R3 + n3]);
-                            x[brev(k2, LOG2R2)] = v;
-                        }
-                        fft_dit<R2, true>(x);
-#pragma unroll
-                        for (int n2 = 0; n2 < R2; ++n2) st8(ab + (uint32_t)n2 * A2_STEP, x[n2]);
-                    }
-                    bar_sync(BAR_MAIN, T);
-                }
-                // inverse pass 1': conj twiddle on load, radix-32 over k1 -> c[n1*M + j]
-                float cp[I1][32];
-                float c1sum = 0.f, c2sum = 0.f;
-                float cbestv = 0.f;                  // best in-window |c|^2 of this thread
-                uint32_t inmask[I1];                 // bit n1: lag n1*M + j lies in [corr_start, corr_stop)
-#pragma unroll
-                for (int it = 0; it < I1; ++it) {
-                    const int j = tid + T * it;
-                    const uint32_t ab = a1_base(j);
-                    float2 x[32];
-                    float2 ws = w1[it], ws4 = w4[it];
-                    asm volatile("" : "+f"(ws.x), "+f"(ws.y), "+f"(ws4.x), "+f"(ws4.y));
-                    float2 cur[4];
-                    cur[0] = ws;
-                    cur[1] = cmul(ws, ws);
-                    cur[2] = cmul(cur[1], ws);
-                    cur[3] = ws4;
-                    x[0] = ld8(ab);
-#pragma unroll
-                    for (int k1 = 1; k1 < 32; ++k1) {
-                        if (k1 > 4) cur[(k1 - 1) & 3] = cmul(cur[(k1 - 1) & 3], ws4);
-                        x[brev(k1, 5)] = cmulc(ld8(ab + (uint32_t)k1 * A1_STEP), cur[(k1 - 1) & 3]);
-                    }
-                    fft_dit<32, true>(x);
-                    // |c|^2 and windowed arg-max over [corr_start, corr_stop) (soa_estimator.py:137-143);
-                    // n = n1*M + j grows with n1, so '>' keeps the first maximum
-                    {
-                        // rows n1 in [lo, hi] are inside the window for this thread's column j
-                        const int lo = max(0, (p.corr_start - j + M - 1) >> LOG2M);
-                        const int hi = min(31, (p.corr_stop - 1 - j) >> LOG2M);    // -1 if j >= corr_stop
-                        const uint32_t upto_hi = hi >= 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u);
-                        inmask[it] = (hi >= lo) ? (upto_hi & ~((1u << lo) - 1u)) : 0u;
-                    }
-#pragma unroll
-                    for (int n1 = 0; n1 < 32; ++n1) {
-                        const float pv = x[n1].x * x[n1].x + x[n1].y * x[n1].y;
-                        cp[it][n1] = pv;
-                        if (inmask[it] & (1u << n1)) cbestv = fmaxf(cbestv, pv);
-                    }
-                    if (need_std_k) {
-#pragma unroll
-                        for (int n1 = 0; n1 < 32; ++n1) {
-                            if (n1 * M + j < p.corr_len) {
-                                c1sum += sqrtf(cp[it][n1]);
-                                c2sum += cp[it][n1];
-                            }
-                        }
-                    }
-                    if (p.dbg_corr && tpl == 0) {
-#pragma unroll
-                        for (int n1 = 0; n1 < 32; ++n1)
-                            if (n1 * M + j < p.corr_len) p.dbg_corr[n1 * M + j] = x[n1];
-                    }
-                }
-                // block arg-max: first maximum of |c|^2 over the window (soa_estimator.py:137-143)
-                auto find_lag = [&](uint32_t gb) {
-                    uint32_t key = 0xffffffffu;
-#pragma unroll
-                    for (int it = 0; it < I1; ++it) {
-#pragma unroll
-                        for (int n1 = 31; n1 >= 0; --n1)
-                            if ((inmask[it] & (1u << n1)) && __float_as_uint(cp[it][n1]) == gb)
-                                key = min(key, (uint32_t)(n1 * M + tid + T * it));
-                    }
-                    return key;
-                };
-                ArgOut rb;
-                if (need_std_k) rb = main_argmax<T, true>(__float_as_uint(cbestv), c1sum, c2sum, red, tid, find_lag);
-                else rb = main_argmax<T, false>(__float_as_uint(cbestv), 0.f, 0.f, red, tid, find_lag);
-                const int s = (int)rb.key;
-                TailSlot &ts = tailslot[q * C::MAX_TPL + tpl];
-                if (tid == 0) {
-                    ts.peak_cp = __uint_as_float(rb.vbits);
-                    ts.s = s;
-                    ts.c1 = rb.s0;
-                    ts.c2 = rb.s1;
-                }
-                // neighbours of the peak for the Gaussian interpolation
-#pragma unroll
-                for (int it = 0; it < I1; ++it) {
-                    const int j = tid + T * it;
-#pragma unroll
-                    for (int dd = -1; dd <= 1; dd += 2) {
-                        const int nt = s + dd;
-                        if (nt >= 0 && nt < N && (nt & (M - 1)) == j) {
-                            const int n1s = nt >> LOG2M;
-                            float v = 0.f;
-#pragma unroll
-                            for (int n1 = 0; n1 < 32; ++n1) v = (n1 == n1s) ? cp[it][n1] : v;
-                            if (dd < 0) ts.pa = v; else ts.pc = v;
-                        }
-                    }
-                }
+                });
                 // next template reuses the FFT buffer: all pass-1' loads are done (reduction barriers)
             }
             if constexpr (SERVICE) {

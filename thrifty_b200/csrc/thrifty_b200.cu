@@ -54,6 +54,8 @@ struct thr_detector {
     cudaStream_t stream = nullptr;       // stream used by the *_device entry points
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float2 *d_tpl = nullptr;
+    float2 *d_tpl_shift = nullptr;       // fastdet semantics: per-carrier-bin shifted template spectra
+    float2 *d_tpl_nat = nullptr;         // fastdet semantics: template spectrum in natural order
     float *d_tpl_energy = nullptr;
     float2 *d_scratch = nullptr;
     float2 *d_xsave = nullptr;
@@ -186,6 +188,8 @@ void thr_destroy(thr_detector *d) {
     if (d->ev0) cudaEventDestroy(d->ev0);
     if (d->ev1) cudaEventDestroy(d->ev1);
     cudaFree(d->d_tpl);
+    cudaFree(d->d_tpl_shift);
+    cudaFree(d->d_tpl_nat);
     cudaFree(d->d_tpl_energy);
     cudaFree(d->d_scratch);
     cudaFree(d->d_xsave);
@@ -208,7 +212,18 @@ int thr_create(const thr_config *cfg, thr_detector **out) {
         return fail(nullptr, THR_ERR_INVALID, "history_len %d must satisfy template_len-1 <= H < block_len", H);
     if (cfg->carrier_len < 1) return fail(nullptr, THR_ERR_INVALID, "carrier_len must be positive");
     if (cfg->max_batch < 1) return fail(nullptr, THR_ERR_INVALID, "max_batch must be positive");
-    if (cfg->flags & ~THR_CFG_OVERLAP_LAUNCHES) return fail(nullptr, THR_ERR_INVALID, "unknown flags 0x%x", cfg->flags);
+    if (cfg->flags & ~(THR_CFG_OVERLAP_LAUNCHES | THR_CFG_FASTDET_SEMANTICS))
+        return fail(nullptr, THR_ERR_INVALID, "unknown flags 0x%x", cfg->flags);
+    const bool fastdet = (cfg->flags & THR_CFG_FASTDET_SEMANTICS) != 0;
+    if (fastdet) {
+        if (NT != 1) return fail(nullptr, THR_ERR_INVALID, "fastdet semantics take exactly one template");
+        if (cfg->carrier_thresh[2] != 0.0 || cfg->corr_thresh[2] != 0.0)
+            return fail(nullptr, THR_ERR_INVALID, "fastdet semantics have no stddev threshold term");
+        if (cfg->window_start < 0 && cfg->window_stop >= 0)   // fastcard/cardet.c:44-48
+            return fail(nullptr, THR_ERR_INVALID, "Carrier frequency window range not supported.");
+        if (!thr::pick_variant_fastdet(N, &var))
+            return fail(nullptr, THR_ERR_INVALID, "no fastdet-semantics kernel for block_len %d in this build", N);
+    }
     int ws, we;
     if (!range_index(cfg->window_start, cfg->window_stop, N, &ws, &we))   // carrier_detect.py:47-49
         return fail(nullptr, THR_ERR_INVALID, "Frequency window out of range: %d - %d", cfg->window_start,
@@ -284,6 +299,30 @@ int thr_create(const thr_config *cfg, thr_detector **out) {
                             make_float2((float)(a[k].real() / N), (float)(-a[k].imag() / N));
                     }
         }
+        if (fastdet) {
+            // a is still FFT(template 0): natural-order conj/N, and one pre-rolled copy per carrier bin of the
+            // window in kernel order (fastdet/corr_detector.cpp:13-17,179: roll(fft, -argmax) == re-index T)
+            const int wlen = (we - ws + 1) > N ? N : (we - ws + 1);
+            std::vector<float2> nat(N);
+            for (int k = 0; k < N; ++k) nat[k] = make_float2((float)(a[k].real() / N), (float)(-a[k].imag() / N));
+            CUC(cudaMalloc(&d->d_tpl_nat, nat.size() * sizeof(float2)));
+            CUC(cudaMemcpy(d->d_tpl_nat, nat.data(), nat.size() * sizeof(float2), cudaMemcpyHostToDevice));
+            if ((size_t)wlen * N * sizeof(float2) <= ((size_t)256 << 20)) {
+                std::vector<float2> sh((size_t)wlen * N);
+                for (int r = 0; r < wlen; ++r) {
+                    const int kpeak = (ws + r) % N;
+                    for (int i = 0; i < I3; ++i)
+                        for (int k3 = 0; k3 < R3; ++k3)
+                            for (int tid = 0; tid < T; ++tid) {
+                                const int g = var.p3_item(tid, i);
+                                const int k = (g / R2) + 32 * (g % R2) + 32 * R2 * k3;
+                                sh[(size_t)r * N + (size_t)(i * R3 + k3) * T + tid] = nat[(k - kpeak + N) % N];
+                            }
+                }
+                CUC(cudaMalloc(&d->d_tpl_shift, sh.size() * sizeof(float2)));
+                CUC(cudaMemcpy(d->d_tpl_shift, sh.data(), sh.size() * sizeof(float2), cudaMemcpyHostToDevice));
+            }
+        }
         CUC(cudaMalloc(&d->d_tpl, perm.size() * sizeof(float2)));
         CUC(cudaMemcpy(d->d_tpl, perm.data(), perm.size() * sizeof(float2), cudaMemcpyHostToDevice));
         CUC(cudaMalloc(&d->d_tpl_energy, NT * sizeof(float)));
@@ -307,12 +346,14 @@ int thr_create(const thr_config *cfg, thr_detector **out) {
     p.n_templates = NT;
     p.tpl_spec = d->d_tpl;
     p.tpl_energy = d->d_tpl_energy;
+    p.tpl_shift = d->d_tpl_shift;
+    p.tpl_nat = d->d_tpl_nat;
     p.scratch = d->d_scratch;
     p.xsave = d->d_xsave;
     p.win_start = ws % N;
     p.win_len = (we - ws + 1) > N ? N : (we - ws + 1);
     // pruned FFT#1: every window bin and its +-3 fit neighbours inside [0,128), no stddev term
-    p.zoom = (ws >= 3 && we + 3 < 128 && we < N && cfg->carrier_thresh[2] == 0.0 && N >= 16384) ? 1 : 0;
+    p.zoom = (!fastdet && ws >= 3 && we + 3 < 128 && we < N && cfg->carrier_thresh[2] == 0.0 && N >= 16384) ? 1 : 0;
     p.c_const = (float)cfg->carrier_thresh[0];
     p.c_snr = (float)cfg->carrier_thresh[1];
     p.c_std = (float)cfg->carrier_thresh[2];

@@ -1,6 +1,6 @@
 // variants.h -- table of compiled detect_kernel instantiations (one per block length), built in two
 // translation units so that they compile in parallel: detect_single.cu (one template, no template
-// loop) and detect_multi.cu (several templates per detector).
+// loop), detect_multi.cu (several templates per detector), detect_fastdet.cu (native-twin semantics).
 #pragma once
 
 #include <stddef.h>
@@ -21,5 +21,6 @@ struct Variant {
 
 bool pick_variant_single(int block_len, Variant *out);   // n_templates == 1
 bool pick_variant_multi(int block_len, Variant *out);    // n_templates >= 1
+bool pick_variant_fastdet(int block_len, Variant *out);  // fastdet semantics (one template)
 
 }  // namespace thr

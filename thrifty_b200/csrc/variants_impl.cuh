@@ -1,8 +1,13 @@
-// variants_impl.cuh -- included by detect_single.cu / detect_multi.cu with THR_MULTI defined to 0 / 1.
+// variants_impl.cuh -- included by detect_single.cu / detect_multi.cu / detect_fastdet.cu with THR_MULTI
+// (and THR_FASTDET) defined.
 #pragma once
 
 #include "detect_kernel.cuh"
 #include "variants.h"
+
+#ifndef THR_FASTDET
+#define THR_FASTDET 0
+#endif
 
 namespace thr {
 
@@ -19,12 +24,18 @@ static Variant make_variant(const char *name) {
     v.p3_item = [](int tid, int it) { return C::p3_item(tid, it); };
     v.launch_threads = C::LAUNCH_THREADS;
     v.smem = C::smem_bytes();
-    v.fn = (const void *)&detect_kernel<LOG2N, T, GMEM, (THR_MULTI != 0)>;
+    v.fn = (const void *)&detect_kernel<LOG2N, T, GMEM, (THR_MULTI != 0), (THR_FASTDET != 0)>;
     v.name = name;
     return v;
 }
 
-#if THR_MULTI
+#ifndef THR_FASTDET
+#define THR_FASTDET 0
+#endif
+#if THR_FASTDET
+#define THR_PICK pick_variant_fastdet
+#define THR_SUFFIX ",fastdet>"
+#elif THR_MULTI
 #define THR_PICK pick_variant_multi
 #define THR_SUFFIX ",multi>"
 #else

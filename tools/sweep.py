@@ -22,13 +22,13 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
 def run(block_len, templates, history, batch, p_signal, steps=64, warmup=4, window=(7, 110), unique=256,
-        label=""):
+        label="", fastdet=False):
     lib = load_library()
     tpl0 = templates[0] if templates.ndim == 2 else templates
     raw, _ = synth.make_blocks(unique, block_len, history, tpl0, p_signal, seed=424242)
     n_tpl = templates.shape[0] if templates.ndim == 2 else 1
     det = NativeDetector(block_len, history, templates, len(tpl0), window, (0., 15., 0.), (0., 15., 0.),
-                         max_batch=batch, overlap_launches=True)
+                         max_batch=batch, overlap_launches=True, fastdet=fastdet)
     # pool > L2 (126 MB): at least 160 MiB of raw blocks, a multiple of the batch
     pool_blocks = max(2 * batch, ((160 << 20) // (2 * block_len) + batch - 1) // batch * batch)
     host = np.ascontiguousarray(raw[np.arange(pool_blocks) % unique])
@@ -126,6 +126,8 @@ def main():
     # signal mixes at N=16384
     run(16384, example, 4920, 4096, 0.5, label="N=16384 50% burst blocks")
     run(16384, example, 4920, 4096, 0.0, label="N=16384 noise only")
+    # fastdet semantics (native twin): 2 transforms per block
+    run(16384, example, 4920, 4096, 1.0, label="N=16384 fastdet semantics (2 FFTs/block)", fastdet=True)
     # config 5: 4 Gold templates jointly
     t11 = np.stack([synth.gold_template(11, i) for i in range(4)])
     run(16384, t11, t11.shape[1] + 6, 4096, 1.0, steps=32, label="cfg5 N=16384, 4 Gold templates")
