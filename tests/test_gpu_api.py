@@ -87,7 +87,9 @@ def test_detector_single_and_yield_data(golden_dir):
     det.close()
     det2 = Detector(_settings(cfg), rxid=5)
     d2, r2 = det2.detect(12.5, 5, raw[0])          # raw uint8 block, no yield_data
-    assert d2 and abs(r2.soa - res.soa) < 1e-9 and r2.corr_info.sample == res.corr_info.sample
+    # the batched path prunes FFT#1 for this window, the yield_data path computes it in full: the carrier
+    # offset (hence the mix) differs in the last float32 bits
+    assert d2 and abs(r2.soa - res.soa) < 1e-6 and r2.corr_info.sample == res.corr_info.sample
     det2.close()
 
 

@@ -90,6 +90,7 @@ struct Cfg {
     static_assert((32 * R3) % T == 0 && I2 >= 1, "bad thread count");
     static_assert((32 * R2) % T == 0 && I3 >= 1, "bad thread count");
     static_assert(R2 >= 1 && R2 <= 32 && R3 <= 32, "unsupported size");
+    static_assert(!GMEM_ || (R2 == 32 && R3 == 32 && (32 * R3) % T_ == 0), "GMEM variant: natural pass-3 order assumed");
     // Shared-memory FFT buffer: rows of 16 complex values padded to 17 (136 bytes), so that a
     // half-warp touches 16 different 8-byte bank pairs both when it walks along a row (passes
     // 1, 2) and when it walks across rows (pass 3), and every access is base + immediate.
@@ -106,14 +107,22 @@ struct Cfg {
     // same slabs in both passes the hand-over 2 -> 3 (and 3' -> 2') only needs __syncwarp(): the warps
     // of a CTA then run the whole stretch  pass 2 -> 3 -> x conj(T) -> 3' -> 2'  without a CTA barrier
     // and drift apart, so the LDS/STS phases of one warp overlap the FMA phases of another.
-    //   R2 == R3: the natural item order already matches.   T == 512, R2 == 32: pass-3 items are
-    //   re-assigned per warp (P3_REMAP); the template spectrum is stored in the matching order.
-    static constexpr bool P3_REMAP = THR_WL23 && (T_ == 512 && R2 == 32 && R3 == 16);
-    static constexpr bool WL23 = THR_WL23 && (P3_REMAP || (R2 == R3 && I2 == I3));
-    // pass-3 item (row of R3 elements) of thread `tid`, iteration `it`
+    // Pass-2 items are (k1, n3) = w >> log2(R3), w & (R3-1) with w = tid + T*it, so a warp owns the slabs
+    // k1 = 2*warp + h + (T/16)*it2 (R3 == 16; h = lane >> 4) or k1 = warp + (T/32)*it2 (R3 == 32); p3_item
+    // hands the R2 rows of exactly those slabs to the same warp.  The template spectrum is stored in the
+    // matching order (thr_create uses the same function).
+    static constexpr bool WL23 = THR_WL23 != 0;
+    // pass-3 item (row of R3 elements: k1*R2 + k2) of thread `tid`, iteration `it`
     __host__ __device__ static constexpr int p3_item(int tid, int it) {
-        return P3_REMAP ? (((tid >> 5) * I3 + it) << 5) + (tid & 31) : tid + T_ * it;
+        if (!WL23 || R3 != 16) return tid + T_ * it;     // R3 == 32: R2 == 32, the natural order matches
+        const int r = it * 32 + (tid & 31);              // row number inside this warp's share
+        const int sidx = r / R2, k2 = r % R2;            // slab number inside the share, row inside the slab
+        const int k1 = 2 * (tid >> 5) + (sidx & 1) + (T_ / 16) * (sidx >> 1);
+        return k1 * R2 + k2;
     }
+    // pruned ("zoom") FFT#1, pass 3: with T == 512 and R2 == 32 a warp finds the 8 bins of its own slabs
+    static constexpr bool ZOOM_WARPLOCAL = WL23 && (T_ == 512 && R2 == 32 && R3 == 16);
+    static constexpr bool ZOOM_OK = (R2 >= 8 && R2 % 4 == 0);      // bins < 128 <=> k2 < 4, k3 == 0
     static constexpr size_t smem_bytes() {           // must cover the carve-up in detect_kernel
         return BUF_BYTES + 2 * (size_t)(2 * N) + (size_t)M * 8
                + 2 * 320 + 2 * 32 + 2 * MAX_TPL * 32 + 256 + 512 + 64;
@@ -852,7 +861,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
     // forward passes 1 and 2 of block i (shared by FFT#1 and FFT#2)
     // zoom (pruned FFT#1): only bins [0,128) are needed, i.e. k3 == 0 and k2 < 4, so pass 2 computes
     // 4 of its R2 outputs and pass 3 degenerates to a sum; the spectrum energy comes from Parseval
-    const bool zoom = !FASTDET && (p.zoom != 0) && (p.dbg_fft_mag == nullptr) && (R2 == 32);
+    const bool zoom = !FASTDET && C::ZOOM_OK && (p.zoom != 0) && (p.dbg_fft_mag == nullptr);
     auto fwd_pass12 = [&](int i, bool mix, const float2 (&ph0)[I1], const float2 *rho, float &energy) {
         const uint16_t *rawt = reinterpret_cast<const uint16_t *>(raw_s + (size_t)(i & 1) * RAW_BYTES);
         const float2 *iqb = use_raw ? nullptr : p.iq + (size_t)((int)blockIdx.x + i * (int)gridDim.x) * N;
@@ -925,11 +934,12 @@ detect_kernel(const __grid_constant__ DetectParams p) {
         // after the pass-1 barrier of the mix pass nobody reads this raw stage any more:
         // prefetch the tile of block i+2 into it
         if ((mix || FASTDET) && use_raw && tid == 0 && has_block(i + 2)) issue_tile(i + 2);
-        if constexpr (R2 == 32) {
+        if constexpr (C::ZOOM_OK) {
             if (!mix && zoom) {
-                // pruned pass 2: outputs k2 = 0..3 of the 32-point DFT over n2 = 8m + r:
-                //   c_r[k] = sum_m a[8m+r] W_4^{mk}   (radix-4, no multiplications)
-                //   B[k]   = sum_r W_32^{rk} c_r[k]   (2 packed FMAs per term)
+                // pruned pass 2: outputs k2 = 0..3 of the R2-point DFT over n2 = Q m + r (Q = R2/4):
+                //   c_r[k] = sum_m a[Q m + r] W_4^{mk}    (radix-4, no multiplications)
+                //   B[k]   = sum_r W_R2^{rk} c_r[k]       (2 packed FMAs per term; W_R2 = W_32^(32/R2))
+                constexpr int Q = R2 / 4, E = 32 / R2;
 #pragma unroll
                 for (int it = 0; it < I2; ++it) {
                     const int w = tid + T * it;
@@ -937,11 +947,11 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                     const uint32_t ab = a2_base(k1, n3);
                     float2 b0, b1, b2, b3;
 #pragma unroll
-                    for (int r = 0; r < 8; ++r) {
+                    for (int r = 0; r < Q; ++r) {
                         const float2 a0 = ld8(ab + (uint32_t)(r) * A2_STEP);
-                        const float2 a1 = ld8(ab + (uint32_t)(8 + r) * A2_STEP);
-                        const float2 a2 = ld8(ab + (uint32_t)(16 + r) * A2_STEP);
-                        const float2 a3 = ld8(ab + (uint32_t)(24 + r) * A2_STEP);
+                        const float2 a1 = ld8(ab + (uint32_t)(Q + r) * A2_STEP);
+                        const float2 a2 = ld8(ab + (uint32_t)(2 * Q + r) * A2_STEP);
+                        const float2 a3 = ld8(ab + (uint32_t)(3 * Q + r) * A2_STEP);
                         const float2 s0 = f2add(a0, a2), s1 = f2sub(a0, a2);
                         const float2 s2 = f2add(a1, a3), s3 = f2sub(a1, a3);
                         const float2 c0 = f2add(s0, s2), c2 = f2sub(s0, s2);
@@ -950,13 +960,13 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                             b0 = c0; b1 = c1; b2 = c2; b3 = c3;
                         } else {
                             b0 = f2add(b0, c0);
-                            if (r == 1) { b1 = fma_tw32<1>(b1, c1); b2 = fma_tw32<2>(b2, c2); b3 = fma_tw32<3>(b3, c3); }
-                            if (r == 2) { b1 = fma_tw32<2>(b1, c1); b2 = fma_tw32<4>(b2, c2); b3 = fma_tw32<6>(b3, c3); }
-                            if (r == 3) { b1 = fma_tw32<3>(b1, c1); b2 = fma_tw32<6>(b2, c2); b3 = fma_tw32<9>(b3, c3); }
-                            if (r == 4) { b1 = fma_tw32<4>(b1, c1); b2 = fma_tw32<8>(b2, c2); b3 = fma_tw32<12>(b3, c3); }
-                            if (r == 5) { b1 = fma_tw32<5>(b1, c1); b2 = fma_tw32<10>(b2, c2); b3 = fma_tw32<15>(b3, c3); }
-                            if (r == 6) { b1 = fma_tw32<6>(b1, c1); b2 = fma_tw32<12>(b2, c2); b3 = fma_tw32<18>(b3, c3); }
-                            if (r == 7) { b1 = fma_tw32<7>(b1, c1); b2 = fma_tw32<14>(b2, c2); b3 = fma_tw32<21>(b3, c3); }
+                            if (r == 1) { b1 = fma_tw32<1 * E>(b1, c1); b2 = fma_tw32<2 * E>(b2, c2); b3 = fma_tw32<3 * E>(b3, c3); }
+                            if (r == 2) { b1 = fma_tw32<2 * E>(b1, c1); b2 = fma_tw32<4 * E>(b2, c2); b3 = fma_tw32<6 * E>(b3, c3); }
+                            if (r == 3) { b1 = fma_tw32<3 * E>(b1, c1); b2 = fma_tw32<6 * E>(b2, c2); b3 = fma_tw32<9 * E>(b3, c3); }
+                            if (r == 4) { b1 = fma_tw32<4 * E>(b1, c1); b2 = fma_tw32<8 * E>(b2, c2); b3 = fma_tw32<12 * E>(b3, c3); }
+                            if (r == 5) { b1 = fma_tw32<5 * E>(b1, c1); b2 = fma_tw32<10 * E>(b2, c2); b3 = fma_tw32<15 * E>(b3, c3); }
+                            if (r == 6) { b1 = fma_tw32<6 * E>(b1, c1); b2 = fma_tw32<12 * E>(b2, c2); b3 = fma_tw32<18 * E>(b3, c3); }
+                            if (r == 7) { b1 = fma_tw32<7 * E>(b1, c1); b2 = fma_tw32<14 * E>(b2, c2); b3 = fma_tw32<21 * E>(b3, c3); }
                         }
                     }
                     st8(ab, b0);
@@ -964,7 +974,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                     st8(ab + 2u * A2_STEP, cmul(b2, tw2[2 * R3 + n3]));
                     st8(ab + 3u * A2_STEP, cmul(b3, tw2[3 * R3 + n3]));
                 }
-                if constexpr (C::P3_REMAP) __syncwarp();   // pruned pass 3 reads this warp's own slabs
+                if constexpr (C::ZOOM_WARPLOCAL) __syncwarp();   // pruned pass 3 reads this warp's own slabs
                 else bar_sync(BAR_MAIN, T);
                 return;
             }
@@ -1291,7 +1301,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 // pass 3 (pruned): X[k1 + 32 k2] = sum_n3 B[k1,k2;n3] for the 128 bins k < 128;
                 // 4 threads per bin, R3/4 terms each, then two shuffles
                 constexpr int PER = R3 / 4;
-                if constexpr (C::P3_REMAP) {
+                if constexpr (C::ZOOM_WARPLOCAL) {
                     // warp w owns slabs k1 = 2w, 2w+1 (written by its own pruned pass 2): 8 bins x 4 lanes
                     const int k1 = 2 * (tid >> 5) + (lane >> 4), k2 = (lane >> 2) & 3, sub = lane & 3;
                     float2 acc = make_float2(0.f, 0.f);

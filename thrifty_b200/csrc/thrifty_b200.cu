@@ -353,7 +353,7 @@ int thr_create(const thr_config *cfg, thr_detector **out) {
     p.win_start = ws % N;
     p.win_len = (we - ws + 1) > N ? N : (we - ws + 1);
     // pruned FFT#1: every window bin and its +-3 fit neighbours inside [0,128), no stddev term
-    p.zoom = (!fastdet && ws >= 3 && we + 3 < 128 && we < N && cfg->carrier_thresh[2] == 0.0 && N >= 16384) ? 1 : 0;
+    p.zoom = (!fastdet && ws >= 3 && we + 3 < 128 && we < N && cfg->carrier_thresh[2] == 0.0 && N >= 4096) ? 1 : 0;
     p.c_const = (float)cfg->carrier_thresh[0];
     p.c_snr = (float)cfg->carrier_thresh[1];
     p.c_std = (float)cfg->carrier_thresh[2];
