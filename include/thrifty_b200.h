@@ -58,6 +58,9 @@ extern "C" {
                                           template.  Record fields keep their meaning (magnitudes = sqrt of the
                                           powers, as fastdet prints them, fastdet.cpp:191-206).               */
 
+#define THR_CFG_GENERIC_KERNEL 4u       /* block_len 32768: always run the generic global-scratch kernel instead of
+                                          the 2 x 16384 shared-memory kernel (tests / comparisons)              */
+
 /* thr_record.flags */
 #define THR_FLAG_CARRIER_DETECTED 1u   /* carrier peak above threshold (carrier_sync.py:69)      */
 #define THR_FLAG_CORR_DETECTED    2u   /* correlation peak above threshold (soa_estimator.py:85) */

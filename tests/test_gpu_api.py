@@ -430,3 +430,39 @@ def test_smoke_entry():
     sys.path.insert(0, ROOT)
     import __graft_entry__
     __graft_entry__.smoke()
+
+
+@pytest.mark.parametrize("kthresh", [(0., 15., 0.), (0.5, 10., 3.)])
+def test_n32768_two_half_kernel_vs_generic_and_oracle(kthresh):
+    """block_len 32768 runs as two interleaved 16384-point transforms (detect_kernel_2x.cuh) when FFT#1 can
+    be pruned; the generic global-scratch kernel and the oracle must agree with it (raw and complex64 input)."""
+    from oracle import thrifty_oracle as orc
+    from thrifty_b200._native import NativeDetector
+    tpl = np.load(os.path.join(os.path.dirname(__file__), "golden", "template_example.npy"))
+    n, h = 32768, 4920
+    raw, _ = synth.make_blocks(40, n, h, tpl, 0.7, seed=9001)
+    idx = 5 + 2 * np.arange(40, dtype=np.int64)
+    st = orc.DetectorSettings(n, h, len(tpl), (0., 15., 0.), (7, 110), tpl, kthresh)
+    ref = orc.detect_blocks(st, raw, idx)
+    two = NativeDetector(n, h, tpl, len(tpl), (7, 110), (0., 15., 0.), kthresh, max_batch=64)
+    gen = NativeDetector(n, h, tpl, len(tpl), (7, 110), (0., 15., 0.), kthresh, max_batch=64, generic_kernel=True)
+    assert "detect2x" in two.info()["kernel"] and "gmem" in gen.info()["kernel"]
+    got2 = two.detect_raw(raw, idx)[:, 0]
+    gotg = gen.detect_raw(raw, idx)[:, 0]
+    stats = parity.compare_records(got2, ref, what="n32768/2x")
+    parity.compare_records(gotg, ref, what="n32768/generic")
+    assert stats["carrier"] > 15
+    assert np.array_equal(got2["corr_sample"], gotg["corr_sample"]) and np.array_equal(got2["flags"], gotg["flags"])
+    iq = np.stack([orc.raw_to_complex(r) for r in raw])
+    got2c = two.detect_c64(iq, idx)[:, 0]
+    assert got2c.tobytes() == got2.tobytes()
+    # more blocks than CTAs: every CTA walks several blocks (software pipeline, single raw stage)
+    big = raw[np.arange(700) % 40]
+    two.close()
+    two = NativeDetector(n, h, tpl, len(tpl), (7, 110), (0., 15., 0.), kthresh, max_batch=700)
+    gotb = two.detect_raw(big)[:, 0]
+    for f in ("flags", "carrier_bin", "corr_sample", "corr_energy", "corr_offset", "carrier_offset"):
+        assert np.array_equal(gotb[f][:40], gotb[f][40 * 16:40 * 17], equal_nan=True), f
+        assert np.array_equal(gotb[f][:40], got2[f], equal_nan=True), f
+    two.close()
+    gen.close()

@@ -163,7 +163,7 @@ class NativeDetector(object):
 
     def __init__(self, block_len, history_len, templates, carrier_len, carrier_window,
                  carrier_thresh, corr_thresh, device=0, max_batch=4096, overlap_launches=False,
-                 fastdet=False):
+                 fastdet=False, generic_kernel=False):
         self._lib = load_library()
         self._h = c_void_p()
         tpl = np.ascontiguousarray(np.atleast_2d(np.asarray(templates, dtype=np.float64)))
@@ -187,7 +187,8 @@ class NativeDetector(object):
         cfg.max_batch = self.max_batch
         # THR_CFG_OVERLAP_LAUNCHES | THR_CFG_FASTDET_SEMANTICS (the native twin's semantics:
         # thresholds (constant, snr) apply to POWERS, fastcard/parse.c:54-99 '<c>c<s>s')
-        cfg.flags = (1 if overlap_launches else 0) | (2 if fastdet else 0)
+        # THR_CFG_GENERIC_KERNEL: block_len 32768 on the generic global-scratch kernel (comparisons)
+        cfg.flags = (1 if overlap_launches else 0) | (2 if fastdet else 0) | (4 if generic_kernel else 0)
         self.fastdet = bool(fastdet)
         rc = self._lib.thr_create(byref(cfg), byref(self._h))
         if rc != THR_OK:

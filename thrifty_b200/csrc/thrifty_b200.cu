@@ -46,6 +46,8 @@ struct Slot {                 // one in-flight chunk of the host-buffer API
 struct thr_detector {
     thr_config cfg;
     Variant var;
+    Variant var_generic;                 // generic kernel of the same block length (debug launches) when var is a
+    bool has_generic = false;            //   specialised one (detect2x_kernel)
     int device = 0;
     int sm_count = 0;
     int ctas_per_sm = 1;
@@ -54,6 +56,7 @@ struct thr_detector {
     cudaStream_t stream = nullptr;       // stream used by the *_device entry points
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float2 *d_tpl = nullptr;
+    float2 *d_tpl_generic = nullptr;     // template spectrum in the generic kernel's order (debug launches of a 2x detector)
     float2 *d_tpl_shift = nullptr;       // fastdet semantics: per-carrier-bin shifted template spectra
     float2 *d_tpl_nat = nullptr;         // fastdet semantics: template spectrum in natural order
     float *d_tpl_energy = nullptr;
@@ -138,12 +141,17 @@ int launch(thr_detector *d, cudaStream_t st, const uint8_t *d_raw, const float *
     p.dbg_corr = dbg_corr;
     p.dbg_fft_mag = dbg_mag;
     const int grid = n_blocks < d->grid ? n_blocks : d->grid;
+    const Variant *var = &d->var;
+    if (d->has_generic && (dbg_sfft || dbg_corr || dbg_mag)) {    // intermediates: generic kernel (one block)
+        var = &d->var_generic;
+        p.tpl_spec = d->d_tpl_generic;
+    }
     void *args[] = {&p};
     cudaLaunchConfig_t lc;
     std::memset(&lc, 0, sizeof lc);
     lc.gridDim = dim3(grid);
-    lc.blockDim = dim3(d->var.launch_threads);     // workers (+ service warpgroup), see detect_kernel.cuh
-    lc.dynamicSmemBytes = d->var.smem;
+    lc.blockDim = dim3(var->launch_threads);       // workers (+ service warpgroup), see detect_kernel.cuh
+    lc.dynamicSmemBytes = var->smem;
     lc.stream = st;
     cudaLaunchAttribute attr[1];
     if (allow_overlap && (d->cfg.flags & THR_CFG_OVERLAP_LAUNCHES) && !d->var.gmem && d->cfg.n_templates == 1) {
@@ -152,7 +160,7 @@ int launch(thr_detector *d, cudaStream_t st, const uint8_t *d_raw, const float *
         lc.attrs = attr;
         lc.numAttrs = 1;
     }
-    CU(d, cudaLaunchKernelExC(&lc, d->var.fn, args));
+    CU(d, cudaLaunchKernelExC(&lc, var->fn, args));
     d->launches++;
     return THR_OK;
 }
@@ -189,6 +197,7 @@ void thr_destroy(thr_detector *d) {
     if (d->ev1) cudaEventDestroy(d->ev1);
     cudaFree(d->d_tpl);
     cudaFree(d->d_tpl_shift);
+    cudaFree(d->d_tpl_generic);
     cudaFree(d->d_tpl_nat);
     cudaFree(d->d_tpl_energy);
     cudaFree(d->d_scratch);
@@ -212,7 +221,7 @@ int thr_create(const thr_config *cfg, thr_detector **out) {
         return fail(nullptr, THR_ERR_INVALID, "history_len %d must satisfy template_len-1 <= H < block_len", H);
     if (cfg->carrier_len < 1) return fail(nullptr, THR_ERR_INVALID, "carrier_len must be positive");
     if (cfg->max_batch < 1) return fail(nullptr, THR_ERR_INVALID, "max_batch must be positive");
-    if (cfg->flags & ~(THR_CFG_OVERLAP_LAUNCHES | THR_CFG_FASTDET_SEMANTICS))
+    if (cfg->flags & ~(THR_CFG_OVERLAP_LAUNCHES | THR_CFG_FASTDET_SEMANTICS | THR_CFG_GENERIC_KERNEL))
         return fail(nullptr, THR_ERR_INVALID, "unknown flags 0x%x", cfg->flags);
     const bool fastdet = (cfg->flags & THR_CFG_FASTDET_SEMANTICS) != 0;
     if (fastdet) {
@@ -229,6 +238,19 @@ int thr_create(const thr_config *cfg, thr_detector **out) {
         return fail(nullptr, THR_ERR_INVALID, "Frequency window out of range: %d - %d", cfg->window_start,
                     cfg->window_stop);
 
+    // block_len 32768 with a pruned-FFT#1 configuration: two interleaved 16384-point transforms in shared memory
+    // (detect_kernel_2x.cuh) instead of the generic global-scratch variant, which stays for debug launches
+    const bool zoom_cfg = (!fastdet && ws >= 3 && we + 3 < 128 && we < N && cfg->carrier_thresh[2] == 0.0 && N >= 4096);
+    Variant var_generic = var;
+    bool use_2x = false;
+    if (zoom_cfg && NT == 1 && N == 32768 && !(cfg->flags & THR_CFG_GENERIC_KERNEL)) {
+        Variant v2;
+        if (thr::pick_variant_2x(N, &v2)) {
+            var = v2;
+            use_2x = true;
+        }
+    }
+
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(nullptr, THR_ERR_NO_DEVICE, "no CUDA device available");
@@ -239,6 +261,8 @@ int thr_create(const thr_config *cfg, thr_detector **out) {
     d->cfg = *cfg;
     d->cfg.templates = nullptr;
     d->var = var;
+    d->var_generic = var_generic;
+    d->has_generic = use_2x;
     d->device = cfg->device;
     auto bail = [&](int code) { g_create_error = d->err; thr_destroy(d); return code; };
 #define CUC(call)                                                                            \
@@ -269,6 +293,8 @@ int thr_create(const thr_config *cfg, thr_detector **out) {
     }
     d->ctas_per_sm = occ;
     d->grid = d->sm_count * occ;
+    if (use_2x)
+        CUC(cudaFuncSetAttribute(var_generic.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)var_generic.smem));
 
     CUC(cudaStreamCreateWithFlags(&d->own_stream, cudaStreamNonBlocking));
     d->stream = d->own_stream;
@@ -278,7 +304,7 @@ int thr_create(const thr_config *cfg, thr_detector **out) {
     // ---- template spectra: conj(FFT(template || zeros))/N, float64 -> float32, kernel order
     {
         const int T = var.threads, R2 = var.r2, R3 = var.r3, I3 = var.i3;
-        std::vector<float2> perm((size_t)NT * N);
+        std::vector<float2> perm((size_t)NT * N), perm_generic;
         std::vector<float> energy(NT);
         std::vector<std::complex<double>> a(N);
         for (int t = 0; t < NT; ++t) {
@@ -295,9 +321,23 @@ int thr_create(const thr_config *cfg, thr_detector **out) {
                     for (int tid = 0; tid < T; ++tid) {
                         const int g = var.p3_item(tid, i);
                         const int k = (g / R2) + 32 * (g % R2) + 32 * R2 * k3;
-                        perm[(size_t)t * N + (size_t)(i * R3 + k3) * T + tid] =
-                            make_float2((float)(a[k].real() / N), (float)(-a[k].imag() / N));
+                        const size_t pos = (size_t)t * N + (size_t)(i * R3 + k3) * T + tid;
+                        perm[pos] = make_float2((float)(a[k].real() / N), (float)(-a[k].imag() / N));
+                        if (var.two_halves)      // bins k >= N/2 in the same thread order, after the first half
+                            perm[pos + N / 2] = make_float2((float)(a[k + N / 2].real() / N), (float)(-a[k + N / 2].imag() / N));
                     }
+            if (use_2x) {                        // the generic kernel's own order for debug launches
+                const int Tg = var_generic.threads, R2g = var_generic.r2, R3g = var_generic.r3, I3g = var_generic.i3;
+                perm_generic.resize(N);
+                for (int i = 0; i < I3g; ++i)
+                    for (int k3 = 0; k3 < R3g; ++k3)
+                        for (int tid = 0; tid < Tg; ++tid) {
+                            const int g = var_generic.p3_item(tid, i);
+                            const int k = (g / R2g) + 32 * (g % R2g) + 32 * R2g * k3;
+                            perm_generic[(size_t)(i * R3g + k3) * Tg + tid] =
+                                make_float2((float)(a[k].real() / N), (float)(-a[k].imag() / N));
+                        }
+            }
         }
         if (fastdet) {
             // a is still FFT(template 0): natural-order conj/N, and one pre-rolled copy per carrier bin of the
@@ -325,10 +365,14 @@ int thr_create(const thr_config *cfg, thr_detector **out) {
         }
         CUC(cudaMalloc(&d->d_tpl, perm.size() * sizeof(float2)));
         CUC(cudaMemcpy(d->d_tpl, perm.data(), perm.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        if (use_2x) {
+            CUC(cudaMalloc(&d->d_tpl_generic, perm_generic.size() * sizeof(float2)));
+            CUC(cudaMemcpy(d->d_tpl_generic, perm_generic.data(), perm_generic.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        }
         CUC(cudaMalloc(&d->d_tpl_energy, NT * sizeof(float)));
         CUC(cudaMemcpy(d->d_tpl_energy, energy.data(), NT * sizeof(float), cudaMemcpyHostToDevice));
     }
-    if (var.gmem) CUC(cudaMalloc(&d->d_scratch, (size_t)d->grid * N * sizeof(float2)));
+    if (var.gmem || use_2x) CUC(cudaMalloc(&d->d_scratch, (size_t)d->grid * N * sizeof(float2)));
     if (NT > 1) CUC(cudaMalloc(&d->d_xsave, (size_t)d->grid * N * sizeof(float2)));
     for (auto &s : d->slot) {
         CUC(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
@@ -353,7 +397,7 @@ int thr_create(const thr_config *cfg, thr_detector **out) {
     p.win_start = ws % N;
     p.win_len = (we - ws + 1) > N ? N : (we - ws + 1);
     // pruned FFT#1: every window bin and its +-3 fit neighbours inside [0,128), no stddev term
-    p.zoom = (!fastdet && ws >= 3 && we + 3 < 128 && we < N && cfg->carrier_thresh[2] == 0.0 && N >= 4096) ? 1 : 0;
+    p.zoom = zoom_cfg ? 1 : 0;
     p.c_const = (float)cfg->carrier_thresh[0];
     p.c_snr = (float)cfg->carrier_thresh[1];
     p.c_std = (float)cfg->carrier_thresh[2];

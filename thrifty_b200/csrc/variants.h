@@ -11,6 +11,7 @@ struct Variant {
     int log2n;
     int threads;
     bool gmem;
+    bool two_halves = false;           // detect2x_kernel: template spectrum stored as [k < F][k >= F]
     int r2, r3, i3;
     int (*p3_item)(int tid, int it);   // pass-3 item owned by (thread, iteration): fixes the template order
     int launch_threads;
@@ -22,5 +23,6 @@ struct Variant {
 bool pick_variant_single(int block_len, Variant *out);   // n_templates == 1
 bool pick_variant_multi(int block_len, Variant *out);    // n_templates >= 1
 bool pick_variant_fastdet(int block_len, Variant *out);  // fastdet semantics (one template)
+bool pick_variant_2x(int block_len, Variant *out);       // 32768 = 2 x 16384 (pruned-FFT#1 configurations, one template)
 
 }  // namespace thr

@@ -8,7 +8,7 @@ cd "$(dirname "$(readlink -f "$0")")/../thrifty_b200/csrc"
 mkdir -p ../_lib/variants
 while [ $# -ge 2 ]; do
   name=$1; flags=$2; shift 2
-  ( make -s -j4 OUTDIR=../_lib/variants/$name EXTRA="-DTHR_ONLY_N16384 $flags" 2>/dev/null >/dev/null \
+  ( make -s -j5 OUTDIR=../_lib/variants/$name EXTRA="-DTHR_ONLY_N16384 $flags" 2>/dev/null >/dev/null \
     && cp ../_lib/variants/$name/libthrifty_b200.so ../_lib/variants/$name.so && echo "built $name" ) &
 done
 wait
