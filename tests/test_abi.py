@@ -81,3 +81,30 @@ def test_product_never_touches_the_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle", text, re.M), f
                 assert "thrifty_oracle" not in text, f
                 assert "/root/reference" not in text, f
+
+
+def test_headline_kernels_keep_their_arrays_in_registers():
+    """A register FFT whose array gets a dynamic index (or a lambda that is not inlined) silently moves to
+    local memory: the kernel stays correct and becomes 2.5x slower (seen once in round 1).  cuobjdump's
+    resource table catches it without a GPU."""
+    import re
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    out = subprocess.run(["cuobjdump", "--dump-resource-usage", _native.LIB_PATH], capture_output=True, text=True).stdout
+    stack = {}
+    name = None
+    for line in out.splitlines():
+        m = re.search(r"Function (\S+):", line)
+        if m:
+            name = m.group(1)
+        m = re.search(r"STACK:(\d+)", line)
+        if m and name:
+            stack[name] = int(m.group(1))
+    headline = [k for k in stack if "detect_kernelILi14ELi512ELb0ELb0ELb0" in k]
+    two_half = [k for k in stack if "detect2x_kernel" in k]
+    fastdet = [k for k in stack if "detect_kernelILi14ELi512ELb0ELb0ELb1" in k]
+    assert headline and two_half and fastdet, sorted(stack)
+    for k in headline + two_half + fastdet:
+        assert stack[k] <= 64, "%s uses %d bytes of local memory per thread" % (k, stack[k])

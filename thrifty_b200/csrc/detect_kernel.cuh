@@ -34,6 +34,11 @@
 #ifndef THR_PACKRAW
 #define THR_PACKRAW 1       // rawconv and the Parseval energy on packed FP32x2 instructions
 #endif
+#ifndef THR_ASYNC_TAIL
+#define THR_ASYNC_TAIL 0    // (measured 1.5 % slower: 32 extra st.cg per thread cost more than the barrier) correlation arg-max with ONE CTA barrier: |c|^2 of every lag goes to an L2 scratch, the
+                            // winning thread posts the peak lag with an atomic, the service warp fetches the
+                            // neighbours; nobody waits for the index (single-template kernels)
+#endif
 #ifndef THR_ARGMAX1
 #define THR_ARGMAX1 0       // block arg-max with one CTA barrier (per-warp first index) instead of two:
                             // measured 4 % slower (every warp pays the index scan), kept for reference
@@ -53,6 +58,7 @@ struct DetectParams {
     const float  *tpl_energy;  // [n_templates] sum(template^2)
     float2 *scratch;           // per-CTA global scratch: [grid][N] FFT buffer (GMEM variant)
     float2 *xsave;             // per-CTA save area for X' when n_templates > 1: [grid][N]
+    float  *cpsave;            // per-CTA |c|^2 of every lag, double buffered: [grid][2][N] (THR_ASYNC_TAIL)
     int win_start, win_len;    // carrier window: start index in [0,N), number of bins
     float c_const, c_snr, c_std;   // carrier threshold coefficients
     float k_const, k_snr, k_std;   // correlation threshold coefficients
@@ -593,6 +599,7 @@ __global__ void __launch_bounds__(Cfg<LOG2N, T, GMEM>::LAUNCH_THREADS, Cfg<LOG2N
 detect_kernel(const __grid_constant__ DetectParams p) {
     using C = Cfg<LOG2N, T, GMEM>;
     constexpr bool SERVICE = C::SERVICE;
+    constexpr bool ASYNC_TAIL = (THR_ASYNC_TAIL != 0) && !MULTI;   // see corr_stage
     constexpr int N = C::N, M = C::M, R2 = C::R2, R3 = C::R3, S = C::S;
     constexpr int I1 = C::I1, I2 = C::I2, I3 = C::I3;
     constexpr int LOG2M = ilog2(M), LOG2R3 = ilog2(R3), LOG2R2 = ilog2(R2), LOG2S = ilog2(S);
@@ -695,6 +702,14 @@ detect_kernel(const __grid_constant__ DetectParams p) {
             } else {
                 // scalar tail (soa_estimator.py:78-134,159-170); float32 except the SoA itself
                 const TailSlot &ts = tailslot[q * C::MAX_TPL + tpl];
+                float pa = ts.pa, pc = ts.pc;
+                if constexpr (ASYNC_TAIL) {     // neighbours of the peak from the |c|^2 scratch of this block
+                    const float *cpq = p.cpsave + ((size_t)blockIdx.x * 2 + (size_t)q) * N;
+                    if (ts.s > 0 && ts.s < p.corr_len - 1) {
+                        pa = __ldcg(&cpq[ts.s - 1]);
+                        pc = __ldcg(&cpq[ts.s + 1]);
+                    }
+                }
                 const float peak_mag_k = sqrtf(ts.peak_cp);
                 // mean |X'|^2 (soa_estimator.py:111) == sum |x|^2 == mean |X|^2 of FFT#1: the mix is a
                 // unit-modulus rotation and both FFTs are unitary up to N (Parseval)
@@ -711,8 +726,8 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 float offset = 0.f;
                 if (detected && ts.s > 0 && ts.s < p.corr_len - 1) {
                     // a,b,c = ln|c|; offset = 0.5 (c-a) / (2b-a-c) with |c| = sqrt(power)
-                    const float num = logf(ts.pc / ts.pa);
-                    const float den = logf((ts.peak_cp / ts.pa) * (ts.peak_cp / ts.pc));
+                    const float num = logf(pc / pa);
+                    const float den = logf((ts.peak_cp / pa) * (ts.peak_cp / pc));
                     offset = fminf(fmaxf(0.5f * num / den, -0.6f), 0.6f);
                 }
                 rec.soa = (double)p.new_len * (double)bidx + (double)ts.s + (double)offset;
@@ -757,6 +772,14 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 const float ca = sqrtf(h.pad[0]), cb = sqrtf(h.peak_mag), cc = sqrtf(h.pad[1]);
                 const float coff = fminf(fmaxf((cc - ca) / (4.f * cb - 2.f * ca - 2.f * cc), -0.5f), 0.5f);
                 const TailSlot &ts = tailslot[q * C::MAX_TPL];
+                float pa = ts.pa, pc = ts.pc;
+                if constexpr (ASYNC_TAIL) {
+                    const float *cpq = p.cpsave + ((size_t)blockIdx.x * 2 + (size_t)q) * N;
+                    if (ts.s > 0 && ts.s < p.corr_len - 1) {
+                        pa = __ldcg(&cpq[ts.s - 1]);
+                        pc = __ldcg(&cpq[ts.s + 1]);
+                    }
+                }
                 // corr_detector.cpp:118-125: the peak power arrives as size_t (truncated), noise clamped at 0
                 float noise_pw = (h.sig_energy1 * p.tpl_energy[0] - truncf(ts.peak_cp)) / (float)N;
                 noise_pw = noise_pw < 0.f ? 0.f : noise_pw;
@@ -765,8 +788,8 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 float offset = 0.f;
                 if (detected && ts.s > 0 && ts.s < p.corr_len - 1) {
                     // :103-116 Gaussian interpolation on ln sqrt(power), clipped to +-0.5
-                    const float num = logf(ts.pc / ts.pa);
-                    const float den = logf((ts.peak_cp / ts.pa) * (ts.peak_cp / ts.pc));
+                    const float num = logf(pc / pa);
+                    const float den = logf((ts.peak_cp / pa) * (ts.peak_cp / pc));
                     offset = fminf(fmaxf(0.5f * num / den, -0.5f), 0.5f);
                 }
                 rec.soa = (double)p.new_len * (double)bidx + (double)ts.s + (double)offset;   // fastdet.cpp:184
@@ -1005,6 +1028,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
     // ---- correlation stage for one template (soa_estimator.py:97-143): this thread's pass-3 outputs X'
     // (supplied by get_x) x conj(T)/N -> inverse passes 3', 2', 1' -> |c|^2 windowed arg-max -> TailSlot
     auto corr_stage = [&](int q, int tpl, auto &&get_tv, auto &&get_x) {
+        [[maybe_unused]] float *cpq = ASYNC_TAIL ? p.cpsave + ((size_t)blockIdx.x * 2 + (size_t)q) * N : nullptr;
 #pragma unroll
         for (int it = 0; it < I3; ++it) {
             const int g = C::p3_item(tid, it);
@@ -1082,6 +1106,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 const float pv = x[n1].x * x[n1].x + x[n1].y * x[n1].y;
                 cp[it][n1] = pv;
                 if (inmask[it] & (1u << n1)) cbestv = fmaxf(cbestv, pv);
+                if constexpr (ASYNC_TAIL) __stcg(&cpq[n1 * M + j], pv);
             }
             if (need_std_k) {
 #pragma unroll
@@ -1110,30 +1135,68 @@ detect_kernel(const __grid_constant__ DetectParams p) {
             }
             return key;
         };
-        ArgOut rb;
-        if (need_std_k) rb = main_argmax<T, true>(__float_as_uint(cbestv), c1sum, c2sum, red, tid, find_lag);
-        else rb = main_argmax<T, false>(__float_as_uint(cbestv), 0.f, 0.f, red, tid, find_lag);
-        const int s = (int)rb.key;
         TailSlot &ts = tailslot[q * C::MAX_TPL + tpl];
-        if (tid == 0) {
-            ts.peak_cp = __uint_as_float(rb.vbits);
-            ts.s = s;
-            ts.c1 = rb.s0;
-            ts.c2 = rb.s1;
-        }
-        // neighbours of the peak for the Gaussian interpolation
+        if constexpr (ASYNC_TAIL) {
+            // one barrier: block maximum by value; the thread(s) holding it post the first lag with an atomic and
+            // everybody moves on -- the service warp reads lag and neighbours after the TAILREQ hand-over
+            constexpr int NW = T / 32;
+            const uint32_t vbits = __float_as_uint(cbestv);
+            const uint32_t wmax = __reduce_max_sync(0xffffffffu, vbits);
+            if (need_std_k) {
+                c1sum = warp_sum(c1sum);
+                c2sum = warp_sum(c2sum);
+            }
+            if (lane == 0) {
+                red[tid >> 5] = wmax;
+                if (need_std_k) {
+                    red[16 + (tid >> 5)] = __float_as_uint(c1sum);
+                    red[32 + (tid >> 5)] = __float_as_uint(c2sum);
+                }
+                if (tid == 0) ts.s = -1;                       // 0xffffffff: no lag posted yet
+            }
+            bar_sync(BAR_MAIN, T);
+            uint32_t gmax = 0u;
 #pragma unroll
-        for (int it = 0; it < I1; ++it) {
-            const int j = tid + T * it;
+            for (int w = 0; w < NW; ++w) gmax = max(gmax, red[w]);
+            if (tid == 0) {
+                ts.peak_cp = __uint_as_float(gmax);
+                float a1 = 0.f, a2 = 0.f;
+                if (need_std_k) {
 #pragma unroll
-            for (int dd = -1; dd <= 1; dd += 2) {
-                const int nt = s + dd;
-                if (nt >= 0 && nt < N && (nt & (M - 1)) == j) {
-                    const int n1s = nt >> LOG2M;
-                    float v = 0.f;
+                    for (int w = 0; w < NW; ++w) {
+                        a1 += __uint_as_float(red[16 + w]);
+                        a2 += __uint_as_float(red[32 + w]);
+                    }
+                }
+                ts.c1 = a1;
+                ts.c2 = a2;
+            }
+            if (vbits == gmax) atomicMin(reinterpret_cast<unsigned int *>(&ts.s), find_lag(gmax));
+        } else {
+            ArgOut rb;
+            if (need_std_k) rb = main_argmax<T, true>(__float_as_uint(cbestv), c1sum, c2sum, red, tid, find_lag);
+            else rb = main_argmax<T, false>(__float_as_uint(cbestv), 0.f, 0.f, red, tid, find_lag);
+            const int s = (int)rb.key;
+            if (tid == 0) {
+                ts.peak_cp = __uint_as_float(rb.vbits);
+                ts.s = s;
+                ts.c1 = rb.s0;
+                ts.c2 = rb.s1;
+            }
+            // neighbours of the peak for the Gaussian interpolation
 #pragma unroll
-                    for (int n1 = 0; n1 < 32; ++n1) v = (n1 == n1s) ? cp[it][n1] : v;
-                    if (dd < 0) ts.pa = v; else ts.pc = v;
+            for (int it = 0; it < I1; ++it) {
+                const int j = tid + T * it;
+#pragma unroll
+                for (int dd = -1; dd <= 1; dd += 2) {
+                    const int nt = s + dd;
+                    if (nt >= 0 && nt < N && (nt & (M - 1)) == j) {
+                        const int n1s = nt >> LOG2M;
+                        float v = 0.f;
+#pragma unroll
+                        for (int n1 = 0; n1 < 32; ++n1) v = (n1 == n1s) ? cp[it][n1] : v;
+                        if (dd < 0) ts.pa = v; else ts.pc = v;
+                    }
                 }
             }
         }

@@ -23,6 +23,8 @@
 // reference citations of each stage).
 #pragma once
 
+#include <type_traits>
+
 #include "detect_kernel.cuh"
 
 namespace thr {
@@ -197,11 +199,12 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
 
     // forward pass 1 of half h of block i: samples x[2m + h], m = n1*M + j (from the shared-memory raw
     // stage in stage A, re-read from global/L2 in stage B) -> radix-32 over n1 -> twiddle W_F^{j k1}
-    auto pass1 = [&](int i, int h, bool mix, float2 ph0, const float2 *rho, float &energy) {
+    auto pass1 = [&](auto mix_c, int i, int h, float2 ph0, const float2 *rho, float &energy) {
+        constexpr bool mix = decltype(mix_c)::value;
         const int blk = (int)blockIdx.x + i * (int)gridDim.x;
         float2 x[32];
         if (use_raw) {
-            if (!mix) {
+            if constexpr (!mix) {
                 const uint16_t *rawt = reinterpret_cast<const uint16_t *>(raw_s);
 #pragma unroll
                 for (int n1 = 0; n1 < 32; ++n1) x[brev(n1, 5)] = rawconv(rawt[2 * (n1 * M + tid) + h]);
@@ -215,7 +218,7 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
 #pragma unroll
             for (int n1 = 0; n1 < 32; ++n1) x[brev(n1, 5)] = __ldg(&iqb[2 * (n1 * M + tid) + h]);
         }
-        if (!mix) {
+        if constexpr (!mix) {
             float2 e2 = make_float2(0.f, 0.f);
 #pragma unroll
             for (int n1 = 0; n1 < 32; ++n1) e2 = __ffma2_rn(x[n1], x[n1], e2);
@@ -237,7 +240,7 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
         cur[1] = cmul(ws, ws);
         cur[2] = cmul(cur[1], ws);
         cur[3] = ws4;
-        if (mix) {
+        if constexpr (mix) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) cur[c] = cmul(cur[c], ph0);
             st8(a1b, cmul(x[0], ph0));
@@ -319,7 +322,7 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
             float tenergy = 0.f;
 #pragma unroll 1
             for (int h = 0; h < 2; ++h) {
-                pass1(ia, h, false, make_float2(1.f, 0.f), nullptr, tenergy);
+                pass1(std::false_type{}, ia, h, make_float2(1.f, 0.f), nullptr, tenergy);
                 bar_sync(BAR_MAIN, T);
                 // the raw stage is not read again in stage A: fetch the next block's tile into it
                 if (h == 1 && use_raw && tid == 0 && has_block(ia + 1)) issue_tile(ia + 1);
@@ -418,7 +421,7 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
             float unused_energy = 0.f;
 
             // ---- half 0: E' = FFT_F(x'[2m]) -> parked
-            pass1(i, 0, true, cispi(2.f * turns0), fs.rho, unused_energy);
+            pass1(std::true_type{}, i, 0, cispi(2.f * turns0), fs.rho, unused_energy);
             bar_sync(BAR_MAIN, T);
             pass2();
             __syncwarp();
@@ -435,7 +438,7 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
             bar_sync(BAR_MAIN, T);          // every warp is done reading the buffer
 
             // ---- half 1: O' = FFT_F(x'[2m+1]); join, x conj(T)/N, split into A (inverted now) and B (parked)
-            pass1(i, 1, true, cispi(2.f * (turns0 + turns_h)), fs.rho, unused_energy);
+            pass1(std::true_type{}, i, 1, cispi(2.f * (turns0 + turns_h)), fs.rho, unused_energy);
             bar_sync(BAR_MAIN, T);
             pass2();
             __syncwarp();
@@ -444,7 +447,10 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
                 const int g = H::p3_item(tid, it);
                 const uint32_t ab = (uint32_t)g * 136u;
                 const int kb = (g >> LOG2R2) + 32 * (g & (R2 - 1));              // bin k = kb + S*k3 < F
-                const float2 wb = cispi(-2.0f * (float)kb / (float)NB);          // W_NB^kb
+                float2 wb = cispi(-2.0f * (float)kb / (float)NB);                // W_NB^kb
+                // opaque: keeps the compiler from hoisting the 32 products wb * W_32^k3 out of the block loop
+                // into a per-thread local-memory table (reloads would miss the small L1)
+                asm volatile("" : "+f"(wb.x), "+f"(wb.y));
                 float2 x[R3];
 #pragma unroll
                 for (int n3 = 0; n3 < R3; ++n3) x[brev(n3, LOG2R3)] = ld8(ab + (uint32_t)n3 * 8u);

@@ -122,7 +122,7 @@ def main():
     run(8192, t10, len(t10) + 6, 4096, 1.0, label="cfg3 N=8192")
     run(16384, example, 4920, 4096, 1.0, label="cfg3 N=16384 (headline, pruned FFT#1)")
     run(16384, example, 4920, 4096, 1.0, window=(7, 300), label="N=16384 full FFT#1 (window 7-300)")
-    run(32768, example, 4920, 2048, 1.0, steps=16, label="cfg3 N=32768 (global-scratch variant)")
+    run(32768, example, 4920, 2048, 1.0, steps=16, label="cfg3 N=32768 (2 x 16384 kernel)")
     # signal mixes at N=16384
     run(16384, example, 4920, 4096, 0.5, label="N=16384 50% burst blocks")
     run(16384, example, 4920, 4096, 0.0, label="N=16384 noise only")
