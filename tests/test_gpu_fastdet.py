@@ -82,3 +82,30 @@ def test_fastdet_invalid_settings():
     with pytest.raises(NativeError):
         NativeDetector(4096, len(tpl) + 6, np.stack([tpl, tpl]), len(tpl), (7, 110), (0, 15, 0), (0, 15, 0),
                        fastdet=True)
+
+
+def test_fastdet_cli_card_to_toad(tmp_path):
+    """`python -m thrifty_b200 fastdet --card ...` writes the `.toad` lines the reference's fastdet writes
+    (fastdet.cpp:191-206; golden lines come from the compiled reference sources)."""
+    import subprocess
+    import sys
+    from thrifty_b200 import block_data, fastdet
+    cfg, raw, block_idx, ref, toads, _ = parity.load_fastdet_golden("n4096_gold9_negwin")
+    card, tpl, out = str(tmp_path / "in.card"), str(tmp_path / "t.tpl"), str(tmp_path / "out.toad")
+    with open(card, "w") as f:
+        block_data.write_card(f, raw, block_idx)
+    fastdet.save_template(tpl, cfg["template"])
+    cmd = [sys.executable, "-m", "thrifty_b200", "fastdet", "--card", "-i", card, "-z", tpl, "-o", out,
+           "-b", str(cfg["block_len"]), "-h", str(cfg["history_len"]), "-w", "%d-%d" % cfg["window"],
+           "-t", "%gc%gs" % cfg["thresh"], "-u", "%gc%gs" % cfg["corr_thresh"], "-r", "0", "--batch", "16"]
+    res = subprocess.run(cmd, capture_output=True, text=True, cwd=parity.ROOT)
+    assert res.returncode == 0, res.stderr
+    lines = open(out).read().splitlines()
+    assert len(lines) == len(toads) == int(ref["corr_detected"].sum())
+    for mine, gold in zip(lines, toads):
+        a, b = mine.split(" "), gold.split(" ")
+        assert len(a) == 12 and a[0] == b[0] and a[2] == b[2] and a[4] == b[4] and a[8] == b[8]
+        assert abs(float(a[3]) - float(b[3])) <= 1e-4                      # soa
+        for x, y in zip(a[5:], b[5:]):
+            assert abs(float(x) - float(y)) <= 1e-4 * max(1.0, abs(float(y)))
+    assert "carrier @" in res.stdout and "Read %d blocks." % len(raw) in res.stdout

@@ -8,11 +8,13 @@ HELP = """usage: thrifty_b200 <command> [<args>]
 
     detect   Detect positioning signals in .card / raw data and estimate SoA (GPU)
     fastdet  Same job with the semantics and options of the reference's native `fastdet` (GPU)
+    identify Merge .toad files, identify transmitters by carrier bin, drop duplicates -> .toads (host)
     synth    Write a synthetic .card file (see SURVEY.md 8d)
 
 Use 'thrifty_b200 help <command>' for a command's arguments."""
 
-MODULES = {"detect": "thrifty_b200.detect", "fastdet": "thrifty_b200.fastdet", "synth": "thrifty_b200.synth_cli"}
+MODULES = {"detect": "thrifty_b200.detect", "fastdet": "thrifty_b200.fastdet", "identify": "thrifty_b200.identify",
+           "synth": "thrifty_b200.synth_cli"}
 
 
 def _main():

@@ -34,6 +34,10 @@
 #ifndef THR_PACKRAW
 #define THR_PACKRAW 1       // rawconv and the Parseval energy on packed FP32x2 instructions
 #endif
+#ifndef THR_TW3
+#define THR_TW3 1           // (+2 %) inter-pass twiddles W_M^{n3 k2} of FFT#2 / IFFT applied on the pass-3 side from a
+                            // per-item register chain instead of the shared-memory table on the pass-2 side
+#endif
 #ifndef THR_ASYNC_TAIL
 #define THR_ASYNC_TAIL 0    // (measured 1.5 % slower: 32 extra st.cg per thread cost more than the barrier) correlation arg-max with ONE CTA barrier: |c|^2 of every lag goes to an L2 scratch, the
                             // winning thread posts the peak lag with an atomic, the service warp fetches the
@@ -600,6 +604,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
     using C = Cfg<LOG2N, T, GMEM>;
     constexpr bool SERVICE = C::SERVICE;
     constexpr bool ASYNC_TAIL = (THR_ASYNC_TAIL != 0) && !MULTI;   // see corr_stage
+    constexpr bool TW3 = (THR_TW3 != 0) && !MULTI && !FASTDET && C::R3 == 16 && C::R2 > 1;
     constexpr int N = C::N, M = C::M, R2 = C::R2, R3 = C::R3, S = C::S;
     constexpr int I1 = C::I1, I2 = C::I2, I3 = C::I3;
     constexpr int LOG2M = ilog2(M), LOG2R3 = ilog2(R3), LOG2R2 = ilog2(R2), LOG2S = ilog2(S);
@@ -1016,7 +1021,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
 #pragma unroll
                 for (int k2 = 0; k2 < R2; ++k2) {
                     float2 v = x[k2];
-                    if (k2 > 0) v = cmul(v, tw2[k2 * R3 + n3]);
+                    if (k2 > 0 && !(TW3 && mix)) v = cmul(v, tw2[k2 * R3 + n3]);
                     st8(ab + (uint32_t)k2 * A2_STEP, v);
                 }
             }
@@ -1027,6 +1032,17 @@ detect_kernel(const __grid_constant__ DetectParams p) {
 
     // ---- correlation stage for one template (soa_estimator.py:97-143): this thread's pass-3 outputs X'
     // (supplied by get_x) x conj(T)/N -> inverse passes 3', 2', 1' -> |c|^2 windowed arg-max -> TailSlot
+    // TW3: powers w^1..w^4 of w = W_M^{k2} for the pass-3 item g (k2 = g mod R2); cur3w4 = w^4 steps the chains
+    float2 cur3w4 = make_float2(1.f, 0.f);
+    auto tw3_seed = [&](int g, float2 (&cur)[4]) {
+        float2 w = cispi(-2.0f * (float)(g & (R2 - 1)) / (float)M);
+        asm volatile("" : "+f"(w.x), "+f"(w.y));       // not hoisted out of the block loop (register pressure)
+        cur[0] = w;
+        cur[1] = cmul(w, w);
+        cur[2] = cmul(cur[1], w);
+        cur[3] = cmul(cur[1], cur[1]);
+        cur3w4 = cur[3];
+    };
     auto corr_stage = [&](int q, int tpl, auto &&get_tv, auto &&get_x) {
         [[maybe_unused]] float *cpq = ASYNC_TAIL ? p.cpsave + ((size_t)blockIdx.x * 2 + (size_t)q) * N : nullptr;
 #pragma unroll
@@ -1043,6 +1059,15 @@ detect_kernel(const __grid_constant__ DetectParams p) {
 #pragma unroll
             for (int k3 = 0; k3 < R3; ++k3) y[brev(k3, LOG2R3)] = cmul(x[k3], tv[k3]);
             fft_dit<R3, true>(y);
+            if constexpr (TW3) {      // conj(W_M^{n3 k2}) here instead of on the pass-2' loads
+                float2 cur[4];
+                tw3_seed(g, cur);
+#pragma unroll
+                for (int n3 = 1; n3 < R3; ++n3) {
+                    if (n3 > 4) cur[(n3 - 1) & 3] = cmul(cur[(n3 - 1) & 3], cur3w4);
+                    y[n3] = cmulc(y[n3], cur[(n3 - 1) & 3]);
+                }
+            }
 #pragma unroll
             for (int n3 = 0; n3 < R3; ++n3) st8(ab + (uint32_t)n3 * 8u, y[n3]);
         }
@@ -1059,7 +1084,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
 #pragma unroll
                 for (int k2 = 0; k2 < R2; ++k2) {
                     float2 v = ld8(ab + (uint32_t)k2 * A2_STEP);
-                    if (k2 > 0) v = cmulc(v, tw2[k2 * R3 + n3]);
+                    if (k2 > 0 && !TW3) v = cmulc(v, tw2[k2 * R3 + n3]);
                     x[brev(k2, LOG2R2)] = v;
                 }
                 fft_dit<R2, true>(x);
@@ -1561,8 +1586,19 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 corr_stage(q, tpl, [&](int it, int, int k3) { return __ldg(&tsp[(size_t)(it * R3 + k3) * T + tid]); },
                            [&](int it, int g, uint32_t ab, float2 (&x)[R3]) {
                 if (tpl == 0) {
+                    if constexpr (TW3) {    // W_M^{n3 k2} on the loads (pass 2 stored its outputs untwiddled)
+                        float2 cur[4];
+                        tw3_seed(g, cur);
+                        x[0] = ld8(ab);
 #pragma unroll
-                    for (int n3 = 0; n3 < R3; ++n3) x[brev(n3, LOG2R3)] = ld8(ab + (uint32_t)n3 * 8u);
+                        for (int n3 = 1; n3 < R3; ++n3) {
+                            if (n3 > 4) cur[(n3 - 1) & 3] = cmul(cur[(n3 - 1) & 3], cur3w4);
+                            x[brev(n3, LOG2R3)] = cmul(ld8(ab + (uint32_t)n3 * 8u), cur[(n3 - 1) & 3]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int n3 = 0; n3 < R3; ++n3) x[brev(n3, LOG2R3)] = ld8(ab + (uint32_t)n3 * 8u);
+                    }
                     fft_dit<R3, false>(x);
                     if (MULTI && p.n_templates > 1) {
 #pragma unroll

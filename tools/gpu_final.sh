@@ -1,0 +1,18 @@
+#!/bin/bash
+# Round-end evidence run (1 GPU): full GPU test-suite, sweep, bench (ours + reference arm), ncu launch list + full capture.
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/f_smi.txt 2>&1
+timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/f_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/f_pytest.log
+tail -4 gpurun_out/f_pytest.log
+timeout 600 python tools/sweep.py > gpurun_out/f_sweep.jsonl 2> gpurun_out/f_sweep.err
+timeout 600 python tools/sweep.py card >> gpurun_out/f_sweep.jsonl 2>> gpurun_out/f_sweep.err
+cut -c1-160 gpurun_out/f_sweep.jsonl
+timeout 900 python bench.py --steps 256 --warmup 8 > gpurun_out/f_bench.json 2> gpurun_out/f_bench.err
+cut -c1-900 gpurun_out/f_bench.json
+timeout 600 python bench.py --impl reference --steps 4 --warmup 1 > gpurun_out/f_bench_ref.json 2> gpurun_out/f_bench_ref.err
+cut -c1-600 gpurun_out/f_bench_ref.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/f_launches.csv \
+   python bench.py --steps 8 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/f_ncu_launches.log 2>&1
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:detect_kernel -s 3 -c 1 -f -o gpurun_out/f_full \
+   python bench.py --steps 4 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/f_ncu_full.log 2>&1
+ls -la gpurun_out | tail -15
