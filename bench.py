@@ -187,7 +187,7 @@ def run_reference_arm(args):
     line = {
         "impl": "reference",
         "metric": "detect Msamples/s (block_len=16384)", "value": value, "unit": "Msamples/s",
-        "n_gpus": 0, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64 (numpy)",
         "data": "synthetic",
         "config": {"workload": workload_name(args), "block_len": BLOCK_LEN, "batch": args.batch,

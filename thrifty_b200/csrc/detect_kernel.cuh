@@ -1323,17 +1323,21 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                     }
                 }
                 const int rel = (int)ra.key;
-                const float2 *tsp = p.tpl_shift ? p.tpl_shift + (size_t)rel * N : nullptr;
-                corr_stage(q, 0,
-                           [&](int it, int g, int k3) {
-                               if (tsp) return __ldg(&tsp[(size_t)(it * R3 + k3) * T + tid]);
-                               const int k = (g >> LOG2R2) + 32 * (g & (R2 - 1)) + S * k3;
-                               return __ldg(&p.tpl_nat[(k - kpeak) & (N - 1)]);
-                           },
-                           [&](int it, int, uint32_t, float2 (&x)[R3]) {
+                auto keep_x = [&](int it, int, uint32_t, float2 (&x)[R3]) {
 #pragma unroll
-                               for (int k3 = 0; k3 < R3; ++k3) x[k3] = xk[it][k3];
-                           });
+                    for (int k3 = 0; k3 < R3; ++k3) x[k3] = xk[it][k3];
+                };
+                if (p.tpl_shift) {      // pre-rolled template spectrum of this carrier bin: coalesced, base + immediate
+                    const float2 *tsp = p.tpl_shift + (size_t)rel * N + tid;
+                    corr_stage(q, 0, [&](int it, int, int k3) { return __ldg(&tsp[(it * R3 + k3) * T]); }, keep_x);
+                } else {                // window too wide for a table: gather from the natural-order spectrum
+                    corr_stage(q, 0,
+                               [&](int, int g, int k3) {
+                                   const int k = (g >> LOG2R2) + 32 * (g & (R2 - 1)) + S * k3;
+                                   return __ldg(&p.tpl_nat[(k - kpeak) & (N - 1)]);
+                               },
+                               keep_x);
+                }
             }
             if constexpr (SERVICE) {
                 bar_arrive(BAR_TAILREQ + q, NTHREADS);

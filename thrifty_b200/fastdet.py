@@ -200,7 +200,17 @@ def main(argv=None):
     parser.add_argument("-q", "--quiet", action="store_true")
     parser.add_argument("--batch", type=int, default=256)
     parser.add_argument("--device", type=int, default=0)
-    args = parser.parse_args(argv)
+    # argp takes "-w -110--7"; argparse would read the negative window as an option: glue such values with '='
+    argv = list(sys.argv[1:] if argv is None else argv)
+    glued, i = [], 0
+    while i < len(argv):
+        if argv[i] in ("-w", "--carrier-window") and i + 1 < len(argv) and re.match(r"-\d", argv[i + 1]):
+            glued.append("--carrier-window=" + argv[i + 1])
+            i += 2
+        else:
+            glued.append(argv[i])
+            i += 1
+    args = parser.parse_args(glued)
 
     thresh = parse_threshold(args.threshold)
     corr_thresh = parse_threshold(args.corr_threshold)
