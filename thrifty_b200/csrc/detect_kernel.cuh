@@ -28,24 +28,9 @@
 #ifndef THR_WL23
 #define THR_WL23 1          // warp-local hand-over between passes 2 and 3 (no CTA barrier)
 #endif
-#ifndef THR_RHO128
-#define THR_RHO128 1        // mix phasor table read two entries per LDS.128 (broadcast)
-#endif
-#ifndef THR_PACKRAW
-#define THR_PACKRAW 1       // rawconv and the Parseval energy on packed FP32x2 instructions
-#endif
 #ifndef THR_TW3
 #define THR_TW3 1           // (+2 %) inter-pass twiddles W_M^{n3 k2} of FFT#2 / IFFT applied on the pass-3 side from a
                             // per-item register chain instead of the shared-memory table on the pass-2 side
-#endif
-#ifndef THR_ASYNC_TAIL
-#define THR_ASYNC_TAIL 0    // (measured 1.5 % slower: 32 extra st.cg per thread cost more than the barrier) correlation arg-max with ONE CTA barrier: |c|^2 of every lag goes to an L2 scratch, the
-                            // winning thread posts the peak lag with an atomic, the service warp fetches the
-                            // neighbours; nobody waits for the index (single-template kernels)
-#endif
-#ifndef THR_ARGMAX1
-#define THR_ARGMAX1 0       // block arg-max with one CTA barrier (per-warp first index) instead of two:
-                            // measured 4 % slower (every warp pays the index scan), kept for reference
 #endif
 
 namespace thr {
@@ -62,7 +47,6 @@ struct DetectParams {
     const float  *tpl_energy;  // [n_templates] sum(template^2)
     float2 *scratch;           // per-CTA global scratch: [grid][N] FFT buffer (GMEM variant)
     float2 *xsave;             // per-CTA save area for X' when n_templates > 1: [grid][N]
-    float  *cpsave;            // per-CTA |c|^2 of every lag, double buffered: [grid][2][N] (THR_ASYNC_TAIL)
     int win_start, win_len;    // carrier window: start index in [0,N), number of bins
     float c_const, c_snr, c_std;   // carrier threshold coefficients
     float k_const, k_snr, k_std;   // correlation threshold coefficients
@@ -455,16 +439,10 @@ __device__ __forceinline__ float dirichlet_fit(float y, int lane, const DetectPa
 // rounds the exact value (b - 127.4f) * 2^-7, which is representable.
 __device__ __forceinline__ float2 rawconv(uint32_t w16) {
     constexpr float c = -127.4f * 0.0078125f;
-#if THR_PACKRAW
     const float2 f = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(w16, 0x4B000000u, 0x7650)),
                                             __uint_as_float(__byte_perm(w16, 0x4B000000u, 0x7651))),
                                 make_float2(-8388608.0f, -8388608.0f));
     return __ffma2_rn(f, make_float2(0.0078125f, 0.0078125f), make_float2(c, c));
-#else
-    const float fx = __uint_as_float(__byte_perm(w16, 0x4B000000u, 0x7650)) - 8388608.0f;
-    const float fy = __uint_as_float(__byte_perm(w16, 0x4B000000u, 0x7651)) - 8388608.0f;
-    return make_float2(fmaf(fx, 0.0078125f, c), fmaf(fy, 0.0078125f, c));
-#endif
 }
 
 // ------------------------------------------------------------------ named barriers
@@ -525,42 +503,6 @@ __device__ __forceinline__ ArgOut main_argmax(uint32_t vbits, float s0, float s1
         s1 = warp_sum(s1);
     }
     const int w = tid >> 5;
-#if THR_ARGMAX1
-    if (NW <= 16) {
-        // one barrier: every warp resolves the first index of its own maximum, the (value, key) pairs
-        // of the NW warps are then combined by every thread
-        uint32_t key = 0xffffffffu;
-        if (vbits == wmax) key = find_key(wmax);
-        key = __reduce_min_sync(0xffffffffu, key);
-        if ((tid & 31) == 0) {
-            red[w] = wmax;
-            red[48 + w] = key;
-            if (SUMS) {
-                red[16 + w] = __float_as_uint(s0);
-                red[32 + w] = __float_as_uint(s1);
-            }
-        }
-        bar_sync(BAR_MAIN, T);
-        ArgOut r;
-        r.vbits = 0u;
-        r.key = 0xffffffffu;
-        r.s0 = 0.f;
-        r.s1 = 0.f;
-#pragma unroll
-        for (int i = 0; i < NW; ++i) {
-            const uint32_t v = red[i], k = red[48 + i];
-            if (v > r.vbits || (v == r.vbits && k < r.key)) {
-                r.vbits = v;
-                r.key = k;
-            }
-            if (SUMS) {
-                r.s0 += __uint_as_float(red[16 + i]);
-                r.s1 += __uint_as_float(red[32 + i]);
-            }
-        }
-        return r;
-    }
-#endif
     if ((tid & 31) == 0) {
         red[w] = wmax;
         if (SUMS) {
@@ -603,7 +545,6 @@ __global__ void __launch_bounds__(Cfg<LOG2N, T, GMEM>::LAUNCH_THREADS, Cfg<LOG2N
 detect_kernel(const __grid_constant__ DetectParams p) {
     using C = Cfg<LOG2N, T, GMEM>;
     constexpr bool SERVICE = C::SERVICE;
-    constexpr bool ASYNC_TAIL = (THR_ASYNC_TAIL != 0) && !MULTI;   // see corr_stage
     constexpr bool TW3 = (THR_TW3 != 0) && !MULTI && !FASTDET && C::R3 == 16 && C::R2 > 1;
     constexpr int N = C::N, M = C::M, R2 = C::R2, R3 = C::R3, S = C::S;
     constexpr int I1 = C::I1, I2 = C::I2, I3 = C::I3;
@@ -707,14 +648,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
             } else {
                 // scalar tail (soa_estimator.py:78-134,159-170); float32 except the SoA itself
                 const TailSlot &ts = tailslot[q * C::MAX_TPL + tpl];
-                float pa = ts.pa, pc = ts.pc;
-                if constexpr (ASYNC_TAIL) {     // neighbours of the peak from the |c|^2 scratch of this block
-                    const float *cpq = p.cpsave + ((size_t)blockIdx.x * 2 + (size_t)q) * N;
-                    if (ts.s > 0 && ts.s < p.corr_len - 1) {
-                        pa = __ldcg(&cpq[ts.s - 1]);
-                        pc = __ldcg(&cpq[ts.s + 1]);
-                    }
-                }
+                const float pa = ts.pa, pc = ts.pc;
                 const float peak_mag_k = sqrtf(ts.peak_cp);
                 // mean |X'|^2 (soa_estimator.py:111) == sum |x|^2 == mean |X|^2 of FFT#1: the mix is a
                 // unit-modulus rotation and both FFTs are unitary up to N (Parseval)
@@ -777,14 +711,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 const float ca = sqrtf(h.pad[0]), cb = sqrtf(h.peak_mag), cc = sqrtf(h.pad[1]);
                 const float coff = fminf(fmaxf((cc - ca) / (4.f * cb - 2.f * ca - 2.f * cc), -0.5f), 0.5f);
                 const TailSlot &ts = tailslot[q * C::MAX_TPL];
-                float pa = ts.pa, pc = ts.pc;
-                if constexpr (ASYNC_TAIL) {
-                    const float *cpq = p.cpsave + ((size_t)blockIdx.x * 2 + (size_t)q) * N;
-                    if (ts.s > 0 && ts.s < p.corr_len - 1) {
-                        pa = __ldcg(&cpq[ts.s - 1]);
-                        pc = __ldcg(&cpq[ts.s + 1]);
-                    }
-                }
+                const float pa = ts.pa, pc = ts.pc;
                 // corr_detector.cpp:118-125: the peak power arrives as size_t (truncated), noise clamped at 0
                 float noise_pw = (h.sig_energy1 * p.tpl_energy[0] - truncf(ts.peak_cp)) / (float)N;
                 noise_pw = noise_pw < 0.f ? 0.f : noise_pw;
@@ -907,20 +834,14 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 for (int n1 = 0; n1 < 32; ++n1) x[brev(n1, 5)] = __ldg(&iqb[n1 * M + j]);
             }
             if (!mix && zoom) {                  // sum |x|^2 (Parseval: sum_k |X[k]|^2 = N sum_n |x[n]|^2)
-#if THR_PACKRAW
                 float2 e2 = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int n1 = 0; n1 < 32; ++n1) e2 = __ffma2_rn(x[n1], x[n1], e2);
                 energy += e2.x + e2.y;
-#else
-#pragma unroll
-                for (int n1 = 0; n1 < 32; ++n1) energy = fmaf(x[n1].x, x[n1].x, fmaf(x[n1].y, x[n1].y, energy));
-#endif
             }
             if (mix) {
                 // row phasor here; the per-thread phasor ph0 is common to the whole item and is
                 // folded into the twiddle seeds below (the DFT is linear)
-#if THR_RHO128
                 const float4 *rho4 = reinterpret_cast<const float4 *>(rho);
 #pragma unroll
                 for (int n1 = 0; n1 < 32; n1 += 2) {
@@ -928,10 +849,6 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                     if (n1 > 0) x[brev(n1, 5)] = cmul(x[brev(n1, 5)], make_float2(r.x, r.y));
                     x[brev(n1 + 1, 5)] = cmul(x[brev(n1 + 1, 5)], make_float2(r.z, r.w));
                 }
-#else
-#pragma unroll
-                for (int n1 = 1; n1 < 32; ++n1) x[brev(n1, 5)] = cmul(x[brev(n1, 5)], rho[n1]);
-#endif
             }
             fft_dit<32, false>(x);
             // Twiddles W_N^{j k1} are regenerated per block from two per-thread seeds.  The opaque
@@ -1044,7 +961,6 @@ detect_kernel(const __grid_constant__ DetectParams p) {
         cur3w4 = cur[3];
     };
     auto corr_stage = [&](int q, int tpl, auto &&get_tv, auto &&get_x) {
-        [[maybe_unused]] float *cpq = ASYNC_TAIL ? p.cpsave + ((size_t)blockIdx.x * 2 + (size_t)q) * N : nullptr;
 #pragma unroll
         for (int it = 0; it < I3; ++it) {
             const int g = C::p3_item(tid, it);
@@ -1131,7 +1047,6 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 const float pv = x[n1].x * x[n1].x + x[n1].y * x[n1].y;
                 cp[it][n1] = pv;
                 if (inmask[it] & (1u << n1)) cbestv = fmaxf(cbestv, pv);
-                if constexpr (ASYNC_TAIL) __stcg(&cpq[n1 * M + j], pv);
             }
             if (need_std_k) {
 #pragma unroll
@@ -1161,67 +1076,29 @@ detect_kernel(const __grid_constant__ DetectParams p) {
             return key;
         };
         TailSlot &ts = tailslot[q * C::MAX_TPL + tpl];
-        if constexpr (ASYNC_TAIL) {
-            // one barrier: block maximum by value; the thread(s) holding it post the first lag with an atomic and
-            // everybody moves on -- the service warp reads lag and neighbours after the TAILREQ hand-over
-            constexpr int NW = T / 32;
-            const uint32_t vbits = __float_as_uint(cbestv);
-            const uint32_t wmax = __reduce_max_sync(0xffffffffu, vbits);
-            if (need_std_k) {
-                c1sum = warp_sum(c1sum);
-                c2sum = warp_sum(c2sum);
-            }
-            if (lane == 0) {
-                red[tid >> 5] = wmax;
-                if (need_std_k) {
-                    red[16 + (tid >> 5)] = __float_as_uint(c1sum);
-                    red[32 + (tid >> 5)] = __float_as_uint(c2sum);
-                }
-                if (tid == 0) ts.s = -1;                       // 0xffffffff: no lag posted yet
-            }
-            bar_sync(BAR_MAIN, T);
-            uint32_t gmax = 0u;
+        ArgOut rb;
+        if (need_std_k) rb = main_argmax<T, true>(__float_as_uint(cbestv), c1sum, c2sum, red, tid, find_lag);
+        else rb = main_argmax<T, false>(__float_as_uint(cbestv), 0.f, 0.f, red, tid, find_lag);
+        const int s = (int)rb.key;
+        if (tid == 0) {
+            ts.peak_cp = __uint_as_float(rb.vbits);
+            ts.s = s;
+            ts.c1 = rb.s0;
+            ts.c2 = rb.s1;
+        }
+        // neighbours of the peak for the Gaussian interpolation
 #pragma unroll
-            for (int w = 0; w < NW; ++w) gmax = max(gmax, red[w]);
-            if (tid == 0) {
-                ts.peak_cp = __uint_as_float(gmax);
-                float a1 = 0.f, a2 = 0.f;
-                if (need_std_k) {
+        for (int it = 0; it < I1; ++it) {
+            const int j = tid + T * it;
 #pragma unroll
-                    for (int w = 0; w < NW; ++w) {
-                        a1 += __uint_as_float(red[16 + w]);
-                        a2 += __uint_as_float(red[32 + w]);
-                    }
-                }
-                ts.c1 = a1;
-                ts.c2 = a2;
-            }
-            if (vbits == gmax) atomicMin(reinterpret_cast<unsigned int *>(&ts.s), find_lag(gmax));
-        } else {
-            ArgOut rb;
-            if (need_std_k) rb = main_argmax<T, true>(__float_as_uint(cbestv), c1sum, c2sum, red, tid, find_lag);
-            else rb = main_argmax<T, false>(__float_as_uint(cbestv), 0.f, 0.f, red, tid, find_lag);
-            const int s = (int)rb.key;
-            if (tid == 0) {
-                ts.peak_cp = __uint_as_float(rb.vbits);
-                ts.s = s;
-                ts.c1 = rb.s0;
-                ts.c2 = rb.s1;
-            }
-            // neighbours of the peak for the Gaussian interpolation
+            for (int dd = -1; dd <= 1; dd += 2) {
+                const int nt = s + dd;
+                if (nt >= 0 && nt < N && (nt & (M - 1)) == j) {
+                    const int n1s = nt >> LOG2M;
+                    float v = 0.f;
 #pragma unroll
-            for (int it = 0; it < I1; ++it) {
-                const int j = tid + T * it;
-#pragma unroll
-                for (int dd = -1; dd <= 1; dd += 2) {
-                    const int nt = s + dd;
-                    if (nt >= 0 && nt < N && (nt & (M - 1)) == j) {
-                        const int n1s = nt >> LOG2M;
-                        float v = 0.f;
-#pragma unroll
-                        for (int n1 = 0; n1 < 32; ++n1) v = (n1 == n1s) ? cp[it][n1] : v;
-                        if (dd < 0) ts.pa = v; else ts.pc = v;
-                    }
+                    for (int n1 = 0; n1 < 32; ++n1) v = (n1 == n1s) ? cp[it][n1] : v;
+                    if (dd < 0) ts.pa = v; else ts.pc = v;
                 }
             }
         }

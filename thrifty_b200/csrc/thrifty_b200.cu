@@ -14,6 +14,7 @@
 #include <complex>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -69,7 +70,6 @@ struct thr_detector {
     float *d_tpl_energy = nullptr;
     float2 *d_scratch = nullptr;
     float2 *d_xsave = nullptr;
-    float *d_cpsave = nullptr;           // |c|^2 scratch of the single-template kernels: [grid][2][N]
     unsigned int *d_bad = nullptr;       // invalid base64 character counter (.card ingest)
     Slot slot[2];
     int c64_chunk = 0;
@@ -212,7 +212,6 @@ void thr_destroy(thr_detector *d) {
     cudaFree(d->d_tpl_energy);
     cudaFree(d->d_scratch);
     cudaFree(d->d_xsave);
-    cudaFree(d->d_cpsave);
     cudaFree(d->d_bad);
     delete d;
 }
@@ -304,6 +303,10 @@ int thr_create(const thr_config *cfg, thr_detector **out) {
     }
     d->ctas_per_sm = occ;
     d->grid = d->sm_count * occ;
+    if (const char *cap = std::getenv("THRIFTY_B200_MAX_GRID")) {      // testing aid: few CTAs walk many blocks each
+        const int g = std::atoi(cap);                                  // (compute-sanitizer runs on small inputs)
+        if (g >= 1 && g < d->grid) d->grid = g;
+    }
     if (use_2x)
         CUC(cudaFuncSetAttribute(var_generic.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)var_generic.smem));
 
@@ -385,7 +388,6 @@ int thr_create(const thr_config *cfg, thr_detector **out) {
     }
     if (var.gmem || use_2x) CUC(cudaMalloc(&d->d_scratch, (size_t)d->grid * N * sizeof(float2)));
     if (NT > 1) CUC(cudaMalloc(&d->d_xsave, (size_t)d->grid * N * sizeof(float2)));
-    else CUC(cudaMalloc(&d->d_cpsave, (size_t)d->grid * 2 * N * sizeof(float)));
     for (auto &s : d->slot) {
         CUC(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         CUC(cudaMalloc(&s.d_in, (size_t)cfg->max_batch * 2 * N));
@@ -408,7 +410,6 @@ int thr_create(const thr_config *cfg, thr_detector **out) {
     p.tpl_nat = d->d_tpl_nat;
     p.scratch = d->d_scratch;
     p.xsave = d->d_xsave;
-    p.cpsave = d->d_cpsave;
     p.win_start = ws % N;
     p.win_len = (we - ws + 1) > N ? N : (we - ws + 1);
     // pruned FFT#1: every window bin and its +-3 fit neighbours inside [0,128), no stddev term

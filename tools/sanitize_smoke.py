@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """Tiny workloads for compute-sanitizer (memcheck / racecheck / synccheck):
 
-    compute-sanitizer --tool racecheck python tools/sanitize_smoke.py
+    THRIFTY_B200_MAX_GRID=2 compute-sanitizer --tool racecheck python tools/sanitize_smoke.py
+
+With the grid capped at 2 CTAs every CTA walks several blocks, so the software pipeline (stage A of block
+i+1 next to the fit / tail of earlier blocks, raw-tile ring, mailboxes) is exercised, not just its prologue.
 """
 import os
 import sys
@@ -14,12 +17,26 @@ from thrifty_b200 import synth  # noqa: E402
 from thrifty_b200._native import NativeDetector  # noqa: E402
 
 example = np.load(os.path.join(ROOT, "tests", "golden", "template_example.npy"))
-cases = [(16384, example, 4920, (7, 110), 10), (16384, example, 4920, (7, 300), 6),
-         (4096, synth.gold_template(9), None, (7, 110), 12), (32768, example, 4920, (7, 110), 3)]
-for n, tpl, hist, win, nblk in cases:
-    hist = hist or len(tpl) + 6
-    raw, _ = synth.make_blocks(nblk, n, hist, tpl, 0.7, seed=5)
-    det = NativeDetector(n, hist, tpl, len(tpl), win, (0., 15., 0.), (0., 15., 0.), max_batch=4)
+t9, t10 = synth.gold_template(9), synth.gold_template(10)
+t11 = np.stack([synth.gold_template(11, i) for i in range(2)])
+# (block_len, template(s), history, window, blocks, detector kwargs)
+cases = [
+    (16384, example, 4920, (7, 110), 10, {}),                          # pruned FFT#1, service warpgroup
+    (16384, example, 4920, (7, 300), 8, {}),                           # full FFT#1
+    (16384, example, 4920, (7, 110), 8, dict(fastdet=True)),           # fastdet semantics (shifted-template table)
+    (16384, t11, None, (7, 110), 6, {}),                               # two templates
+    (8192, t10, None, (7, 110), 10, {}),                               # 2 CTAs/SM variant, inline service
+    (4096, t9, None, (7, 110), 12, {}),
+    (4096, t9, None, (1, 2047), 8, dict(fastdet=True)),                # fastdet gather fall-back
+    (32768, example, 4920, (7, 110), 7, {}),                           # 2 x 16384 kernel
+    (32768, example, 4920, (7, 110), 4, dict(generic_kernel=True)),    # global-scratch variant
+]
+for n, tpl, hist, win, nblk, kw in cases:
+    tpl0 = tpl[0] if tpl.ndim == 2 else tpl
+    hist = hist or len(tpl0) + 6
+    raw, _ = synth.make_blocks(nblk, n, hist, tpl0, 0.7, seed=5)
+    det = NativeDetector(n, hist, tpl, len(tpl0), win, (0., 15., 0.), (0., 15., 0.), max_batch=16, **kw)
     rec = det.detect_raw(raw)
-    print(n, win, "carrier", int((rec["flags"] & 1).sum()), "detected", int(((rec["flags"] & 2) != 0).sum()), flush=True)
+    print(n, win, kw, det.info()["kernel"], "grid", det.info()["grid"], "carrier", int((rec["flags"] & 1).sum()),
+          "detected", int(((rec["flags"] & 2) != 0).sum()), flush=True)
     det.close()
