@@ -242,7 +242,10 @@ def test_fresh_seeds_vs_oracle(block_len, n_blocks, seed):
     ((7, 300), (0., 15., 0.), (0., 15., 0.)),         # window beyond bin 124: full FFT#1 path
     ((7, 110), (1., 12., 2.), (0.5, 10., 3.)),        # stddev terms: full FFT#1 path, extra reductions
     ((-300, -7), (0., 15., 0.), (0., 15., 0.)),       # negative-frequency window
-    ((3, 124), (0., 15., 0.), (0., 15., 0.)),         # widest window the pruned FFT#1 path accepts
+    ((3, 124), (0., 15., 0.), (0., 15., 0.)),         # widest window the pruned FFT#1 path accepts without pre-shift
+    ((-110, -7), (0., 15., 0.), (0., 15., 0.)),       # narrow negative-frequency window: pruned path, band pre-shifted
+    ((300, 400), (0., 15., 0.), (0., 15., 0.)),       # narrow window far from DC: pruned path, band pre-shifted
+    ((16000, 16100), (0., 15., 0.), (0., 15., 0.)),   # same, given as unsigned bins above N/2
 ])
 def test_n16384_carrier_paths(window, cthresh, kthresh):
     """N=16384: the pruned ('zoom') and the full FFT#1 carrier paths both match the oracle."""
@@ -466,3 +469,17 @@ def test_n32768_two_half_kernel_vs_generic_and_oracle(kthresh):
         assert np.array_equal(gotb[f][:40], got2[f], equal_nan=True), f
     two.close()
     gen.close()
+
+
+def test_shifted_zoom_band_small_blocks():
+    """Pruned FFT#1 with a pre-shifted band at N=4096 and 8192 (negative-frequency windows)."""
+    from thrifty_b200._native import NativeDetector
+    for n, tpl in ((4096, synth.gold_template(9)), (8192, synth.gold_template(10))):
+        hist = len(tpl) + 6
+        raw, _ = synth.make_blocks(64, n, hist, tpl, 0.7, seed=2468 + n, bin_range=(-108.0, -9.0))
+        st = orc.DetectorSettings(n, hist, len(tpl), (0., 15., 0.), (-110, -7), tpl, (0., 15., 0.))
+        ref = orc.detect_blocks(st, raw)
+        det = NativeDetector(n, hist, tpl, len(tpl), (-110, -7), (0., 15., 0.), (0., 15., 0.), max_batch=64)
+        stats = parity.compare_records(det.detect_raw(raw)[:, 0], ref, what="N=%d window -110..-7" % n)
+        assert stats["carrier"] >= 30
+        det.close()

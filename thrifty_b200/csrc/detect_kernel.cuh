@@ -52,7 +52,9 @@ struct DetectParams {
     float k_const, k_snr, k_std;   // correlation threshold coefficients
     int corr_start, corr_stop, corr_len;
     int new_len;               // N - H
-    int zoom;                  // 1: carrier window (+-3 bins) lies in [0,128) and no stddev term -> pruned FFT#1
+    int zoom;                  // 1: carrier window (+-3 bins) spans <= 128 bins and no stddev term -> pruned FFT#1
+    int zoom_base;             // first bin b0 of the 128-bin zoom band: the block is pre-shifted by -b0 bins (0: none)
+    int zoom_w0;               // window start inside the band: (win_start - zoom_base) mod N
     float fit_tab[7][4];       // per fit point x=-3..3: sin(aWx), cos(aWx), sin(ax), cos(ax), a = pi/N
     float fit_W;               // carrier_len
     float fit_WoverN;          // W / N
@@ -119,7 +121,7 @@ struct Cfg {
     static constexpr bool ZOOM_OK = (R2 >= 8 && R2 % 4 == 0);      // bins < 128 <=> k2 < 4, k3 == 0
     static constexpr size_t smem_bytes() {           // must cover the carve-up in detect_kernel
         return BUF_BYTES + 2 * (size_t)(2 * N) + (size_t)M * 8
-               + 2 * 320 + 2 * 32 + 2 * MAX_TPL * 32 + 256 + 512 + 64;
+               + 2 * 320 + 2 * 32 + 2 * MAX_TPL * 32 + 256 + 512 + 256 + 64;
     }
 };
 
@@ -577,8 +579,10 @@ detect_kernel(const __grid_constant__ DetectParams p) {
     off += 2 * (size_t)C::MAX_TPL * sizeof(TailSlot);
     uint32_t *red = reinterpret_cast<uint32_t *>(smem + off);        // 64 words reduction scratch
     off += 256;
-    float *zpow = reinterpret_cast<float *>(smem + off);             // |X[k]|^2, k < 128 (zoom path)
+    float *zpow = reinterpret_cast<float *>(smem + off);             // |X[b0 + k]|^2, k < 128 (zoom path)
     off += 512;
+    float2 *zrho = reinterpret_cast<float2 *>(smem + off);           // W_32^{b0 n1}: row phasors of the zoom pre-shift
+    off += 256;
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + off);       // 2 barriers
 
     // Launch-invariant switches are re-read from the kernel parameters (constant bank, uniform
@@ -605,6 +609,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
         const int e = (n3 * k2) & (M - 1);
         tw2[idx] = cispi(-2.0f * (float)e / (float)M);
     }
+    if (tid < 32) zrho[tid] = cispi(-2.0f * (float)((p.zoom_base * tid) & 31) * 0.03125f);
     __syncthreads();
 
     // =====================================================================================
@@ -814,10 +819,14 @@ detect_kernel(const __grid_constant__ DetectParams p) {
     uint32_t par0 = 0, par1 = 0;    // phase parity of the two tile barriers
 
     // forward passes 1 and 2 of block i (shared by FFT#1 and FFT#2)
-    // zoom (pruned FFT#1): only bins [0,128) are needed, i.e. k3 == 0 and k2 < 4, so pass 2 computes
-    // 4 of its R2 outputs and pass 3 degenerates to a sum; the spectrum energy comes from Parseval
+    // zoom (pruned FFT#1): only the 128 bins [b0, b0+128) are needed; after the pre-shift by -b0 they are the bins
+    // k3 == 0, k2 < 4, so pass 2 computes 4 of its R2 outputs and pass 3 degenerates to a sum; the spectrum energy
+    // comes from Parseval
     const bool zoom = !FASTDET && C::ZOOM_OK && (p.zoom != 0) && (p.dbg_fft_mag == nullptr);
-    auto fwd_pass12 = [&](int i, bool mix, const float2 (&ph0)[I1], const float2 *rho, float &energy) {
+    //   shift : multiply the samples by a phasor exp(-2 pi i s n/N) = rho[n1] * ph0[j] (the mix of stage B, or the
+    //           integer pre-shift that moves an arbitrary narrow carrier window into the 128-bin zoom band)
+    //   stageB: FFT#2 (full pass 2, raw tile released after pass 1); otherwise FFT#1 (pruned if `zoom`)
+    auto fwd_pass12 = [&](int i, bool shift, bool stageB, const float2 (&ph0)[I1], const float2 *rho, float &energy) {
         const uint16_t *rawt = reinterpret_cast<const uint16_t *>(raw_s + (size_t)(i & 1) * RAW_BYTES);
         const float2 *iqb = use_raw ? nullptr : p.iq + (size_t)((int)blockIdx.x + i * (int)gridDim.x) * N;
         // pass 1: samples (rawconv or complex64) [* mix phasor] -> radix-32 over n1 (stride M)
@@ -833,13 +842,13 @@ detect_kernel(const __grid_constant__ DetectParams p) {
 #pragma unroll
                 for (int n1 = 0; n1 < 32; ++n1) x[brev(n1, 5)] = __ldg(&iqb[n1 * M + j]);
             }
-            if (!mix && zoom) {                  // sum |x|^2 (Parseval: sum_k |X[k]|^2 = N sum_n |x[n]|^2)
+            if (!stageB && zoom) {               // sum |x|^2 (Parseval: sum_k |X[k]|^2 = N sum_n |x[n]|^2)
                 float2 e2 = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int n1 = 0; n1 < 32; ++n1) e2 = __ffma2_rn(x[n1], x[n1], e2);
                 energy += e2.x + e2.y;
             }
-            if (mix) {
+            if (shift) {
                 // row phasor here; the per-thread phasor ph0 is common to the whole item and is
                 // folded into the twiddle seeds below (the DFT is linear)
                 const float4 *rho4 = reinterpret_cast<const float4 *>(rho);
@@ -862,7 +871,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
             cur[2] = cmul(cur[1], ws);
             cur[3] = ws4;
             const uint32_t ab = a1_base(j);
-            if (mix) {
+            if (shift) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) cur[c] = cmul(cur[c], ph0[it]);
                 st8(ab, cmul(x[0], ph0[it]));
@@ -878,9 +887,9 @@ detect_kernel(const __grid_constant__ DetectParams p) {
         bar_sync(BAR_MAIN, T);
         // after the pass-1 barrier of the mix pass nobody reads this raw stage any more:
         // prefetch the tile of block i+2 into it
-        if ((mix || FASTDET) && use_raw && tid == 0 && has_block(i + 2)) issue_tile(i + 2);
+        if ((stageB || FASTDET) && use_raw && tid == 0 && has_block(i + 2)) issue_tile(i + 2);
         if constexpr (C::ZOOM_OK) {
-            if (!mix && zoom) {
+            if (!stageB && zoom) {
                 // pruned pass 2: outputs k2 = 0..3 of the R2-point DFT over n2 = Q m + r (Q = R2/4):
                 //   c_r[k] = sum_m a[Q m + r] W_4^{mk}    (radix-4, no multiplications)
                 //   B[k]   = sum_r W_R2^{rk} c_r[k]       (2 packed FMAs per term; W_R2 = W_32^(32/R2))
@@ -938,7 +947,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
 #pragma unroll
                 for (int k2 = 0; k2 < R2; ++k2) {
                     float2 v = x[k2];
-                    if (k2 > 0 && !(TW3 && mix)) v = cmul(v, tw2[k2 * R3 + n3]);
+                    if (k2 > 0 && !(TW3 && stageB)) v = cmul(v, tw2[k2 * R3 + n3]);
                     st8(ab + (uint32_t)k2 * A2_STEP, v);
                 }
             }
@@ -1122,7 +1131,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
 #pragma unroll
             for (int it = 0; it < I1; ++it) ph_unused[it] = make_float2(1.f, 0.f);
             float tenergy = 0.f;
-            fwd_pass12(i, false, ph_unused, nullptr, tenergy);
+            fwd_pass12(i, false, false, ph_unused, nullptr, tenergy);
             // pass 3, power spectrum (fastcard.c:180), sum (cardet.c:12) and windowed maximum (cardet.c:15-19)
             float2 xk[I3][R3];
             float esum = 0.f, bestv = 0.f;
@@ -1234,11 +1243,20 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 mbar_wait(&mbar[q], q ? par1 : par0);
                 if (q) par1 ^= 1; else par0 ^= 1;
             }
-            float2 ph_unused[I1];
+            // zoom band not at bin 0: pre-shift the block by -b0 bins, folded into pass 1 like the mix of stage B
+            const bool shiftA = zoom && (p.zoom_base != 0);
+            float2 phA[I1];
 #pragma unroll
-            for (int it = 0; it < I1; ++it) ph_unused[it] = make_float2(1.f, 0.f);
+            for (int it = 0; it < I1; ++it) {
+                phA[it] = make_float2(1.f, 0.f);
+                if (shiftA) {
+                    const int e = (int)(((long long)p.zoom_base * (tid + T * it)) & (N - 1));
+                    phA[it] = cispi(-2.0f * (float)e / (float)N);
+                }
+            }
             float tenergy = 0.f;
-            fwd_pass12(ia, false, ph_unused, nullptr, tenergy);
+            if (shiftA) fwd_pass12(ia, true, false, phA, zrho, tenergy);     // two specialised copies: a run-time
+            else fwd_pass12(ia, false, false, phA, zrho, tenergy);           // flag inside pass 1 costs registers
 
             FitSlot &fs = fitslot[q];
             // carrier decision in float32 (carrier_detect.py:99-115); returns the peak bin or -1
@@ -1308,7 +1326,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const int k = lane + 32 * c;
-                    const uint32_t rel = (uint32_t)(k - p.win_start);
+                    const uint32_t rel = (uint32_t)(k - p.zoom_w0);
                     vb = max(vb, rel < (uint32_t)p.win_len ? __float_as_uint(zpow[k]) : 0u);
                 }
                 const uint32_t gb = __reduce_max_sync(0xffffffffu, vb);
@@ -1316,7 +1334,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
 #pragma unroll
                 for (int c = 3; c >= 0; --c) {
                     const int k = lane + 32 * c;
-                    const uint32_t rel = (uint32_t)(k - p.win_start);
+                    const uint32_t rel = (uint32_t)(k - p.zoom_w0);
                     if (rel < (uint32_t)p.win_len && __float_as_uint(zpow[k]) == gb) key = rel;
                 }
                 ra.vbits = gb;
@@ -1328,7 +1346,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 ra.s1 = 0.f;
                 const int kpeak = decide(ra);
                 // the 7 magnitudes around the peak for the Dirichlet fit
-                if (kpeak >= 0 && tid < 7) fs.mags[tid] = sqrtf(zpow[kpeak - 3 + tid]);
+                if (kpeak >= 0 && tid < 7) fs.mags[tid] = sqrtf(zpow[p.zoom_w0 + (int)ra.key - 3 + tid]);
             } else {
                 // pass 3 + power spectrum (Signal.mag, signal_utils.py:99-107) + windowed arg-max
                 float pw[I3][R3];
@@ -1459,7 +1477,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 ph0[it] = cispi(2.f * turns);
             }
             float unused_energy = 0.f;
-            fwd_pass12(i, true, ph0, fs.rho, unused_energy);
+            fwd_pass12(i, true, true, ph0, fs.rho, unused_energy);
 
             // ---- pass 3 of FFT#2, then per template: x conj(T)/N and the inverse transform
             for (int tpl = 0; tpl < n_tpl; ++tpl) {

@@ -250,10 +250,14 @@ int thr_create(const thr_config *cfg, thr_detector **out) {
 
     // block_len 32768 with a pruned-FFT#1 configuration: two interleaved 16384-point transforms in shared memory
     // (detect_kernel_2x.cuh) instead of the generic global-scratch variant, which stays for debug launches
-    const bool zoom_cfg = (!fastdet && ws >= 3 && we + 3 < 128 && we < N && cfg->carrier_thresh[2] == 0.0 && N >= 4096);
+    // pruned FFT#1: the carrier window and its +-3 fit neighbours span at most 128 consecutive bins (mod N), no stddev
+    // term.  The band starts at bin 0 when the window lies in [3,124] (no pre-shift), else 3 bins below the window.
+    const int wlen_cfg = (we - ws + 1) > N ? N : (we - ws + 1);
+    const bool zoom_cfg = (!fastdet && wlen_cfg + 6 <= 128 && cfg->carrier_thresh[2] == 0.0 && N >= 4096);
+    const int zoom_base = (ws >= 3 && we + 3 < 128) ? 0 : ((ws % N) - 3 + N) % N;
     Variant var_generic = var;
     bool use_2x = false;
-    if (zoom_cfg && NT == 1 && N == 32768 && !(cfg->flags & THR_CFG_GENERIC_KERNEL)) {
+    if (zoom_cfg && zoom_base == 0 && NT == 1 && N == 32768 && !(cfg->flags & THR_CFG_GENERIC_KERNEL)) {
         Variant v2;
         if (thr::pick_variant_2x(N, &v2)) {
             var = v2;
@@ -414,6 +418,8 @@ int thr_create(const thr_config *cfg, thr_detector **out) {
     p.win_len = (we - ws + 1) > N ? N : (we - ws + 1);
     // pruned FFT#1: every window bin and its +-3 fit neighbours inside [0,128), no stddev term
     p.zoom = zoom_cfg ? 1 : 0;
+    p.zoom_base = zoom_cfg ? zoom_base : 0;
+    p.zoom_w0 = ((ws % N) - p.zoom_base + N) % N;
     p.c_const = (float)cfg->carrier_thresh[0];
     p.c_snr = (float)cfg->carrier_thresh[1];
     p.c_std = (float)cfg->carrier_thresh[2];

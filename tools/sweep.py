@@ -22,10 +22,10 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
 def run(block_len, templates, history, batch, p_signal, steps=64, warmup=4, window=(7, 110), unique=256,
-        label="", fastdet=False):
+        label="", fastdet=False, bin_range=(8.0, 109.0)):
     lib = load_library()
     tpl0 = templates[0] if templates.ndim == 2 else templates
-    raw, _ = synth.make_blocks(unique, block_len, history, tpl0, p_signal, seed=424242)
+    raw, _ = synth.make_blocks(unique, block_len, history, tpl0, p_signal, seed=424242, bin_range=bin_range)
     n_tpl = templates.shape[0] if templates.ndim == 2 else 1
     det = NativeDetector(block_len, history, templates, len(tpl0), window, (0., 15., 0.), (0., 15., 0.),
                          max_batch=batch, overlap_launches=True, fastdet=fastdet)
@@ -158,6 +158,8 @@ def main():
     run(8192, t10, len(t10) + 6, 4096, 1.0, label="cfg3 N=8192")
     run(16384, example, 4920, 4096, 1.0, label="cfg3 N=16384 (headline, pruned FFT#1)")
     run(16384, example, 4920, 4096, 1.0, window=(7, 300), label="N=16384 full FFT#1 (window 7-300)")
+    run(16384, example, 4920, 4096, 1.0, window=(-110, -7), bin_range=(-108.0, -9.0),
+        label="N=16384 window -110..-7 (pruned FFT#1, pre-shifted band)")
     run(32768, example, 4920, 2048, 1.0, steps=16, label="cfg3 N=32768 (2 x 16384 kernel)")
     # signal mixes at N=16384
     run(16384, example, 4920, 4096, 0.5, label="N=16384 50% burst blocks")
