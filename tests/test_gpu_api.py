@@ -483,3 +483,30 @@ def test_shifted_zoom_band_small_blocks():
         stats = parity.compare_records(det.detect_raw(raw)[:, 0], ref, what="N=%d window -110..-7" % n)
         assert stats["carrier"] >= 30
         det.close()
+
+
+@pytest.mark.parametrize("tpl_len,hist", [(1226, 1225), (1226, 1232), (1226, 3000), (700, 699), (333, 1000)])
+def test_template_and_history_geometries_with_edge_peaks(tpl_len, hist):
+    """Ragged template lengths, minimal history (H = L-1: every lag is in the peak window) and long history;
+    bursts forced onto the first / last lag of the peak window and just outside it (soa_estimator.py:20-39,137-143)."""
+    from thrifty_b200._native import NativeDetector
+    n = 4096
+    tpl = synth.gold_template(9)[:tpl_len]
+    start, stop = synth.peak_window(n, hist, tpl_len)
+    positions = [start, start + 1, stop - 2, stop - 1, max(start - 1, 0), min(stop, n - tpl_len)]
+    raws = []
+    for b in range(48):
+        rng = np.random.default_rng(8800 + 97 * b + tpl_len)
+        raw, _ = synth.make_block(rng, n, hist, tpl, 1.0, force_pos=positions[b % len(positions)] if b < 36 else None)
+        raws.append(raw)
+    raw = np.stack(raws)
+    st = orc.DetectorSettings(n, hist, tpl_len, (0., 15., 0.), (7, 110), tpl, (0., 15., 0.))
+    with np.errstate(all="ignore"):
+        ref = orc.detect_blocks(st, raw)
+    det = NativeDetector(n, hist, tpl, tpl_len, (7, 110), (0., 15., 0.), (0., 15., 0.), max_batch=64)
+    got = det.detect_raw(raw)[:, 0]
+    stats = parity.compare_records(got, ref, what="L=%d H=%d" % (tpl_len, hist))
+    assert stats["carrier"] >= 40
+    edge = (ref["corr_sample"] == start) | (ref["corr_sample"] == stop - 1)
+    assert edge.sum() >= 8            # peaks on the window edges were exercised
+    det.close()

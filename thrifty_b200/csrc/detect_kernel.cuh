@@ -55,7 +55,6 @@ struct DetectParams {
     int zoom;                  // 1: carrier window (+-3 bins) spans <= 128 bins and no stddev term -> pruned FFT#1
     int zoom_base;             // first bin b0 of the 128-bin zoom band: the block is pre-shifted by -b0 bins (0: none)
     int zoom_w0;               // window start inside the band: (win_start - zoom_base) mod N
-    float fit_tab[7][4];       // per fit point x=-3..3: sin(aWx), cos(aWx), sin(ax), cos(ax), a = pi/N
     float fit_W;               // carrier_len
     float fit_WoverN;          // W / N
     float fit_invN;            // 1 / N
@@ -351,20 +350,19 @@ __device__ __forceinline__ RedOut block_reduce(float s0, float s1, unsigned long
 // Least-squares fit of A*|D(x - d)| to 7 magnitudes at x = -3..3 (carrier_sync.py:150-196,
 // scipy curve_fit 'lm' from p0 = (y[0], 0)).  Executed by one warp: lane i (mod 8) < 7 owns
 // point i; the four groups of 8 lanes compute the same thing so control flow stays uniform.
-// D(z) = sin(aWz) / (W sin(az)), a = pi/N.  The trig of the fixed abscissae comes from
-// fit_tab; each iteration only needs sincos of a*W*d and a*d (angle-difference identities).
+// D(z) = sin(aWz) / (W sin(az)), a = pi/N; every lane evaluates its own point (two sincospi per evaluation).
 struct FitSums {
     float jaa, jad, jdd, jar, jdr, cost;
 };
-__device__ __forceinline__ FitSums fit_eval(float y, bool active, float A, float d, const float (&tab)[4],
-                                            float W, float WoverN, float invN) {
-    float sd1, cd1, sd2, cd2;
-    sincospif(WoverN * d, &sd1, &cd1);
-    sincospif(invN * d, &sd2, &cd2);
-    const float s1 = tab[0] * cd1 - tab[1] * sd1;     // sin(aW(x-d))
-    const float c1 = tab[1] * cd1 + tab[0] * sd1;     // cos(aW(x-d))
-    const float s2 = tab[2] * cd2 - tab[3] * sd2;     // sin(a(x-d))
-    const float c2 = tab[3] * cd2 + tab[2] * sd2;     // cos(a(x-d))
+// xi: abscissa of this lane's point (-3..3).  The sines are taken of (xi - d) directly: angle-difference
+// identities on tabulated sin/cos of xi lose the leading digits of sin(a (xi - d)) when d approaches a sample
+// point other than 0 (|d| > 0.5 happens on weak, wide peaks) and the fit then stalls 5e-4 bins off.
+__device__ __forceinline__ FitSums fit_eval(float y, bool active, float A, float d, float xi, float W,
+                                            float WoverN, float invN) {
+    const float z = xi - d;
+    float s1, c1, s2, c2;
+    sincospif(WoverN * z, &s1, &c1);                  // sin, cos of a W (x - d),  a = pi/N
+    sincospif(invN * z, &s2, &c2);                    // sin, cos of a (x - d)
     float D, Dp;
     if (fabsf(s2) < 1e-30f) {
         D = 1.0f;
@@ -403,13 +401,11 @@ __device__ __forceinline__ FitSums fit_eval(float y, bool active, float A, float
 __device__ __forceinline__ float dirichlet_fit(float y, int lane, const DetectParams &p) {
     const int li = lane & 7;
     const bool active = li < 7;
-    float tab[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) tab[q] = p.fit_tab[active ? li : 0][q];
+    const float xi = (float)((active ? li : 0) - 3);
     float A = __shfl_sync(0xffffffffu, y, 3);
     float d = 0.f;
     float lambda = 0.f;                   // Gauss-Newton first; Marquardt damping only if a step fails
-    FitSums f = fit_eval(y, active, A, d, tab, p.fit_W, p.fit_WoverN, p.fit_invN);
+    FitSums f = fit_eval(y, active, A, d, xi, p.fit_W, p.fit_WoverN, p.fit_invN);
     for (int it = 0; it < 30; ++it) {
         const float a11 = f.jaa * (1.f + lambda), a22 = f.jdd * (1.f + lambda), a12 = f.jad;
         const float det = a11 * a22 - a12 * a12;
@@ -417,9 +413,9 @@ __device__ __forceinline__ float dirichlet_fit(float y, int lane, const DetectPa
         const float idet = 1.0f / det;
         const float dA = (a22 * f.jar - a12 * f.jdr) * idet;
         const float dd = (a11 * f.jdr - a12 * f.jar) * idet;
-        const bool tiny = fabsf(dd) < 5e-7f && fabsf(dA) <= 1e-6f * fabsf(A);
+        const bool tiny = fabsf(dd) < 2e-6f && fabsf(dA) <= 2e-6f * fabsf(A);
         const float An = A + dA, dn = d + dd;
-        const FitSums fn = fit_eval(y, active, An, dn, tab, p.fit_W, p.fit_WoverN, p.fit_invN);
+        const FitSums fn = fit_eval(y, active, An, dn, xi, p.fit_W, p.fit_WoverN, p.fit_invN);
         if (fn.cost <= f.cost * 1.000001f) {
             A = An;
             d = dn;

@@ -434,14 +434,7 @@ int thr_create(const thr_config *cfg, thr_detector **out) {
     }
     p.new_len = N - H;
     {
-        const double pi = 3.14159265358979323846, a = pi / N, W = cfg->carrier_len;
-        for (int i = 0; i < 7; ++i) {
-            const double x = i - 3;
-            p.fit_tab[i][0] = (float)std::sin(a * W * x);
-            p.fit_tab[i][1] = (float)std::cos(a * W * x);
-            p.fit_tab[i][2] = (float)std::sin(a * x);
-            p.fit_tab[i][3] = (float)std::cos(a * x);
-        }
+        const double W = cfg->carrier_len;
         p.fit_W = (float)W;
         p.fit_WoverN = (float)(W / N);
         p.fit_invN = (float)(1.0 / N);
