@@ -1,0 +1,103 @@
+#!/usr/bin/env python
+"""Randomised parity stress: random detector geometries / thresholds / signal levels, CUDA path vs oracle.
+
+    python tools/stress_parity.py [n_configs] [seed]
+
+Prints one line per configuration and a summary of any mismatch (the parity bar of tests/parity_util.py)."""
+import os
+import sys
+import traceback
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import parity_util as parity  # noqa: E402
+from oracle import thrifty_oracle as orc  # noqa: E402
+from thrifty_b200 import synth  # noqa: E402
+from thrifty_b200._native import NativeDetector  # noqa: E402
+
+
+def random_config(rng):
+    n = int(rng.choice([1024, 2048, 4096, 8192, 16384]))
+    bits = {1024: 7, 2048: 8, 4096: 9, 8192: 10, 16384: 11}[n]
+    full = synth.gold_template(bits)
+    tlen = int(rng.integers(max(64, len(full) // 4), min(len(full), n - 64)))
+    tpl = full[:tlen]
+    hist = int(rng.integers(tlen - 1, min(n - 1, tlen + n // 3)))
+    kind = rng.integers(0, 4)
+    if kind == 0:
+        lo = int(rng.integers(3, 40)); window = (lo, lo + int(rng.integers(10, 100)))
+    elif kind == 1:
+        hi = -int(rng.integers(5, 40)); window = (hi - int(rng.integers(10, 100)), hi)
+    elif kind == 2:
+        lo = int(rng.integers(100, n // 2 - 200)); window = (lo, lo + int(rng.integers(10, 300)))
+    else:
+        window = (int(rng.integers(5, 20)), int(rng.integers(200, n // 2 - 1)))
+    cth = (float(rng.choice([0., 1., 50.])), float(rng.uniform(5, 25)), float(rng.choice([0., 0., 1.5])))
+    kth = (float(rng.choice([0., 0.5])), float(rng.uniform(5, 25)), float(rng.choice([0., 0., 2.0])))
+    carrier_len = int(rng.choice([tlen, tlen, max(32, tlen // 2)]))
+    return dict(n=n, tpl=tpl, hist=hist, window=window, cth=cth, kth=kth, carrier_len=carrier_len)
+
+
+def make_blocks(rng, cfg, nblk):
+    n, hist, tpl, (w0, w1) = cfg["n"], cfg["hist"], cfg["tpl"], cfg["window"]
+    raws = []
+    for _ in range(nblk):
+        brng = np.random.default_rng(int(rng.integers(0, 2**31)))
+        raw, _ = synth.make_block(brng, n, hist, tpl, 0.75, bin_range=(w0 + 0.6, w1 - 0.6))
+        mode = rng.integers(0, 6)
+        if mode == 0:       # weak signal: scale towards the noise floor (re-quantise around mid-scale)
+            x = (raw.astype(np.float32) - 127.4) * float(rng.uniform(0.05, 0.4)) + 127.4
+            raw = np.clip(x, 0, 255).astype(np.uint8)
+        elif mode == 1:     # hard clipping
+            x = (raw.astype(np.float32) - 127.4) * float(rng.uniform(2, 6)) + 127.4
+            raw = np.clip(x, 0, 255).astype(np.uint8)
+        raws.append(raw)
+    return np.stack(raws)
+
+
+def main(n_cfg=None, seed=None):
+    if n_cfg is None:
+        n_cfg = int(sys.argv[1]) if len(sys.argv) > 1 else 24
+    if seed is None:
+        seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    rng = np.random.default_rng(seed)
+    bad = 0
+    for c in range(n_cfg):
+        cfg = random_config(rng)
+        nblk = 48 if cfg["n"] >= 16384 else 64
+        raw = make_blocks(rng, cfg, nblk)
+        tag = "cfg %d: N=%d L=%d H=%d W=%d window=%s cth=%s kth=%s" % (
+            c, cfg["n"], len(cfg["tpl"]), cfg["hist"], cfg["carrier_len"], cfg["window"], cfg["cth"], cfg["kth"])
+        try:
+            st = orc.DetectorSettings(cfg["n"], cfg["hist"], cfg["carrier_len"], cfg["cth"], cfg["window"], cfg["tpl"],
+                                      cfg["kth"])
+            with np.errstate(all="ignore"):
+                ref = orc.detect_blocks(st, raw)
+            det = NativeDetector(cfg["n"], cfg["hist"], cfg["tpl"], cfg["carrier_len"], cfg["window"], cfg["cth"],
+                                 cfg["kth"], max_batch=nblk)
+            got = det.detect_raw(raw)[:, 0]
+            kern = det.info()["kernel"]
+            det.close()
+            # ill-conditioned Dirichlet fits (main lobe much wider than the 7 fitted bins) are sensitive to the
+            # last bits of the magnitudes: widen the carrier-offset bar by 10 sigma of that sensitivity
+            tol = [parity.carrier_offset_tolerance(raw[b], int(ref["carrier_bin"][b]), float(ref["carrier_offset"][b]),
+                                                   cfg["n"], cfg["carrier_len"]) if ref["carrier_detected"][b] else 0.0
+                   for b in range(nblk)]
+            stats = parity.compare_records(got, ref, what=tag, carrier_offset_atol=tol)
+            stats["max_offset_tol"] = float(max(tol))
+            print("ok  ", tag, kern, {k: (round(v, 7) if isinstance(v, float) else v) for k, v in stats.items()}, flush=True)
+        except Exception as e:      # noqa: BLE001
+            bad += 1
+            print("FAIL", tag, "\n    ", str(e).replace("\n", " ")[:600], flush=True)
+            if not isinstance(e, AssertionError):
+                traceback.print_exc()
+    print("configs", n_cfg, "failed", bad)
+    return bad
+
+
+if __name__ == "__main__":
+    sys.exit(1 if main() else 0)
