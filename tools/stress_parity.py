@@ -59,6 +59,37 @@ def make_blocks(rng, cfg, nblk):
     return np.stack(raws)
 
 
+def main_fastdet(n_cfg, seed):
+    """Same, for the fastdet-semantics kernels against oracle/fastdet_oracle.py."""
+    from oracle import fastdet_oracle as fo
+    rng = np.random.default_rng(seed)
+    bad = 0
+    for c in range(n_cfg):
+        cfg = random_config(rng)
+        nblk = 32 if cfg["n"] >= 16384 else 64
+        raw = make_blocks(rng, cfg, nblk)
+        thresh, kthresh = (cfg["cth"][0] * 100, cfg["cth"][1]), (cfg["kth"][0] * 100, cfg["kth"][1])
+        tpl32 = np.asarray(cfg["tpl"], dtype=np.float32)
+        tag = "fastdet cfg %d: N=%d L=%d H=%d window=%s t=%s u=%s" % (
+            c, cfg["n"], len(tpl32), cfg["hist"], cfg["window"], thresh, kthresh)
+        try:
+            with np.errstate(all="ignore"):
+                ref = fo.detect_blocks(cfg["n"], cfg["hist"], thresh, cfg["window"], tpl32, kthresh, raw)
+            det = NativeDetector(cfg["n"], cfg["hist"], tpl32.astype(np.float64), len(tpl32), cfg["window"],
+                                 (thresh[0], thresh[1], 0.0), (kthresh[0], kthresh[1], 0.0), max_batch=nblk, fastdet=True)
+            got = det.detect_raw(raw)[:, 0]
+            det.close()
+            stats = parity.compare_fastdet(got, ref, what=tag)
+            print("ok  ", tag, {k: (round(v, 7) if isinstance(v, float) else v) for k, v in stats.items()}, flush=True)
+        except Exception as e:      # noqa: BLE001
+            bad += 1
+            print("FAIL", tag, "\n    ", str(e).replace("\n", " ")[:600], flush=True)
+            if not isinstance(e, AssertionError):
+                traceback.print_exc()
+    print("fastdet configs", n_cfg, "failed", bad)
+    return bad
+
+
 def main(n_cfg=None, seed=None):
     if n_cfg is None:
         n_cfg = int(sys.argv[1]) if len(sys.argv) > 1 else 24
@@ -100,4 +131,6 @@ def main(n_cfg=None, seed=None):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 3 and sys.argv[3] == "fastdet":
+        sys.exit(1 if main_fastdet(int(sys.argv[1]), int(sys.argv[2])) else 0)
     sys.exit(1 if main() else 0)
