@@ -109,3 +109,27 @@ def test_fastdet_cli_card_to_toad(tmp_path):
         for x, y in zip(a[5:], b[5:]):
             assert abs(float(x) - float(y)) <= 1e-4 * max(1.0, abs(float(y)))
     assert "carrier @" in res.stdout and "Read %d blocks." % len(raw) in res.stdout
+
+
+def test_fastdet_cli_raw_stream(tmp_path):
+    """`fastdet -i capture.dat` (raw uint8 I/Q, no --card): blocks are formed like fastcard's raw_reader
+    (raw_reader.c:15-46, first history = uint16 127) and read in place on the GPU."""
+    import subprocess
+    import sys
+    from thrifty_b200 import fastdet
+    cfg, raw, block_idx, ref, toads, stream = parity.load_fastdet_golden("n4096_gold9_stream")
+    dat, tpl, out = str(tmp_path / "in.dat"), str(tmp_path / "t.tpl"), str(tmp_path / "out.toad")
+    stream.tofile(dat)
+    fastdet.save_template(tpl, cfg["template"])
+    cmd = [sys.executable, "-m", "thrifty_b200", "fastdet", "-i", dat, "-z", tpl, "-o", out, "-k", "0", "-q",
+           "-b", str(cfg["block_len"]), "-h", str(cfg["history_len"]), "-w", "%d-%d" % cfg["window"],
+           "-t", "%gc%gs" % cfg["thresh"], "-u", "%gc%gs" % cfg["corr_thresh"], "-r", "3", "--batch", "10"]
+    res = subprocess.run(cmd, capture_output=True, text=True, cwd=parity.ROOT)
+    assert res.returncode == 0, res.stderr
+    lines = open(out).read().splitlines()
+    det = ref[ref["corr_detected"] != 0]
+    assert len(lines) == len(det)
+    for mine, r in zip(lines, det):
+        f = mine.split(" ")
+        assert int(f[0]) == 3 and int(f[2]) == int(r["block_idx"]) and int(f[4]) == int(r["corr_peak_idx"])
+        assert int(f[8]) == int(r["carrier_argmax"]) and abs(float(f[3]) - float(r["soa"])) <= 1e-4
