@@ -94,9 +94,13 @@ struct Cfg {
     // T == 512 (one CTA per SM): a dedicated service warpgroup runs the serial fit / tail while the
     // workers go on with the next block; registers are re-split with setmaxnreg (workers 112,
     // service 32).  Smaller T: several CTAs per SM hide the serial parts, warp 0 runs them inline.
-    static constexpr bool SERVICE = (T >= 512);
+    // One CTA per SM (the buffer takes more than half of the shared memory, or T == 512): service warpgroup.
+    static constexpr bool ONE_CTA = (T >= 512) || (BUF_BYTES > 100 * 1024);
+    static constexpr bool SERVICE = ONE_CTA;
     static constexpr int LAUNCH_THREADS = SERVICE ? T + 128 : T;
-    static constexpr int MIN_CTAS = T >= 512 ? 1 : (T >= 256 ? 2 : (T >= 128 ? 4 : 8));
+    static constexpr int MIN_CTAS = ONE_CTA ? 1 : (T >= 256 ? 2 : (T >= 128 ? 4 : 8));
+    // registers per worker after setmaxnreg: what the 64 K file leaves beside the 128 x 32 of the service warpgroup
+    static constexpr int WORKER_REGS = T >= 512 ? 112 : (T >= 256 ? 232 : 240);
     static constexpr int MAX_TPL = 32;               // templates per detector (tail mailbox size)
     // Passes 2 and 3 both work inside one k1 slab (M consecutive elements).  When every warp owns the
     // same slabs in both passes the hand-over 2 -> 3 (and 3' -> 2') only needs __syncwarp(): the warps
@@ -766,7 +770,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
             }
             return;
         }
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C::WORKER_REGS));
     }
 
     // =====================================================================================
