@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/thrifty_b200.h"
@@ -47,6 +48,8 @@ struct Slot {                 // one in-flight chunk of the host-buffer API
     int64_t *h_idx = nullptr;        // page-locked, 2 * max_batch (block indices, payload offsets)
     thr_record *pending_dst = nullptr;
     size_t pending_n = 0;
+    uint8_t *h_in = nullptr;         // page-locked input staging for pageable callers (lazily, h_in_cap bytes)
+    size_t h_in_cap = 0;
 };
 
 }  // namespace
@@ -200,6 +203,7 @@ void thr_destroy(thr_detector *d) {
         cudaFree(s.d_off);
         if (s.h_out) cudaFreeHost(s.h_out);
         if (s.h_idx) cudaFreeHost(s.h_idx);
+        if (s.h_in) cudaFreeHost(s.h_in);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     if (d->own_stream) { cudaStreamSynchronize(d->own_stream); cudaStreamDestroy(d->own_stream); }
@@ -509,6 +513,48 @@ int thr_detect_batch_device_c64(thr_detector *d, const float *d_iq, const int64_
     return launch(d, d->stream, nullptr, d_iq, d_idx, n_blocks, d_out, nullptr, nullptr, nullptr, true);
 }
 
+// memcpy on up to 4 threads: one core moves ~10 GB/s, PCIe Gen5 takes 50
+static void parallel_memcpy(void *dst, const void *src, size_t bytes) {
+    constexpr size_t MIN_PART = (size_t)2 << 20;
+    const int parts = bytes >= 4 * MIN_PART ? 4 : (bytes >= 2 * MIN_PART ? 2 : 1);
+    if (parts == 1) {
+        std::memcpy(dst, src, bytes);
+        return;
+    }
+    const size_t part = ((bytes / parts) + 63) & ~(size_t)63;
+    std::thread th[3];
+    for (int i = 1; i < parts; ++i) {
+        const size_t off = (size_t)i * part, len = off >= bytes ? 0 : (bytes - off < part ? bytes - off : part);
+        th[i - 1] = std::thread([=] { if (len) std::memcpy((char *)dst + off, (const char *)src + off, len); });
+    }
+    std::memcpy(dst, src, part < bytes ? part : bytes);
+    for (int i = 1; i < parts; ++i) th[i - 1].join();
+}
+
+static bool is_pageable(const void *p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();                        // unregistered host memory reports an error on old drivers
+        return true;
+    }
+    return attr.type == cudaMemoryTypeUnregistered;
+}
+
+// Pageable input (a NumPy array, a Python bytes object): an "asynchronous" copy from it is staged by the driver at
+// ~10 GB/s and blocks the calling thread.  Copying the chunk into page-locked staging ourselves (4 threads) runs at
+// ~25 GB/s and leaves the DMA truly asynchronous, so it overlaps the kernel of the other slot.
+static int stage_pageable(thr_detector *d, Slot &s, const void **src, size_t bytes, size_t cap_hint) {
+    if (s.h_in_cap < bytes) {
+        if (s.h_in) cudaFreeHost(s.h_in);
+        s.h_in = nullptr;
+        s.h_in_cap = cap_hint > bytes ? cap_hint : bytes;
+        CU(d, cudaMallocHost(&s.h_in, s.h_in_cap));
+    }
+    parallel_memcpy(s.h_in, *src, bytes);
+    *src = s.h_in;
+    return THR_OK;
+}
+
 // Slot hand-over of the host-buffer entry points: wait for the chunk that used this slot two chunks ago and move
 // its records from the page-locked staging buffer to the caller's buffer.
 static int slot_flush(thr_detector *d, Slot &s) {
@@ -538,16 +584,20 @@ static int detect_host(thr_detector *d, const uint8_t *raw, const float *iq, con
         for (auto &s : d->slot)
             if (!s.d_iq) CU(d, cudaMalloc(&s.d_iq, (size_t)d->c64_chunk * N * 8));
     }
+    const bool pageable = is_pageable(raw ? (const void *)raw : (const void *)iq);
     int c = 0;
     for (int64_t b0 = 0; b0 < n_blocks; b0 += chunk, ++c) {
         Slot &s = d->slot[c & 1];
         const int nb = (int)((n_blocks - b0) < chunk ? (n_blocks - b0) : chunk);
         int rc = slot_flush(d, s);                 // chunk c-2 done: its records go to the caller, staging is free
         if (rc != THR_OK) return rc;
-        if (raw)
-            CU(d, cudaMemcpyAsync(s.d_in, raw + (size_t)b0 * 2 * N, (size_t)nb * 2 * N, cudaMemcpyHostToDevice, s.stream));
-        else
-            CU(d, cudaMemcpyAsync(s.d_iq, iq + (size_t)b0 * 2 * N, (size_t)nb * N * 8, cudaMemcpyHostToDevice, s.stream));
+        const void *src = raw ? (const void *)(raw + (size_t)b0 * 2 * N) : (const void *)(iq + (size_t)b0 * 2 * N);
+        const size_t bytes = raw ? (size_t)nb * 2 * N : (size_t)nb * N * 8;
+        if (pageable) {
+            rc = stage_pageable(d, s, &src, bytes, (size_t)chunk * (raw ? 2 * N : 8 * N));
+            if (rc != THR_OK) return rc;
+        }
+        CU(d, cudaMemcpyAsync(raw ? (void *)s.d_in : (void *)s.d_iq, src, bytes, cudaMemcpyHostToDevice, s.stream));
         for (int i = 0; i < nb; ++i) s.h_idx[i] = block_idx ? block_idx[b0 + i] : b0 + i;
         CU(d, cudaMemcpyAsync(s.d_idx, s.h_idx, (size_t)nb * sizeof(int64_t), cudaMemcpyHostToDevice, s.stream));
         rc = launch(d, s.stream, raw ? s.d_in : nullptr, raw ? nullptr : s.d_iq, s.d_idx, nb, s.d_out, nullptr,
@@ -725,6 +775,7 @@ int thr_detect_card(thr_detector *d, const char *text, size_t len, int32_t final
     CU(d, cudaMemsetAsync(d->d_bad, 0, sizeof(unsigned int), d->slot[0].stream));
     CU(d, cudaStreamSynchronize(d->slot[0].stream));
     const int64_t chunk = d->host_chunk;
+    const bool pageable = is_pageable(text);
     int c = 0;
     for (int64_t b0 = 0; b0 < nb_total; b0 += chunk, ++c) {
         Slot &s = d->slot[c & 1];
@@ -746,7 +797,12 @@ int thr_detect_card(thr_detector *d, const char *text, size_t len, int32_t final
             s.h_idx[i] = block_idx[b0 + i];
             h_rel[i] = off[b0 + i] - t0;
         }
-        CU(d, cudaMemcpyAsync(s.d_text, text + t0, bytes, cudaMemcpyHostToDevice, s.stream));
+        const void *tsrc = text + t0;
+        if (pageable) {
+            rc = stage_pageable(d, s, &tsrc, bytes, bytes + bytes / 4);
+            if (rc != THR_OK) return rc;
+        }
+        CU(d, cudaMemcpyAsync(s.d_text, tsrc, bytes, cudaMemcpyHostToDevice, s.stream));
         CU(d, cudaMemcpyAsync(s.d_off, h_rel, (size_t)nb * sizeof(int64_t), cudaMemcpyHostToDevice, s.stream));
         CU(d, cudaMemcpyAsync(s.d_idx, s.h_idx, (size_t)nb * sizeof(int64_t), cudaMemcpyHostToDevice, s.stream));
         const dim3 grid((unsigned)((want + thr::B64_SEG_CHARS - 1) / thr::B64_SEG_CHARS), (unsigned)nb);
@@ -800,6 +856,7 @@ int thr_detect_stream(thr_detector *d, const uint8_t *stream, int64_t n_stream_b
     const int64_t nb_total = n_stream_bytes >= 2 * N ? (n_stream_bytes - 2 * N) / stride + 1 : 0;
     *n_blocks_out = nb_total;
     const int64_t chunk = d->host_chunk;
+    const bool pageable = is_pageable(stream);
     int c = 0;
     for (int64_t b0 = 0; b0 < nb_total; b0 += chunk, ++c) {
         Slot &s = d->slot[c & 1];
@@ -807,7 +864,12 @@ int thr_detect_stream(thr_detector *d, const uint8_t *stream, int64_t n_stream_b
         int rc = slot_flush(d, s);
         if (rc != THR_OK) return rc;
         const size_t bytes = (size_t)((nb - 1) * stride + 2 * N);        // <= nb * 2N: fits the raw staging buffer
-        CU(d, cudaMemcpyAsync(s.d_in, stream + b0 * stride, bytes, cudaMemcpyHostToDevice, s.stream));
+        const void *ssrc = stream + b0 * stride;
+        if (pageable) {
+            rc = stage_pageable(d, s, &ssrc, bytes, (size_t)chunk * 2 * N);
+            if (rc != THR_OK) return rc;
+        }
+        CU(d, cudaMemcpyAsync(s.d_in, ssrc, bytes, cudaMemcpyHostToDevice, s.stream));
         for (int i = 0; i < nb; ++i) s.h_idx[i] = first_block + b0 + i;
         CU(d, cudaMemcpyAsync(s.d_idx, s.h_idx, (size_t)nb * sizeof(int64_t), cudaMemcpyHostToDevice, s.stream));
         rc = launch(d, s.stream, s.d_in, nullptr, s.d_idx, nb, s.d_out, nullptr, nullptr, nullptr, false, stride);
