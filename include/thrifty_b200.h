@@ -125,7 +125,10 @@ typedef struct thr_info {
     char    kernel[64];
 } thr_info;
 
-/* ---- lifecycle (cf. fastcard_new / fastcard_free) ---- */
+/* ---- lifecycle (cf. fastcard_new / fastcard_free) ----
+ * thr_create fails with THR_ERR_NO_DEVICE unless the device is sm_100 (the library carries sm_100a code only; there is
+ * no CPU fallback).  Testing aid: the environment variable THRIFTY_B200_MAX_GRID=<n> caps the persistent grid at n CTAs
+ * so that small inputs exercise the multi-block pipeline of a CTA (compute-sanitizer runs). */
 int  thr_create(const thr_config *cfg, thr_detector **out);
 void thr_destroy(thr_detector *det);
 /* Message for the last error on `det`, or for the last failed thr_create if det == NULL. */
@@ -138,7 +141,10 @@ int  thr_device_count(void);
  *            block_data.py:129-131 / fastcard/card_reader.c:69-75)
  * block_idx: n_blocks int64 block indices (NULL -> 0,1,2,...)
  * out:       n_blocks * n_templates records
- * n_blocks may exceed max_batch; the call chunks and overlaps copies with compute. */
+ * n_blocks may exceed max_batch; the call chunks and overlaps copies with compute.
+ * Host buffers may be pageable or page-locked (thr_host_alloc): page-locked ones are DMA'd directly (PCIe-bound,
+ * ~1.6 M blocks/s at N = 16384), pageable ones go through internal page-locked staging (~0.75 M blocks/s);
+ * records always return through page-locked staging.  The same holds for thr_detect_card and thr_detect_stream. */
 int thr_detect_batch(thr_detector *det, const uint8_t *raw, const int64_t *block_idx,
                      int64_t n_blocks, thr_record *out);
 /* Same, complex64 samples (interleaved re,im float32), n_blocks * N * 8 bytes:
