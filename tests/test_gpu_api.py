@@ -520,3 +520,34 @@ def test_random_geometries_stress():
     sys.path.insert(0, os.path.join(parity.ROOT, "tools"))
     import stress_parity
     assert stress_parity.main(30, 2024) == 0
+
+
+def test_pageable_inputs_large():
+    """Pageable (NumPy / bytes) inputs above the 4-thread staging threshold, with sizes that are not multiples of the
+    64-byte copy granule: `.card` text whose lines change length (block index 999 -> 1000), a raw stream, raw blocks."""
+    from thrifty_b200._native import NativeDetector
+    tpl = np.load(os.path.join(parity.GOLDEN, "template_example.npy"))
+    n, h = 16384, 4920
+    base, _ = synth.make_blocks(48, n, h, tpl, 0.8, seed=606)
+    det = NativeDetector(n, h, tpl, len(tpl), (7, 110), (0., 15., 0.), (0., 15., 0.), max_batch=256)
+    # .card text: lines 768..1279 cross the 3 -> 4 digit block index boundary
+    idx = np.arange(768, 1280, dtype=np.int64)
+    raw = base[np.arange(len(idx)) % 48]
+    ref = det.detect_raw(raw, idx)[:, 0]
+    buf = io.StringIO()
+    block_data.write_card(buf, raw, idx)
+    text = buf.getvalue().encode()
+    for a, b in ((0, 256), (0, 512), (3, 301)):
+        lines = [l + b"\n" for l in text.split(b"\n") if l and not l.startswith(b"#")]
+        ts, got_idx, recs, used = det.detect_card(b"".join(lines[a:b]), final=True)
+        assert np.array_equal(got_idx, idx[a:b]) and recs[:, 0].tobytes() == ref[a:b].tobytes()
+    # raw stream (pageable): 450 blocks, (450 - 1) * 22928 + 32768 bytes
+    nblk = 450
+    new = 2 * (n - h)
+    stream = np.concatenate([base[0][:2 * h]] + [base[b % 48][2 * h:] for b in range(nblk)])
+    blocks = np.stack([stream[b * new:b * new + 2 * n] for b in range(nblk)])
+    assert len(stream) % 64 != 0
+    got = det.detect_stream(stream, 0)[:, 0]
+    want = det.detect_raw(blocks, np.arange(nblk))[:, 0]
+    assert got.tobytes() == want.tobytes()
+    det.close()

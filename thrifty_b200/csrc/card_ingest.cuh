@@ -33,7 +33,7 @@ constexpr int B64_THREADS = 256;             // 16 characters per thread
 
 __global__ void __launch_bounds__(B64_THREADS)
 b64_decode_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__ payload_off, int n_chars,
-                  int raw_bytes, uint8_t *__restrict__ raw_out, unsigned int *__restrict__ n_bad) {
+                  int raw_bytes, uint8_t *__restrict__ raw_out, unsigned int *__restrict__ n_bad, int blk_base) {
     __shared__ __align__(16) uint8_t chars[B64_SEG_CHARS + 16];
     const int blk = blockIdx.y;
     const int seg0 = blockIdx.x * B64_SEG_CHARS;
@@ -78,7 +78,18 @@ b64_decode_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__ 
         if (g == 2) { out[1] |= (b0 << 16) | (b1 << 24); out[2] = b2; }
         if (g == 3) { out[2] |= (b0 << 8) | (b1 << 16) | (b2 << 24); }
     }
-    if (bad) atomicAdd(n_bad, 1u);
+    if (bad) {      // n_bad[0] = count; the first reporter also leaves (block, character position, 16 raw characters)
+        if (atomicAdd(n_bad, 1u) == 0u) {
+            n_bad[1] = (unsigned int)(blk_base + blk);
+            n_bad[2] = (unsigned int)(seg0 + c0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                unsigned int w = 0;
+                for (int b = 0; b < 4; ++b) w |= (unsigned int)(c0 + 4 * k + b < seg_len ? chars[c0 + 4 * k + b] : 0) << (8 * b);
+                n_bad[3 + k] = w;
+            }
+        }
+    }
     const int o0 = (seg0 / 4) * 3 + threadIdx.x * 12;          // byte offset inside the block's raw row
     uint8_t *dst = raw_out + (size_t)blk * raw_bytes + o0;
     if (valid_bytes == 12 && o0 + 12 <= raw_bytes) {

@@ -521,13 +521,13 @@ static void parallel_memcpy(void *dst, const void *src, size_t bytes) {
         std::memcpy(dst, src, bytes);
         return;
     }
-    const size_t part = ((bytes / parts) + 63) & ~(size_t)63;
+    const size_t part = (bytes / parts) & ~(size_t)63;            // the last part also takes the remainder
     std::thread th[3];
     for (int i = 1; i < parts; ++i) {
-        const size_t off = (size_t)i * part, len = off >= bytes ? 0 : (bytes - off < part ? bytes - off : part);
-        th[i - 1] = std::thread([=] { if (len) std::memcpy((char *)dst + off, (const char *)src + off, len); });
+        const size_t off = (size_t)i * part, len = (i == parts - 1) ? bytes - off : part;
+        th[i - 1] = std::thread([=] { std::memcpy((char *)dst + off, (const char *)src + off, len); });
     }
-    std::memcpy(dst, src, part < bytes ? part : bytes);
+    std::memcpy(dst, src, part);
     for (int i = 1; i < parts; ++i) th[i - 1].join();
 }
 
@@ -770,9 +770,9 @@ int thr_detect_card(thr_detector *d, const char *text, size_t len, int32_t final
                     (long long)bad_line, (long long)want);
     const int64_t nb_total = *n_blocks;
     if (!d->d_bad) {
-        CU(d, cudaMalloc(&d->d_bad, sizeof(unsigned int)));
+        CU(d, cudaMalloc(&d->d_bad, 8 * sizeof(unsigned int)));
     }
-    CU(d, cudaMemsetAsync(d->d_bad, 0, sizeof(unsigned int), d->slot[0].stream));
+    CU(d, cudaMemsetAsync(d->d_bad, 0, 8 * sizeof(unsigned int), d->slot[0].stream));
     CU(d, cudaStreamSynchronize(d->slot[0].stream));
     const int64_t chunk = d->host_chunk;
     const bool pageable = is_pageable(text);
@@ -807,7 +807,7 @@ int thr_detect_card(thr_detector *d, const char *text, size_t len, int32_t final
         CU(d, cudaMemcpyAsync(s.d_idx, s.h_idx, (size_t)nb * sizeof(int64_t), cudaMemcpyHostToDevice, s.stream));
         const dim3 grid((unsigned)((want + thr::B64_SEG_CHARS - 1) / thr::B64_SEG_CHARS), (unsigned)nb);
         thr::b64_decode_kernel<<<grid, thr::B64_THREADS, 0, s.stream>>>(s.d_text, s.d_off, (int)want, 2 * N, s.d_in,
-                                                                       d->d_bad);
+                                                                       d->d_bad, (int)b0);
         CU(d, cudaGetLastError());
         d->launches++;
         rc = launch(d, s.stream, s.d_in, nullptr, s.d_idx, nb, s.d_out, nullptr, nullptr, nullptr);
@@ -819,9 +819,18 @@ int thr_detect_card(thr_detector *d, const char *text, size_t len, int32_t final
         rc = slot_flush(d, s);
         if (rc != THR_OK) return rc;
     }
-    unsigned int n_bad = 0;
-    CU(d, cudaMemcpy(&n_bad, d->d_bad, sizeof n_bad, cudaMemcpyDeviceToHost));
-    if (n_bad) return fail(d, THR_ERR_INVALID, ".card payload contains %u group(s) with non-base64 characters", n_bad);
+    unsigned int n_bad[8] = {0};
+    CU(d, cudaMemcpy(n_bad, d->d_bad, sizeof n_bad, cudaMemcpyDeviceToHost));
+    if (n_bad[0]) {
+        char shown[17];
+        for (int i = 0; i < 16; ++i) {
+            const unsigned char ch = (unsigned char)(n_bad[3 + i / 4] >> (8 * (i % 4)));
+            shown[i] = (ch >= 32 && ch < 127) ? (char)ch : '?';
+        }
+        shown[16] = 0;
+        return fail(d, THR_ERR_INVALID, ".card payload contains %u group(s) with non-base64 characters (first: data line %u of "
+                    "this call, payload character %u: \"%s\")", n_bad[0], n_bad[1] + 1, n_bad[2], shown);
+    }
     return THR_OK;
 }
 
