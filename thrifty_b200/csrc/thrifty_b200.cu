@@ -565,6 +565,16 @@ static int slot_flush(thr_detector *d, Slot &s) {
     }
     return THR_OK;
 }
+// Entry of every host-buffer call: a previous call that failed half-way may have left records queued for a buffer the
+// caller no longer owns -- drop them (after the streams have drained) instead of copying into it.
+static int slots_reset(thr_detector *d) {
+    for (auto &s : d->slot) {
+        CU(d, cudaStreamSynchronize(s.stream));
+        s.pending_n = 0;
+        s.pending_dst = nullptr;
+    }
+    return THR_OK;
+}
 static int slot_queue_records(thr_detector *d, Slot &s, thr_record *dst, size_t n) {
     CU(d, cudaMemcpyAsync(s.h_out, s.d_out, n * sizeof(thr_record), cudaMemcpyDeviceToHost, s.stream));
     s.pending_dst = dst;
@@ -585,6 +595,7 @@ static int detect_host(thr_detector *d, const uint8_t *raw, const float *iq, con
             if (!s.d_iq) CU(d, cudaMalloc(&s.d_iq, (size_t)d->c64_chunk * N * 8));
     }
     const bool pageable = is_pageable(raw ? (const void *)raw : (const void *)iq);
+    if (int rc0 = slots_reset(d)) return rc0;
     int c = 0;
     for (int64_t b0 = 0; b0 < n_blocks; b0 += chunk, ++c) {
         Slot &s = d->slot[c & 1];
@@ -769,6 +780,7 @@ int thr_detect_card(thr_detector *d, const char *text, size_t len, int32_t final
         return fail(d, rc, ".card data line %lld is malformed (expected '<time> <index> <%lld base64 chars>')",
                     (long long)bad_line, (long long)want);
     const int64_t nb_total = *n_blocks;
+    if (int rc0 = slots_reset(d)) return rc0;
     if (!d->d_bad) {
         CU(d, cudaMalloc(&d->d_bad, 8 * sizeof(unsigned int)));
     }
@@ -866,6 +878,7 @@ int thr_detect_stream(thr_detector *d, const uint8_t *stream, int64_t n_stream_b
     *n_blocks_out = nb_total;
     const int64_t chunk = d->host_chunk;
     const bool pageable = is_pageable(stream);
+    if (int rc0 = slots_reset(d)) return rc0;
     int c = 0;
     for (int64_t b0 = 0; b0 < nb_total; b0 += chunk, ++c) {
         Slot &s = d->slot[c & 1];
