@@ -20,9 +20,12 @@ from thrifty_b200 import synth  # noqa: E402
 from thrifty_b200._native import NativeDetector  # noqa: E402
 
 
+SIZES = [1024, 2048, 4096, 8192, 16384]      # `... <n> <seed> big` adds 32768 (2 x 16384 kernel and its fall-back)
+
+
 def random_config(rng):
-    n = int(rng.choice([1024, 2048, 4096, 8192, 16384]))
-    bits = {1024: 7, 2048: 8, 4096: 9, 8192: 10, 16384: 11}[n]
+    n = int(rng.choice(SIZES))
+    bits = {1024: 7, 2048: 8, 4096: 9, 8192: 10, 16384: 11, 32768: 11}[n]
     full = synth.gold_template(bits)
     tlen = int(rng.integers(max(64, len(full) // 4), min(len(full), n - 64)))
     tpl = full[:tlen]
@@ -99,7 +102,7 @@ def main(n_cfg=None, seed=None):
     bad = 0
     for c in range(n_cfg):
         cfg = random_config(rng)
-        nblk = 48 if cfg["n"] >= 16384 else 64
+        nblk = 24 if cfg["n"] > 16384 else (48 if cfg["n"] >= 16384 else 64)
         raw = make_blocks(rng, cfg, nblk)
         tag = "cfg %d: N=%d L=%d H=%d W=%d window=%s cth=%s kth=%s" % (
             c, cfg["n"], len(cfg["tpl"]), cfg["hist"], cfg["carrier_len"], cfg["window"], cfg["cth"], cfg["kth"])
@@ -131,6 +134,8 @@ def main(n_cfg=None, seed=None):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 3 and sys.argv[3] == "big":
+        SIZES[:] = [16384, 32768, 32768]
     if len(sys.argv) > 3 and sys.argv[3] == "fastdet":
         sys.exit(1 if main_fastdet(int(sys.argv[1]), int(sys.argv[2])) else 0)
     sys.exit(1 if main() else 0)
