@@ -435,6 +435,21 @@ def test_smoke_entry():
     __graft_entry__.smoke()
 
 
+def test_n32768_two_half_kernel_shifted_band():
+    """2 x 16384 kernel with the zoom band pre-shifted (negative-frequency window) against the oracle."""
+    from thrifty_b200._native import NativeDetector
+    tpl = np.load(os.path.join(os.path.dirname(__file__), "golden", "template_example.npy"))
+    n, h = 32768, 4920
+    raw, _ = synth.make_blocks(40, n, h, tpl, 0.7, seed=9002, bin_range=(-108.0, -9.0))
+    st = orc.DetectorSettings(n, h, len(tpl), (0., 15., 0.), (-110, -7), tpl, (0., 15., 0.))
+    ref = orc.detect_blocks(st, raw)
+    det = NativeDetector(n, h, tpl, len(tpl), (-110, -7), (0., 15., 0.), (0., 15., 0.), max_batch=64)
+    assert "detect2x" in det.info()["kernel"]
+    stats = parity.compare_records(det.detect_raw(raw)[:, 0], ref, what="n32768/2x shifted band")
+    assert stats["carrier"] > 15
+    det.close()
+
+
 @pytest.mark.parametrize("kthresh", [(0., 15., 0.), (0.5, 10., 3.)])
 def test_n32768_two_half_kernel_vs_generic_and_oracle(kthresh):
     """block_len 32768 runs as two interleaved 16384-point transforms (detect_kernel_2x.cuh) when FFT#1 can

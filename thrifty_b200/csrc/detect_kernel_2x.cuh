@@ -15,8 +15,9 @@
 // leaves the SM.  |c|^2 of every lag is also written there so that the neighbours of the peak (which
 // belong to the other half-transform) can be fetched without keeping 64 more registers alive.
 //
-// Scope: the pruned ("zoom") FFT#1 configuration only -- carrier window (+-3 bins) inside bins [0,128),
-// no stddev threshold term, one template (true for example/detector.cfg).  Every other configuration at
+// Scope: the pruned ("zoom") FFT#1 configurations only -- carrier window (+-3 bins) at most 128 bins wide (moved to
+// bin 0 by an integer pre-shift if necessary), no carrier stddev threshold term, one template (true for
+// example/detector.cfg).  Every other configuration at
 // this block length runs the generic global-scratch variant of detect_kernel.
 //
 // Same semantics, mailboxes, service-warp pipeline and record format as detect_kernel (see there for the
@@ -39,7 +40,7 @@ struct Cfg2x {
     static constexpr size_t BUF_BYTES = (size_t)(F / 16) * 136;
     static constexpr size_t smem_bytes() {
         return BUF_BYTES + (size_t)(2 * NB) + (size_t)M * 8 + 2 * 320 + 2 * 32 + 2 * 32 + 256
-               + 2 * 128 * 8 + 512 + 64;
+               + 2 * 128 * 8 + 512 + 256 + 64;
     }
     using Half = Cfg<14, 512, false>;                // geometry of one half (pass-3 item order)
 };
@@ -75,8 +76,10 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
     off += 256;
     float2 *zc = reinterpret_cast<float2 *>(smem + off);                 // [2][128] pruned spectra of E, O
     off += 2 * 128 * 8;
-    float *zpow = reinterpret_cast<float *>(smem + off);                 // |X[k]|^2, k < 128
+    float *zpow = reinterpret_cast<float *>(smem + off);                 // |X[b0 + k]|^2, k < 128
     off += 512;
+    float2 *zrho = reinterpret_cast<float2 *>(smem + off);               // W_32^{b0 n1}: row phasors of the zoom pre-shift
+    off += 256;
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + off);
 
 #define use_raw (p.raw != nullptr)
@@ -94,6 +97,7 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
         const int k2 = idx >> LOG2R3, n3 = idx & (R3 - 1);
         tw2[idx] = cispi(-2.0f * (float)((n3 * k2) & (M - 1)) / (float)M);
     }
+    if (tid < 32) zrho[tid] = cispi(-2.0f * (float)((p.zoom_base * tid) & 31) * 0.03125f);
     __syncthreads();
 
     // ---- serial work (service warp): Dirichlet fit + mix phasor table, scalar tail + record
@@ -199,12 +203,14 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
 
     // forward pass 1 of half h of block i: samples x[2m + h], m = n1*M + j (from the shared-memory raw
     // stage in stage A, re-read from global/L2 in stage B) -> radix-32 over n1 -> twiddle W_F^{j k1}
-    auto pass1 = [&](auto mix_c, int i, int h, float2 ph0, const float2 *rho, float &energy) {
-        constexpr bool mix = decltype(mix_c)::value;
+    //   SHIFT : multiply by the phasor rho[n1] * ph0 (mix of stage B, or the integer pre-shift of the zoom band)
+    //   STAGEB: FFT#2 (raw block re-read from global/L2, no energy sum); otherwise FFT#1 from the shared raw stage
+    auto pass1 = [&](auto shift_c, auto stageb_c, int i, int h, float2 ph0, const float2 *rho, float &energy) {
+        constexpr bool shift = decltype(shift_c)::value, stageb = decltype(stageb_c)::value;
         const int blk = (int)blockIdx.x + i * (int)gridDim.x;
         float2 x[32];
         if (use_raw) {
-            if constexpr (!mix) {
+            if constexpr (!stageb) {
                 const uint16_t *rawt = reinterpret_cast<const uint16_t *>(raw_s);
 #pragma unroll
                 for (int n1 = 0; n1 < 32; ++n1) x[brev(n1, 5)] = rawconv(rawt[2 * (n1 * M + tid) + h]);
@@ -218,12 +224,13 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
 #pragma unroll
             for (int n1 = 0; n1 < 32; ++n1) x[brev(n1, 5)] = __ldg(&iqb[2 * (n1 * M + tid) + h]);
         }
-        if constexpr (!mix) {
+        if constexpr (!stageb) {
             float2 e2 = make_float2(0.f, 0.f);
 #pragma unroll
             for (int n1 = 0; n1 < 32; ++n1) e2 = __ffma2_rn(x[n1], x[n1], e2);
             energy += e2.x + e2.y;
-        } else {
+        }
+        if constexpr (shift) {
             const float4 *rho4 = reinterpret_cast<const float4 *>(rho);
 #pragma unroll
             for (int n1 = 0; n1 < 32; n1 += 2) {
@@ -240,7 +247,7 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
         cur[1] = cmul(ws, ws);
         cur[2] = cmul(cur[1], ws);
         cur[3] = ws4;
-        if constexpr (mix) {
+        if constexpr (shift) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) cur[c] = cmul(cur[c], ph0);
             st8(a1b, cmul(x[0], ph0));
@@ -320,9 +327,16 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
                 par ^= 1;
             }
             float tenergy = 0.f;
+            const bool shiftA = (p.zoom_base != 0);
 #pragma unroll 1
             for (int h = 0; h < 2; ++h) {
-                pass1(std::false_type{}, ia, h, make_float2(1.f, 0.f), nullptr, tenergy);
+                if (shiftA) {     // zoom band not at bin 0: x[n] exp(-2 pi i b0 n / NB), n = 2 (n1 M + j) + h
+                    const int e = (int)(((long long)p.zoom_base * tid) & (F - 1));
+                    const float turns = -((float)e / (float)F) - (float)h * ((float)p.zoom_base / (float)NB);
+                    pass1(std::true_type{}, std::false_type{}, ia, h, cispi(2.f * turns), zrho, tenergy);
+                } else {
+                    pass1(std::false_type{}, std::false_type{}, ia, h, make_float2(1.f, 0.f), nullptr, tenergy);
+                }
                 bar_sync(BAR_MAIN, T);
                 // the raw stage is not read again in stage A: fetch the next block's tile into it
                 if (h == 1 && use_raw && tid == 0 && has_block(ia + 1)) issue_tile(ia + 1);
@@ -357,7 +371,7 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const int k = lane + 32 * c;
-                const uint32_t rel = (uint32_t)(k - p.win_start);
+                const uint32_t rel = (uint32_t)(k - p.zoom_w0);
                 vb = max(vb, rel < (uint32_t)p.win_len ? __float_as_uint(zpow[k]) : 0u);
             }
             const uint32_t gb = __reduce_max_sync(0xffffffffu, vb);
@@ -365,7 +379,7 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
 #pragma unroll
             for (int c = 3; c >= 0; --c) {
                 const int k = lane + 32 * c;
-                const uint32_t rel = (uint32_t)(k - p.win_start);
+                const uint32_t rel = (uint32_t)(k - p.zoom_w0);
                 if (rel < (uint32_t)p.win_len && __float_as_uint(zpow[k]) == gb) key = rel;
             }
             key = __reduce_min_sync(0xffffffffu, key);
@@ -386,7 +400,7 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
                 fs.sig_energy1 = s0 / (float)NB;
                 fs.delta = 0.f;
             }
-            if (carrier && tid < 7) fs.mags[tid] = sqrtf(zpow[kpeak - 3 + tid]);
+            if (carrier && tid < 7) fs.mags[tid] = sqrtf(zpow[p.zoom_w0 + (int)key - 3 + tid]);
             bar_arrive(BAR_FITREQ + q, NTHREADS);
         }
 
@@ -421,7 +435,7 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
             float unused_energy = 0.f;
 
             // ---- half 0: E' = FFT_F(x'[2m]) -> parked
-            pass1(std::true_type{}, i, 0, cispi(2.f * turns0), fs.rho, unused_energy);
+            pass1(std::true_type{}, std::true_type{}, i, 0, cispi(2.f * turns0), fs.rho, unused_energy);
             bar_sync(BAR_MAIN, T);
             pass2();
             __syncwarp();
@@ -438,7 +452,7 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
             bar_sync(BAR_MAIN, T);          // every warp is done reading the buffer
 
             // ---- half 1: O' = FFT_F(x'[2m+1]); join, x conj(T)/N, split into A (inverted now) and B (parked)
-            pass1(std::true_type{}, i, 1, cispi(2.f * (turns0 + turns_h)), fs.rho, unused_energy);
+            pass1(std::true_type{}, std::true_type{}, i, 1, cispi(2.f * (turns0 + turns_h)), fs.rho, unused_energy);
             bar_sync(BAR_MAIN, T);
             pass2();
             __syncwarp();

@@ -261,7 +261,7 @@ int thr_create(const thr_config *cfg, thr_detector **out) {
     const int zoom_base = (ws >= 3 && we + 3 < 128) ? 0 : ((ws % N) - 3 + N) % N;
     Variant var_generic = var;
     bool use_2x = false;
-    if (zoom_cfg && zoom_base == 0 && NT == 1 && N == 32768 && !(cfg->flags & THR_CFG_GENERIC_KERNEL)) {
+    if (zoom_cfg && NT == 1 && N == 32768 && !(cfg->flags & THR_CFG_GENERIC_KERNEL)) {
         Variant v2;
         if (thr::pick_variant_2x(N, &v2)) {
             var = v2;
