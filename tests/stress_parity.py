@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Randomised parity stress: random detector geometries / thresholds / signal levels, CUDA path vs oracle.
 
-    python tools/stress_parity.py [n_configs] [seed]
+    python tests/stress_parity.py [n_configs] [seed]
 
 Prints one line per configuration and a summary of any mismatch (the parity bar of tests/parity_util.py)."""
 import os
@@ -12,7 +12,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))      # a checker: lives with the tests, the only users of oracle/
 
 import parity_util as parity  # noqa: E402
 from oracle import thrifty_oracle as orc  # noqa: E402

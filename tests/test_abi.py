@@ -81,6 +81,16 @@ def test_product_never_touches_the_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle", text, re.M), f
                 assert "thrifty_oracle" not in text, f
                 assert "/root/reference" not in text, f
+                assert "fastdet_oracle" not in text, f
+    # tools/ (sweeps, profiling helpers, microbenchmarks) do not use the oracle either; bench.py only in its CPU legs
+    for f in os.listdir(os.path.join(ROOT, "tools")):
+        if f.endswith((".py", ".sh")):
+            text = open(os.path.join(ROOT, "tools", f)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", text, re.M) and "thrifty_oracle" not in text, f
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+    gpu_arm = bench[bench.index("def run_ours("):bench.index("def main(")]
+    assert "from oracle" not in gpu_arm and "import oracle" not in gpu_arm
+    assert gpu_arm.count("cpu_oracle_rate_single(") == 1      # the cpu_baseline leg, rank 0, N = 1 only
 
 
 def test_headline_kernels_keep_their_arrays_in_registers():

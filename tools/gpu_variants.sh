@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 : > gpurun_out/variants.jsonl
 for v in "$@"; do
-  THRIFTY_B200_LIB=$PWD/thrifty_b200/_lib/variants/$v.so timeout 300 python tools/variant_check.py >> gpurun_out/variants.jsonl 2>> gpurun_out/variants.err
+  THRIFTY_B200_LIB=$PWD/thrifty_b200/_lib/variants/$v.so timeout 300 python tests/variant_check.py >> gpurun_out/variants.jsonl 2>> gpurun_out/variants.err
 done
 python - <<'PY'
 import json
