@@ -361,6 +361,17 @@ def run_ours(args):
                 traffic = json.load(open(prof)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
+        # the binding resource is the FP32 pipe, not HBM: algorithmic flops = 3 FFTs x 5 N log2 N + 40 N
+        # pointwise per block, against 148 SMs x 128 lanes x 2 flop x the SM clock sampled during the timed region
+        alg_flops = batch * (3 * 5 * n * int(np.log2(n)) + 40 * n)
+        fp32_peak = 148 * 128 * 2 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e12
+        fp32_ach = alg_flops / (ms_kernel * 1e-3) / 1e12
+        fma_pipe = None
+        try:
+            m = json.load(open(os.path.join(ROOT, "profiles", "r01b_final_ncu_summary.json")))["metrics"]
+            fma_pipe = float(m["sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"]["value"]) / 100.0
+        except Exception:
+            pass
         line = {
             "metric": "detect Msamples/s (block_len=16384)", "value": value, "unit": "Msamples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -377,6 +388,9 @@ def run_ours(args):
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "kernel_ms_per_launch": ms_kernel,
+                         "fp32": {"achieved": fp32_ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_ach / fp32_peak,
+                                  "algorithmic_flops_per_launch": alg_flops,
+                                  "fma_pipe_cycles_active_ncu": fma_pipe},
                          "note": "fused kernel is FP32-issue/shared-memory bound (~125 FLOP/B), see DESIGN.md"},
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": batch * (2 * n + 8),
                     "d2h_bytes_per_step": batch * 64, "ms_per_step": e2e_ms, "steps": e2e_steps,

@@ -28,6 +28,12 @@
 #ifndef THR_WL23
 #define THR_WL23 1          // warp-local hand-over between passes 2 and 3 (no CTA barrier)
 #endif
+#ifndef THR_SERVICE_T256
+#define THR_SERVICE_T256 1      // (+12 % at N = 8192) service warpgroup also for the 2-CTAs-per-SM kernel
+#endif
+#ifndef THR_SERVICE_T128
+#define THR_SERVICE_T128 1      // (+10 % at N = 4096) the same for the 4-CTAs-per-SM kernel (N = 4096): 64 x 256 = 128 x 96 + 128 x 32
+#endif
 #ifndef THR_TW3
 #define THR_TW3 1           // (+2 %) inter-pass twiddles W_M^{n3 k2} of FFT#2 / IFFT applied on the pass-3 side from a
                             // per-item register chain instead of the shared-memory table on the pass-2 side
@@ -68,7 +74,7 @@ struct DetectParams {
     float  *dbg_fft_mag;       // optional [N]
 };
 
-template <int LOG2N_, int T_, bool GMEM_>
+template <int LOG2N_, int T_, bool GMEM_, bool FASTDET_ = false>
 struct Cfg {
     static constexpr int LOG2N = LOG2N_;
     static constexpr int N = 1 << LOG2N_;
@@ -96,11 +102,18 @@ struct Cfg {
     // service 32).  Smaller T: several CTAs per SM hide the serial parts, warp 0 runs them inline.
     // One CTA per SM (the buffer takes more than half of the shared memory, or T == 512): service warpgroup.
     static constexpr bool ONE_CTA = (T >= 512) || (BUF_BYTES > 100 * 1024);
-    static constexpr bool SERVICE = ONE_CTA;
+    // setmaxnreg moves registers inside the pool the CTA was launched with (launch registers x LAUNCH_THREADS):
+    // T == 512: 96 x 640 = 512 x 112 + 128 x 32.  T == 256 with two CTAs per SM (N = 8192): 80 x 384 = 256 x 104 + 128 x 32.
+    // Measured at N = 8192: 133 -> 149 Gsamples/s with the service warpgroup; the fastdet flow (no fit, a short tail) is
+    // better off with the registers: 196 vs 180 Gsamples/s, so it keeps the inline service.
+    static constexpr bool SERVICE = ONE_CTA || (THR_SERVICE_T256 != 0 && T == 256 && !FASTDET_)
+                                            || (THR_SERVICE_T128 != 0 && T == 128 && !FASTDET_);
     static constexpr int LAUNCH_THREADS = SERVICE ? T + 128 : T;
     static constexpr int MIN_CTAS = ONE_CTA ? 1 : (T >= 256 ? 2 : (T >= 128 ? 4 : 8));
     // registers per worker after setmaxnreg: what the 64 K file leaves beside the 128 x 32 of the service warpgroup
-    static constexpr int WORKER_REGS = T >= 512 ? 112 : (T >= 256 ? 232 : 240);
+    static constexpr int WORKER_REGS = !ONE_CTA ? (T == 256 ? 104 : 96) : (T >= 512 ? 112 : (T >= 256 ? 232 : 240));
+    static_assert(!SERVICE || T * WORKER_REGS + 128 * 32 <= (65536 / MIN_CTAS / LAUNCH_THREADS / 8 * 8) * LAUNCH_THREADS,
+                  "setmaxnreg targets exceed the CTA's register pool (the kernel would dead-lock)");
     static constexpr int MAX_TPL = 32;               // templates per detector (tail mailbox size)
     // Passes 2 and 3 both work inside one k1 slab (M consecutive elements).  When every warp owns the
     // same slabs in both passes the hand-over 2 -> 3 (and 3' -> 2') only needs __syncwarp(): the warps
@@ -543,9 +556,9 @@ __device__ __forceinline__ ArgOut main_argmax(uint32_t vbits, float s0, float s1
 // integer-bin carrier shift folded into the template spectrum (so FFT #2 disappears: 2 transforms per
 // block), parabolic carrier offset, +-0.5 clip -- see the FASTDET section below.
 template <int LOG2N, int T, bool GMEM, bool MULTI, bool FASTDET = false>
-__global__ void __launch_bounds__(Cfg<LOG2N, T, GMEM>::LAUNCH_THREADS, Cfg<LOG2N, T, GMEM>::MIN_CTAS)
+__global__ void __launch_bounds__(Cfg<LOG2N, T, GMEM, FASTDET>::LAUNCH_THREADS, Cfg<LOG2N, T, GMEM, FASTDET>::MIN_CTAS)
 detect_kernel(const __grid_constant__ DetectParams p) {
-    using C = Cfg<LOG2N, T, GMEM>;
+    using C = Cfg<LOG2N, T, GMEM, FASTDET>;
     constexpr bool SERVICE = C::SERVICE;
     constexpr bool TW3 = (THR_TW3 != 0) && !MULTI && !FASTDET && C::R3 == 16 && C::R2 > 1;
     constexpr int N = C::N, M = C::M, R2 = C::R2, R3 = C::R3, S = C::S;

@@ -13,7 +13,7 @@ namespace thr {
 
 template <int LOG2N, int T, bool GMEM>
 static Variant make_variant(const char *name) {
-    using C = Cfg<LOG2N, T, GMEM>;
+    using C = Cfg<LOG2N, T, GMEM, (THR_FASTDET != 0)>;
     Variant v;
     v.log2n = LOG2N;
     v.threads = T;
@@ -29,9 +29,6 @@ static Variant make_variant(const char *name) {
     return v;
 }
 
-#ifndef THR_FASTDET
-#define THR_FASTDET 0
-#endif
 #if THR_FASTDET
 #define THR_PICK pick_variant_fastdet
 #define THR_SUFFIX ",fastdet>"

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Tiny workloads for compute-sanitizer (memcheck / racecheck / synccheck):
 
-    THRIFTY_B200_MAX_GRID=2 compute-sanitizer --tool racecheck python tools/sanitize_smoke.py
+    THRIFTY_B200_MAX_GRID=2 compute-sanitizer --tool racecheck python tools/sanitize_smoke.py [block_len ...]
 
 With the grid capped at 2 CTAs every CTA walks several blocks, so the software pipeline (stage A of block
 i+1 next to the fit / tail of earlier blocks, raw-tile ring, mailboxes) is exercised, not just its prologue.
@@ -25,13 +25,17 @@ cases = [
     (16384, example, 4920, (7, 300), 8, {}),                           # full FFT#1
     (16384, example, 4920, (7, 110), 8, dict(fastdet=True)),           # fastdet semantics (shifted-template table)
     (16384, t11, None, (7, 110), 6, {}),                               # two templates
-    (8192, t10, None, (7, 110), 10, {}),                               # 2 CTAs/SM variant, inline service
-    (4096, t9, None, (7, 110), 12, {}),
+    (8192, t10, None, (7, 110), 10, {}),                               # 2 CTAs/SM variant, service warpgroup
+    (8192, np.stack([synth.gold_template(10, i) for i in range(2)]), None, (7, 300), 8, {}),   # ... two templates, full FFT#1
+    (4096, t9, None, (7, 110), 12, {}),                                # 4 CTAs/SM variant
     (4096, t9, None, (1, 2047), 8, dict(fastdet=True)),                # fastdet gather fall-back
     (32768, example, 4920, (7, 110), 7, {}),                           # 2 x 16384 kernel
     (32768, example, 4920, (7, 110), 4, dict(generic_kernel=True)),    # global-scratch variant
 ]
+only = [int(a) for a in sys.argv[1:]]                                 # optional: block lengths to run
 for n, tpl, hist, win, nblk, kw in cases:
+    if only and n not in only:
+        continue
     tpl0 = tpl[0] if tpl.ndim == 2 else tpl
     hist = hist or len(tpl0) + 6
     raw, _ = synth.make_blocks(nblk, n, hist, tpl0, 0.7, seed=5)
