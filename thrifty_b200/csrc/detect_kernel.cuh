@@ -34,6 +34,9 @@
 #ifndef THR_SERVICE_T128
 #define THR_SERVICE_T128 1      // (+10 % at N = 4096) the same for the 4-CTAs-per-SM kernel (N = 4096): 64 x 256 = 128 x 96 + 128 x 32
 #endif
+#ifndef THR_T128_CTAS
+#define THR_T128_CTAS 4         // resident CTAs per SM of that kernel (3: 80 x 256 = 128 x 128 + 128 x 32, no spills, but -4 %)
+#endif
 #ifndef THR_TW3
 #define THR_TW3 1           // (+2 %) inter-pass twiddles W_M^{n3 k2} of FFT#2 / IFFT applied on the pass-3 side from a
                             // per-item register chain instead of the shared-memory table on the pass-2 side
@@ -109,9 +112,10 @@ struct Cfg {
     static constexpr bool SERVICE = ONE_CTA || (THR_SERVICE_T256 != 0 && T == 256 && !FASTDET_)
                                             || (THR_SERVICE_T128 != 0 && T == 128 && !FASTDET_);
     static constexpr int LAUNCH_THREADS = SERVICE ? T + 128 : T;
-    static constexpr int MIN_CTAS = ONE_CTA ? 1 : (T >= 256 ? 2 : (T >= 128 ? 4 : 8));
+    static constexpr int MIN_CTAS = ONE_CTA ? 1 : (T >= 256 ? 2 : (T >= 128 ? (SERVICE ? THR_T128_CTAS : 4) : 8));
     // registers per worker after setmaxnreg: what the 64 K file leaves beside the 128 x 32 of the service warpgroup
-    static constexpr int WORKER_REGS = !ONE_CTA ? (T == 256 ? 104 : 96) : (T >= 512 ? 112 : (T >= 256 ? 232 : 240));
+    static constexpr int WORKER_REGS = !ONE_CTA ? (T == 256 ? 104 : (THR_T128_CTAS == 3 ? 128 : 96))
+                                                : (T >= 512 ? 112 : (T >= 256 ? 232 : 240));
     static_assert(!SERVICE || T * WORKER_REGS + 128 * 32 <= (65536 / MIN_CTAS / LAUNCH_THREADS / 8 * 8) * LAUNCH_THREADS,
                   "setmaxnreg targets exceed the CTA's register pool (the kernel would dead-lock)");
     static constexpr int MAX_TPL = 32;               // templates per detector (tail mailbox size)
