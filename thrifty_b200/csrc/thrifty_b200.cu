@@ -513,16 +513,26 @@ int thr_detect_batch_device_c64(thr_detector *d, const float *d_iq, const int64_
     return launch(d, d->stream, nullptr, d_iq, d_idx, n_blocks, d_out, nullptr, nullptr, nullptr, true);
 }
 
-// memcpy on up to 4 threads: one core moves ~10 GB/s, PCIe Gen5 takes 50
+// memcpy on several threads: one core moves ~10 GB/s, PCIe Gen5 takes 50.  THRIFTY_B200_COPY_THREADS (1..16) overrides
+// the default of 8 threads (4 on hosts with fewer than 16 hardware threads).
+static int copy_threads() {
+    static const int n = [] {
+        int v = std::thread::hardware_concurrency() >= 16 ? 8 : 4;
+        if (const char *e = std::getenv("THRIFTY_B200_COPY_THREADS")) v = std::atoi(e);
+        return v < 1 ? 1 : (v > 16 ? 16 : v);
+    }();
+    return n;
+}
 static void parallel_memcpy(void *dst, const void *src, size_t bytes) {
     constexpr size_t MIN_PART = (size_t)2 << 20;
-    const int parts = bytes >= 4 * MIN_PART ? 4 : (bytes >= 2 * MIN_PART ? 2 : 1);
-    if (parts == 1) {
+    int parts = (int)(bytes / MIN_PART);
+    if (parts > copy_threads()) parts = copy_threads();
+    if (parts <= 1) {
         std::memcpy(dst, src, bytes);
         return;
     }
     const size_t part = (bytes / parts) & ~(size_t)63;            // the last part also takes the remainder
-    std::thread th[3];
+    std::thread th[15];
     for (int i = 1; i < parts; ++i) {
         const size_t off = (size_t)i * part, len = (i == parts - 1) ? bytes - off : part;
         th[i - 1] = std::thread([=] { std::memcpy((char *)dst + off, (const char *)src + off, len); });
@@ -541,8 +551,8 @@ static bool is_pageable(const void *p) {
 }
 
 // Pageable input (a NumPy array, a Python bytes object): an "asynchronous" copy from it is staged by the driver at
-// ~10 GB/s and blocks the calling thread.  Copying the chunk into page-locked staging ourselves (4 threads) runs at
-// ~25 GB/s and leaves the DMA truly asynchronous, so it overlaps the kernel of the other slot.
+// ~10 GB/s and blocks the calling thread.  Copying the chunk into page-locked staging ourselves (several threads) runs at
+// 25+ GB/s and leaves the DMA truly asynchronous, so it overlaps the kernel of the other slot.
 static int stage_pageable(thr_detector *d, Slot &s, const void **src, size_t bytes, size_t cap_hint) {
     if (s.h_in_cap < bytes) {
         if (s.h_in) cudaFreeHost(s.h_in);

@@ -167,6 +167,9 @@ def run_pageable(n_blocks=8192, reps=3):
 
 
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "pageable":
+        run_pageable()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "card":
         run_card(n_blocks=4096)
         run_stream()
