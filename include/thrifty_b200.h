@@ -130,7 +130,8 @@ typedef struct thr_info {
  * no CPU fallback).  Testing aid: the environment variable THRIFTY_B200_MAX_GRID=<n> caps the persistent grid at n CTAs
  * so that small inputs exercise the multi-block pipeline of a CTA (compute-sanitizer runs).
  * THRIFTY_B200_COPY_THREADS=<1..16> sets how many host threads copy pageable input into the page-locked staging buffers
- * (default 8, or 4 on hosts with fewer than 16 hardware threads). */
+ * (default 8, or 4 on hosts with fewer than 16 hardware threads); they use non-temporal stores unless
+ * THRIFTY_B200_COPY_NT=0. */
 int  thr_create(const thr_config *cfg, thr_detector **out);
 void thr_destroy(thr_detector *det);
 /* Message for the last error on `det`, or for the last failed thr_create if det == NULL. */
