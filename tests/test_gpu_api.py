@@ -135,6 +135,14 @@ def test_card_ingest_gpu_decode():
         bad[len(bad) // 2] = ord("!")
         with pytest.raises(NativeError):
             det.detect_card(bytes(bad))
+        # a short payload in a later chunk (lines are scanned chunk by chunk): same line number as a scan of the whole text
+        lines = data.split(b"\n")
+        victim = [i for i, ln in enumerate(lines) if ln and ln[:1].isdigit()][len(raw) - 2]
+        lines[victim] = lines[victim][:-5]
+        with pytest.raises(NativeError, match="data line %d is malformed" % (victim + 1)):
+            det.detect_card(b"\n".join(lines))
+        ts3, _, r3, _ = det.detect_card(data)                # the detector is usable after both errors
+        assert r3.tobytes() == want.tobytes()
         det.close()
     # the Detector front end over a binary stream
     cfg, raw, block_idx, ref, _ = parity.load_golden("n4096_gold9")

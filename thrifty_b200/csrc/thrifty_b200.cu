@@ -729,14 +729,16 @@ static bool starts_with(const char *p, const char *e, const char *lit) {
     return (size_t)(e - p) >= n && std::memcmp(p, lit, n) == 0;
 }
 
-int thr_card_scan(const char *text, size_t len, int32_t block_len, int32_t final_chunk, int64_t max_blocks,
-                  double *timestamps, int64_t *block_idx, int64_t *payload_off, int64_t *n_found,
-                  int64_t *consumed, int64_t *bad_line) {
+// `lines` (optional): in = lines seen by earlier calls on the same text, out = lines seen including this call, so that
+// a caller scanning piecewise reports the same line numbers as one scan over the whole text.
+static int card_scan_lines(const char *text, size_t len, int32_t block_len, int32_t final_chunk, int64_t max_blocks,
+                           double *timestamps, int64_t *block_idx, int64_t *payload_off, int64_t *n_found,
+                           int64_t *consumed, int64_t *bad_line, int64_t *lines) {
     if (!text || !timestamps || !block_idx || !payload_off || !n_found || !consumed || block_len < 1)
         return THR_ERR_INVALID;
     const int64_t want = ((2 * (int64_t)block_len + 2) / 3) * 4;       // base64 characters per payload
     const char *p = text, *end = text + len;
-    int64_t n = 0, line_no = 0;
+    int64_t n = 0, line_no = lines ? *lines : 0;
     if (bad_line) *bad_line = -1;
     while (p < end && n < max_blocks) {
         // Fast path: a data line's payload has a known length, so after the two numbers the end of the
@@ -803,7 +805,15 @@ int thr_card_scan(const char *text, size_t len, int32_t block_len, int32_t final
     }
     *n_found = n;
     *consumed = p - text;
+    if (lines) *lines = line_no;
     return THR_OK;
+}
+
+int thr_card_scan(const char *text, size_t len, int32_t block_len, int32_t final_chunk, int64_t max_blocks,
+                  double *timestamps, int64_t *block_idx, int64_t *payload_off, int64_t *n_found,
+                  int64_t *consumed, int64_t *bad_line) {
+    return card_scan_lines(text, len, block_len, final_chunk, max_blocks, timestamps, block_idx, payload_off, n_found,
+                           consumed, bad_line, nullptr);
 }
 
 int thr_detect_card(thr_detector *d, const char *text, size_t len, int32_t final_chunk, int64_t max_blocks,
@@ -814,14 +824,9 @@ int thr_detect_card(thr_detector *d, const char *text, size_t len, int32_t final
     CU(d, cudaSetDevice(d->device));
     const int N = d->cfg.block_len, NT = d->cfg.n_templates;
     const int64_t want = ((2 * (int64_t)N + 2) / 3) * 4;
-    std::vector<int64_t> off((size_t)max_blocks);
-    int64_t bad_line = -1;
-    int rc = thr_card_scan(text, len, N, final_chunk, max_blocks, timestamps, block_idx, off.data(), n_blocks,
-                           consumed, &bad_line);
-    if (rc != THR_OK)
-        return fail(d, rc, ".card data line %lld is malformed (expected '<time> <index> <%lld base64 chars>')",
-                    (long long)bad_line, (long long)want);
-    const int64_t nb_total = *n_blocks;
+    if (max_blocks < 0) return fail(d, THR_ERR_INVALID, "max_blocks is negative");
+    *n_blocks = 0;
+    *consumed = 0;
     if (int rc0 = slots_reset(d)) return rc0;
     if (!d->d_bad) {
         CU(d, cudaMalloc(&d->d_bad, 8 * sizeof(unsigned int)));
@@ -830,14 +835,30 @@ int thr_detect_card(thr_detector *d, const char *text, size_t len, int32_t final
     CU(d, cudaStreamSynchronize(d->slot[0].stream));
     const int64_t chunk = d->host_chunk;
     const bool pageable = is_pageable(text);
-    int c = 0;
-    for (int64_t b0 = 0; b0 < nb_total; b0 += chunk, ++c) {
+    std::vector<int64_t> off((size_t)chunk);
+    // The lines of chunk c+1 are scanned while chunk c crosses PCIe: each line costs two cache (and TLB) misses in a text of
+    // hundreds of megabytes, ~1 ms per 4096 lines if done up front.
+    int64_t pos = 0, b0 = 0, lines = 0;
+    int rc = THR_OK;
+    for (int c = 0; b0 < max_blocks; ++c) {
+        const int64_t ask = (max_blocks - b0) < chunk ? (max_blocks - b0) : chunk;
+        int64_t got = 0, used = 0, bad_line = -1;
+        rc = card_scan_lines(text + pos, len - (size_t)pos, N, final_chunk, ask, timestamps + b0, block_idx + b0, off.data(),
+                             &got, &used, &bad_line, &lines);
+        if (rc != THR_OK)
+            return fail(d, rc, ".card data line %lld is malformed (expected '<time> <index> <%lld base64 chars>')",
+                        (long long)bad_line, (long long)want);
+        const char *ctext = text + pos;            // payload offsets of this chunk are relative to it
+        pos += used;
+        *consumed = pos;
+        if (got == 0) break;
         Slot &s = d->slot[c & 1];
-        const int nb = (int)((nb_total - b0) < chunk ? (nb_total - b0) : chunk);
+        const int nb = (int)got;
         rc = slot_flush(d, s);
         if (rc != THR_OK) return rc;
-        // byte range of the text that covers the payloads of this chunk (aligned down to 4)
-        const int64_t t0 = off[b0] & ~(int64_t)3, t1 = off[b0 + nb - 1] + want;
+        // byte range of the text that covers the payloads of this chunk (aligned down to 4 in the caller's buffer)
+        const int64_t lead = (int64_t)((uintptr_t)(ctext + off[0]) & 3);
+        const int64_t t0 = off[0] - lead, t1 = off[nb - 1] + want;
         const size_t bytes = (size_t)(t1 - t0);
         if (s.text_cap < bytes + 16) {
             cudaFree(s.d_text);
@@ -849,9 +870,9 @@ int thr_detect_card(thr_detector *d, const char *text, size_t len, int32_t final
         int64_t *h_rel = s.h_idx + d->cfg.max_batch;
         for (int i = 0; i < nb; ++i) {
             s.h_idx[i] = block_idx[b0 + i];
-            h_rel[i] = off[b0 + i] - t0;
+            h_rel[i] = off[i] - t0;
         }
-        const void *tsrc = text + t0;
+        const void *tsrc = ctext + t0;
         if (pageable) {
             rc = stage_pageable(d, s, &tsrc, bytes, bytes + bytes / 4);
             if (rc != THR_OK) return rc;
@@ -868,6 +889,9 @@ int thr_detect_card(thr_detector *d, const char *text, size_t len, int32_t final
         if (rc != THR_OK) return rc;
         rc = slot_queue_records(d, s, out + (size_t)b0 * NT, (size_t)nb * NT);
         if (rc != THR_OK) return rc;
+        b0 += got;
+        *n_blocks = b0;
+        if (got < ask) break;                      // end of the text (or an unterminated last line) reached
     }
     for (auto &s : d->slot) {
         rc = slot_flush(d, s);
