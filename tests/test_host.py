@@ -274,3 +274,37 @@ def test_fastdet_toad_line_matches_native_format():
     for a, b in zip(mine[5:], gold[5:]):
         assert abs(float(a) - float(b)) <= 1e-4 * max(1.0, abs(float(b)))
     assert "carrier @" in fastdet.info_line(rec, (0., 15.), (0., 15.))
+
+
+def test_records_to_results_matches_single_record_conversion():
+    """The batch conversion of thr_records (used by every iterator of the Detector seam) yields the same values
+    and field types as the per-record one: carrier energy / noise numpy float32 (reference: float32 spectrum),
+    the rest Python numbers, corr_info / soa None without a carrier, offsets 0 below threshold (detect.py:60-78)."""
+    from thrifty_b200 import detect
+    from thrifty_b200._native import RECORD_DTYPE
+    rng = np.random.default_rng(5)
+    n = 500
+    recs = np.zeros(n, dtype=RECORD_DTYPE)
+    f = rng.integers(0, 3, n)
+    recs["flags"] = np.where(f == 2, 3, f)
+    recs["soa"] = rng.random(n) * 1e7
+    for k in ("carrier_offset", "carrier_energy", "carrier_noise", "corr_offset", "corr_energy", "corr_noise"):
+        recs[k] = rng.random(n).astype(np.float32)
+    recs["carrier_noise"][::7] = np.nan
+    recs["block_idx"] = np.arange(n) + 10
+    recs["carrier_bin"] = rng.integers(0, 16384, n)
+    recs["corr_sample"] = rng.integers(0, 11000, n)
+    ts = rng.random(n)
+
+    def key(detected, r):
+        def tv(x):
+            return type(x).__name__, repr(x)
+        return (detected, tv(r.timestamp), tv(r.block), tv(r.soa), tuple(tv(x) for x in r.carrier_info),
+                None if r.corr_info is None else tuple(tv(x) for x in r.corr_info), r.rxid, r.txid)
+
+    one = [detect.record_to_result(recs[i], float(ts[i]), 3) for i in range(n)]
+    many = detect.records_to_results(recs, ts, 3)
+    assert [key(*p) for p in one] == [key(*p) for p in many]
+    assert detect.records_to_results(recs[:0], ts[:0], 3) == []
+    assert [r.timestamp for _, r in detect.records_to_results(recs[:3], 1.5, 3)] == [1.5] * 3
+    assert [r.serialize() for d, r in one if d] == [r.serialize() for d, r in many if d]

@@ -19,6 +19,7 @@ the 64-byte records back into the reference's result types.  There is no CPU fal
 from __future__ import print_function
 
 import argparse
+import gc
 import sys
 from collections import namedtuple
 
@@ -52,6 +53,58 @@ def record_to_result(rec, timestamp, rxid):
     result = toads_data.DetectionResult(timestamp, int(rec["block_idx"]), soa, carrier_info,
                                         corr_info, rxid)
     return detected, result
+
+
+def records_to_results(recs, timestamps, rxid):
+    """Batch form of record_to_result: 1-D thr_record array + timestamps -> list of (detected, DetectionResult).
+
+    Same values and field types as record_to_result (carrier energy / noise stay numpy float32 scalars like the
+    reference's, everything else Python numbers), but the columns are pulled out of the structured array once per batch:
+    ~1 us instead of ~12 us per block, which matters once the GPU side ingests a million blocks a second."""
+    n = len(recs)
+    if n == 0:
+        return []
+    flags = recs["flags"].tolist()
+    block_idx = recs["block_idx"].tolist()
+    soa = recs["soa"].tolist()
+    cbin = recs["carrier_bin"].tolist()
+    coff = recs["carrier_offset"].tolist()
+    cen = list(recs["carrier_energy"])
+    cno = list(recs["carrier_noise"])
+    ksam = recs["corr_sample"].tolist()
+    koff = recs["corr_offset"].tolist()
+    ken = recs["corr_energy"].tolist()
+    kno = recs["corr_noise"].tolist()
+    if np.ndim(timestamps) == 0:
+        timestamps = [timestamps] * n
+    elif isinstance(timestamps, np.ndarray):
+        timestamps = timestamps.tolist()
+    carrier_cls, corr_cls, result_cls = toads_data.CarrierSyncInfo, toads_data.CorrDetectionInfo, toads_data.DetectionResult
+    out = []
+    # 3 n container objects without reference cycles: the cyclic collector would only re-scan them (2-3x slower)
+    gc_was_on = gc.isenabled()
+    gc.disable()
+    try:
+        _fill_results(out, n, flags, timestamps, block_idx, soa, cbin, coff, cen, cno, ksam, koff, ken, kno, rxid,
+                      carrier_cls, corr_cls, result_cls)
+    finally:
+        if gc_was_on:
+            gc.enable()
+    return out
+
+
+def _fill_results(out, n, flags, timestamps, block_idx, soa, cbin, coff, cen, cno, ksam, koff, ken, kno, rxid,
+                  carrier_cls, corr_cls, result_cls):
+    for i in range(n):
+        f = flags[i]
+        detected = bool(f & FLAG_CORR)
+        if f & FLAG_CARRIER:
+            carrier_info = carrier_cls(cbin[i], coff[i], cen[i], cno[i])
+            corr_info = corr_cls(ksam[i], koff[i] if detected else 0, ken[i], kno[i])
+            out.append((detected, result_cls(timestamps[i], block_idx[i], soa[i], carrier_info, corr_info, rxid)))
+        else:
+            out.append((detected, result_cls(timestamps[i], block_idx[i], None, carrier_cls(cbin[i], 0, cen[i], cno[i]),
+                                             None, rxid)))
 
 
 class Detector(object):
@@ -124,7 +177,7 @@ class Detector(object):
                 assert len(b) == n                                  # detect.py:62
                 conv.append(np.asarray(b, dtype=np.complex64))
             recs = self.native.detect_c64(np.stack(conv), idx)
-        return [record_to_result(recs[i, 0], items[i][0], self.rxid) for i in range(len(items))]
+        return records_to_results(recs[:, 0], [it[0] for it in items], self.rxid)
 
     # ---- whole `.card` streams: scan on the host, base64 decode + detect on the GPU
     def detect_card_stream(self, stream, chunk_bytes=64 << 20):
@@ -154,8 +207,8 @@ class Detector(object):
                 if total == 0:
                     break
                 ts, idx, recs, consumed = self.native.detect_card_ptr(buf.ptr, total, final=final)
-                for i in range(len(ts)):
-                    yield record_to_result(recs[i, 0], float(ts[i]), self.rxid)
+                for pair in records_to_results(recs[:, 0], ts, self.rxid):
+                    yield pair
                 fill = total - consumed
                 if fill:
                     view[:fill] = view[consumed:total].copy()
@@ -204,8 +257,8 @@ class Detector(object):
             buf = np.concatenate([tail, np.frombuffer(data[:nblk * new], dtype=np.uint8)])
             recs = self.native.detect_stream(buf, next_block)
             now = time.time()
-            for i in range(nblk):
-                yield record_to_result(recs[i, 0], now, self.rxid)
+            for pair in records_to_results(recs[:nblk, 0], now, self.rxid):
+                yield pair
             tail = buf[len(buf) - 2 * h:] if h else np.zeros(0, dtype=np.uint8)
             next_block += nblk
             if len(data) < chunk_blocks * new:

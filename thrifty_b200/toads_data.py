@@ -14,6 +14,8 @@ CorrDetectionInfo = namedtuple("CorrDetectionInfo", ["sample", "offset", "energy
 class DetectionResult(object):
     """One block's detection outcome (thrifty/toads_data.py:22-45)."""
 
+    __slots__ = ("timestamp", "block", "soa", "carrier_info", "corr_info", "rxid", "txid")
+
     def __init__(self, timestamp, block, soa, carrier_info, corr_info, rxid=None, txid=None):
         self.timestamp = timestamp
         self.block = block
