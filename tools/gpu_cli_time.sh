@@ -1,6 +1,7 @@
 #!/bin/bash
 # wall-clock of the `detect` / `fastdet` command lines on a synthetic 4096-block .card (N=16384)
 mkdir -p gpurun_out /tmp/cli
+export PYTHONPATH=$PWD${PYTHONPATH:+:$PYTHONPATH}
 python - <<'PY'
 import numpy as np, sys
 sys.path.insert(0, '.')
