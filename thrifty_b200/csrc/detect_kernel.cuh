@@ -28,6 +28,9 @@
 #ifndef THR_WL23
 #define THR_WL23 1          // warp-local hand-over between passes 2 and 3 (no CTA barrier)
 #endif
+#ifndef THR_TW3_MULTI
+#define THR_TW3_MULTI 0     // the same in the multi-template kernels: measured -6 % (176 bytes of spills with the template loop)
+#endif
 #ifndef THR_SERVICE_T256
 #define THR_SERVICE_T256 1      // (+12 % at N = 8192) service warpgroup also for the 2-CTAs-per-SM kernel
 #endif
@@ -564,7 +567,7 @@ __global__ void __launch_bounds__(Cfg<LOG2N, T, GMEM, FASTDET>::LAUNCH_THREADS, 
 detect_kernel(const __grid_constant__ DetectParams p) {
     using C = Cfg<LOG2N, T, GMEM, FASTDET>;
     constexpr bool SERVICE = C::SERVICE;
-    constexpr bool TW3 = (THR_TW3 != 0) && !MULTI && !FASTDET && C::R3 == 16 && C::R2 > 1;
+    constexpr bool TW3 = (THR_TW3 != 0) && (!MULTI || THR_TW3_MULTI != 0) && !FASTDET && C::R3 == 16 && C::R2 > 1;
     constexpr int N = C::N, M = C::M, R2 = C::R2, R3 = C::R3, S = C::S;
     constexpr int I1 = C::I1, I2 = C::I2, I3 = C::I3;
     constexpr int LOG2M = ilog2(M), LOG2R3 = ilog2(R3), LOG2R2 = ilog2(R2), LOG2S = ilog2(S);
