@@ -146,7 +146,7 @@ int  thr_device_count(void);
  * out:       n_blocks * n_templates records
  * n_blocks may exceed max_batch; the call chunks and overlaps copies with compute.
  * Host buffers may be pageable or page-locked (thr_host_alloc): page-locked ones are DMA'd directly (PCIe-bound,
- * ~1.6 M blocks/s at N = 16384), pageable ones go through internal page-locked staging (~0.75 M blocks/s);
+ * ~1.6 M blocks/s at N = 16384), pageable ones go through internal page-locked staging (host-memory bound, ~0.7-1.2 M blocks/s);
  * records always return through page-locked staging.  The same holds for thr_detect_card and thr_detect_stream. */
 int thr_detect_batch(thr_detector *det, const uint8_t *raw, const int64_t *block_idx,
                      int64_t n_blocks, thr_record *out);
@@ -162,7 +162,9 @@ int thr_detect_batch_c64(thr_detector *det, const float *iq, const int64_t *bloc
  *   returned.  A payload whose length is not 4*ceil(2N/3) is an error (*bad_line = 1-based line number).
  *   With final_chunk == 0 an unterminated last line is left unconsumed (*consumed = bytes used).
  * thr_detect_card: scan + copy the text to the device + base64 decode ON THE GPU + detect, pipelined
- *   in chunks; timestamps / block_idx / out must hold max_blocks entries (out: max_blocks * n_templates). */
+ *   in chunks (the lines of chunk c+1 are scanned while chunk c crosses PCIe); timestamps / block_idx / out must hold
+ *   max_blocks entries (out: max_blocks * n_templates).  On a malformed line the call fails with the 1-based line
+ *   number in thr_last_error; *n_blocks / *consumed then tell how far the scan got and `out` is unspecified. */
 int thr_card_scan(const char *text, size_t len, int32_t block_len, int32_t final_chunk, int64_t max_blocks,
                   double *timestamps, int64_t *block_idx, int64_t *payload_off, int64_t *n_found,
                   int64_t *consumed, int64_t *bad_line);
