@@ -17,6 +17,7 @@ bool pick_variant_2x(int n, Variant *out) {
     v.i3 = 2;
     v.p3_item = [](int tid, int it) { return H::p3_item(tid, it); };
     v.launch_threads = Cfg2x::LAUNCH_THREADS;
+    v.worker_regs = 112;               // detect_kernel_2x.cuh: setmaxnreg.inc 112 / dec 32
     v.smem = Cfg2x::smem_bytes();
     v.fn = (const void *)&detect2x_kernel;
     v.name = "detect2x_kernel<N=32768 as 2x16384,T=512,smem+L2 park>";

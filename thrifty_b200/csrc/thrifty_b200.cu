@@ -312,6 +312,20 @@ int thr_create(const thr_config *cfg, thr_detector **out) {
         fail(d, THR_ERR_CUDA, "kernel %s does not fit on an SM (smem %zu)", var.name, var.smem);
         return bail(THR_ERR_CUDA);
     }
+    // setmaxnreg only moves registers inside the pool the CTA was launched with; a kernel whose targets exceed it does
+    // not fail, it dead-locks -- refuse such a build here (detect_kernel.cuh asserts the same at compile time, assuming
+    // ptxas allocates what __launch_bounds__ allows)
+    for (const Variant *v : {&var, &var_generic}) {
+        if (!v->worker_regs) continue;
+        cudaFuncAttributes fa;
+        CUC(cudaFuncGetAttributes(&fa, v->fn));
+        const int workers = v->launch_threads - 128;
+        if (fa.numRegs * v->launch_threads < workers * v->worker_regs + 128 * 32) {
+            fail(d, THR_ERR_CUDA, "kernel %s was built with %d registers x %d threads, fewer than its setmaxnreg split needs "
+                 "(%d x %d + 128 x 32)", v->name, fa.numRegs, v->launch_threads, workers, v->worker_regs);
+            return bail(THR_ERR_CUDA);
+        }
+    }
     d->ctas_per_sm = occ;
     d->grid = d->sm_count * occ;
     if (const char *cap = std::getenv("THRIFTY_B200_MAX_GRID")) {      // testing aid: few CTAs walk many blocks each

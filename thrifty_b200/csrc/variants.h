@@ -15,6 +15,7 @@ struct Variant {
     int r2, r3, i3;
     int (*p3_item)(int tid, int it);   // pass-3 item owned by (thread, iteration): fixes the template order
     int launch_threads;
+    int worker_regs = 0;               // setmaxnreg target of the workers (0: the kernel does not re-split registers)
     size_t smem;
     const void *fn;
     const char *name;
