@@ -204,6 +204,34 @@ def run_reference_arm(args):
 
 
 # ----------------------------------------------------------------------------- our arm
+def bind_to_gpu_numa_node(local_rank):
+    """Multi-GPU hosts: run this rank (and so allocate its page-locked buffers, first touch) on the CPUs of the NUMA node
+    its GPU hangs off, so that the e2e leg's H2D traffic does not cross the socket interconnect.  Best effort: returns the
+    node, or None when the host exposes a single node / no locality (then nothing is changed)."""
+    try:
+        import glob
+        import torch
+        nodes = glob.glob("/sys/devices/system/node/node[0-9]*")
+        if len(nodes) < 2:
+            return None
+        pr = torch.cuda.get_device_properties(local_rank)
+        dev = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open(dev).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -216,6 +244,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device -- the detect path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL / c10d print their version banner on stdout when the communicator is created:
@@ -381,7 +410,7 @@ def run_ours(args):
                        "pool_blocks_per_gpu": pool_blocks,
                        "l2_policy": "inputs larger than L2: %d MiB raw pool cycled per GPU" % (pool_blocks * 2 * n >> 20),
                        "kernel": info["kernel"], "grid": info["grid"], "threads": info["threads"],
-                       "smem_bytes": info["smem_bytes"], "parallelism": "stripe%d" % world, "record_gather": ("all_gather of the 64-B record ring every %d steps" % GATHER_EVERY) if world > 1 else "none (1 GPU)",
+                       "smem_bytes": info["smem_bytes"], "parallelism": "stripe%d" % world, "numa_node_rank0": numa_node, "record_gather": ("all_gather of the 64-B record ring every %d steps" % GATHER_EVERY) if world > 1 else "none (1 GPU)",
                        "carrier_detected_last_batch": n_car, "corr_detected_last_batch": n_det,
                        "blocks_per_s": world * batch / (ms_per_step * 1e-3)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
