@@ -103,10 +103,10 @@ struct Cfg {
     // 1, 2) and when it walks across rows (pass 3), and every access is base + immediate.
     static constexpr int ROW_BYTES = GMEM_ ? R3 * 8 : 136;
     static constexpr size_t BUF_BYTES = GMEM_ ? 0 : (size_t)(N / 16) * 136;
-    // T == 512 (one CTA per SM): a dedicated service warpgroup runs the serial fit / tail while the
-    // workers go on with the next block; registers are re-split with setmaxnreg (workers 112,
-    // service 32).  Smaller T: several CTAs per SM hide the serial parts, warp 0 runs them inline.
-    // One CTA per SM (the buffer takes more than half of the shared memory, or T == 512): service warpgroup.
+    // A dedicated service warpgroup runs the serial fit / tail while the workers go on with the next block; registers
+    // are re-split with setmaxnreg (T == 512: workers 112, service 32).  Without it (T <= 64, fastdet flow at T <= 256)
+    // warp 0 runs the serial parts inline and the other CTAs of the SM hide them.
+    // ONE_CTA: one CTA per SM (the buffer takes more than half of the shared memory, or T == 512).
     static constexpr bool ONE_CTA = (T >= 512) || (BUF_BYTES > 100 * 1024);
     // setmaxnreg moves registers inside the pool the CTA was launched with (launch registers x LAUNCH_THREADS):
     // T == 512: 96 x 640 = 512 x 112 + 128 x 32.  T == 256 with two CTAs per SM (N = 8192): 80 x 384 = 256 x 104 + 128 x 32.
