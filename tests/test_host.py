@@ -308,3 +308,12 @@ def test_records_to_results_matches_single_record_conversion():
     assert detect.records_to_results(recs[:0], ts[:0], 3) == []
     assert [r.timestamp for _, r in detect.records_to_results(recs[:3], 1.5, 3)] == [1.5] * 3
     assert [r.serialize() for d, r in one if d] == [r.serialize() for d, r in many if d]
+
+
+def test_bench_numa_binding_is_a_no_op_without_locality_information():
+    """bench.py binds multi-GPU ranks to their GPU's NUMA node on a best-effort basis: with no GPU / a single node /
+    no sysfs entry it must return None and leave the CPU affinity alone."""
+    import bench
+    before = os.sched_getaffinity(0)
+    assert bench.bind_to_gpu_numa_node(0) is None
+    assert os.sched_getaffinity(0) == before
