@@ -216,3 +216,29 @@ def compare_fastdet(got, ref, what="", rtol=RTOL_MAG, atol_off=ATOL_OFFSET):
             assert abs(float(g["soa"]) - float(r["soa"])) <= atol_off, tag + ": soa"
             stats["detected"] += int(bool(r["corr_detected"]))
     return stats
+
+
+# ------------------------------------------------------------------ several templates jointly (BASELINE config 5)
+def make_multi_blocks(n_blocks, block_len, history_len, templates, p_signal, seed):
+    """Block b carries (with probability p_signal) a burst spread with ONE of the templates, chosen by
+    default_rng(seed).  -> (raw uint8[B, 2N], which int[B])."""
+    rng = np.random.default_rng(seed)
+    which = rng.integers(0, len(templates), n_blocks)
+    raw = np.empty((n_blocks, 2 * block_len), dtype=np.uint8)
+    for b in range(n_blocks):
+        raw[b] = synth.make_blocks(1, block_len, history_len, templates[which[b]], p_signal, seed=seed + 1 + b)[0][0]
+    return raw, which
+
+
+def load_multi_golden(name="n16384_gold11x4"):
+    """-> (cfg, templates [T, L], raw, block_idx, reference records [T, B])."""
+    g = np.load(os.path.join(GOLDEN, "detect_%s.npz" % name))
+    tpls = np.stack([synth.gold_template(int(g["gold_bits"]), int(i)) for i in g["gold_idx"]])
+    cfg = dict(name=name, block_len=int(g["block_len"]), history_len=int(g["history_len"]),
+               window=tuple(int(v) for v in g["window"]), n_blocks=int(g["n_blocks"]), p_signal=float(g["p_signal"]),
+               cthresh=tuple(float(v) for v in g["cthresh"]), kthresh=tuple(float(v) for v in g["kthresh"]),
+               seed=int(g["seed"]))
+    raw, which = make_multi_blocks(cfg["n_blocks"], cfg["block_len"], cfg["history_len"], tpls, cfg["p_signal"], cfg["seed"])
+    assert np.uint32(zlib.crc32(raw.tobytes())) == g["raw_crc32"], "synthetic generator drifted"
+    block_idx = 10 + 3 * np.arange(cfg["n_blocks"], dtype=np.int64)
+    return cfg, tpls, raw, block_idx, g["records"], which

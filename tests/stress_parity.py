@@ -118,11 +118,14 @@ def main(n_cfg=None, seed=None):
             det.close()
             # ill-conditioned Dirichlet fits (main lobe much wider than the 7 fitted bins) are sensitive to the
             # last bits of the magnitudes: widen the carrier-offset bar by 10 sigma of that sensitivity
-            tol = [parity.carrier_offset_tolerance(raw[b], int(ref["carrier_bin"][b]), float(ref["carrier_offset"][b]),
-                                                   cfg["n"], cfg["carrier_len"]) if ref["carrier_detected"][b] else 0.0
-                   for b in range(nblk)]
-            stats = parity.compare_records(got, ref, what=tag, carrier_offset_atol=tol)
-            stats["max_offset_tol"] = float(max(tol))
+            if os.environ.get("STRESS_WIDE"):
+                tol = [parity.carrier_offset_tolerance(raw[b], int(ref["carrier_bin"][b]), float(ref["carrier_offset"][b]),
+                                                       cfg["n"], cfg["carrier_len"]) if ref["carrier_detected"][b] else 0.0
+                       for b in range(nblk)]
+                stats = parity.compare_records(got, ref, what=tag, carrier_offset_atol=tol)
+                stats["max_offset_tol"] = float(max(tol))
+            else:
+                stats = parity.compare_records(got, ref, what=tag)
             print("ok  ", tag, kern, {k: (round(v, 7) if isinstance(v, float) else v) for k, v in stats.items()}, flush=True)
         except Exception as e:      # noqa: BLE001
             bad += 1

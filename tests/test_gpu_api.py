@@ -437,6 +437,30 @@ def test_multi_template_vs_independent_oracles():
     det.close()
 
 
+def test_multi_template_n16384_gold11x4_vs_reference_golden():
+    """BASELINE config 5 at its stated size: four Gold-11 templates (L=4914), block_len 16384, history 4920, 320 blocks
+    (> 2 per persistent CTA) through MultiTemplateDetector == four independent runs of the reference's own Detector
+    (tests/golden/detect_n16384_gold11x4.npz, written by oracle/make_golden_multi.py from /root/reference)."""
+    from thrifty_b200.detect import DetectorSettings, MultiTemplateDetector
+    cfg, tpls, raw, block_idx, ref, which = parity.load_multi_golden()
+    settings = DetectorSettings(cfg["block_len"], cfg["history_len"], tpls.shape[1], cfg["cthresh"], cfg["window"],
+                                tpls[0], cfg["kthresh"])
+    det = MultiTemplateDetector(settings, tpls, rxid=2, batch=512)
+    assert "multi" in det.native.info()["kernel"] and "16384" in det.native.info()["kernel"]
+    out = det.detect_many([(0.0, int(block_idx[i]), raw[i]) for i in range(len(raw))])
+    for t in range(len(tpls)):
+        rows = _results_to_rows([o[t] for o in out])
+        stats = parity.compare_records(_rows_as_records(rows), ref[t], what="gold11x4 template %d" % t)
+        assert stats["carrier"] > 200 and stats["detected"] > 200
+        assert all(o[t][1].txid == t for o in out)
+    # the raw record path (no result objects): same launch, records [B, T]
+    recs = det.native.detect_raw(raw, block_idx)
+    for t in range(len(tpls)):
+        assert np.all(recs[:, t]["template_idx"] == t)
+        parity.compare_records(recs[:, t], ref[t], what="gold11x4 records template %d" % t)
+    det.close()
+
+
 def test_smoke_entry():
     sys.path.insert(0, ROOT)
     import __graft_entry__

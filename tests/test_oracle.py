@@ -158,6 +158,22 @@ def test_oracle_matches_reference_golden(name):
             np.testing.assert_array_equal(got[f], ref[f][:limit])
 
 
+def test_oracle_matches_reference_multi_template_golden():
+    """BASELINE config 5 (4 Gold-11 templates at N=16384): golden = four independent reference Detectors."""
+    cfg, tpls, raw, block_idx, ref, _ = parity.load_multi_golden()
+    assert ref.shape == (4, cfg["n_blocks"]) and cfg["n_blocks"] > 2 * 148
+    limit = 10
+    for t in (0, 3):
+        st = orc.DetectorSettings(cfg["block_len"], cfg["history_len"], tpls.shape[1], cfg["cthresh"], cfg["window"],
+                                  tpls[t], cfg["kthresh"])
+        got = orc.detect_blocks(st, raw[:limit], block_idx[:limit])
+        for f in ref.dtype.names:
+            if ref[f].dtype.kind == "f":
+                np.testing.assert_allclose(got[f], ref[t][f][:limit], rtol=1e-10, atol=1e-10, equal_nan=True)
+            else:
+                np.testing.assert_array_equal(got[f], ref[t][f][:limit])
+
+
 def test_golden_arrays(golden_dir):
     import os
     from thrifty_b200 import synth

@@ -23,6 +23,7 @@
 #include <math.h>
 
 #include "../../include/thrifty_b200.h"
+#include "dirichlet_lm.cuh"
 
 // experiment switches (compile-time; defaults are the measured-best configuration)
 #ifndef THR_WL23
@@ -67,9 +68,9 @@ struct DetectParams {
     int zoom;                  // 1: carrier window (+-3 bins) spans <= 128 bins and no stddev term -> pruned FFT#1
     int zoom_base;             // first bin b0 of the 128-bin zoom band: the block is pre-shifted by -b0 bins (0: none)
     int zoom_w0;               // window start inside the band: (win_start - zoom_base) mod N
-    float fit_W;               // carrier_len
-    float fit_WoverN;          // W / N
-    float fit_invN;            // 1 / N
+    double fit_W;              // carrier_len (the Dirichlet fit runs in float64, dirichlet_lm.cuh)
+    double fit_piW;            // pi * W, rounded as the reference's np.pi*W (carrier_sync.py:129)
+    double fit_N;              // block_len
     // fastdet-semantics kernels (FASTDET = true) only:
     const float2 *tpl_shift;   // [win_len][N]: conj(T)[(k - kpeak) mod N]/N per carrier bin of the window, kernel
                                // order (the integer roll of fastdet/corr_detector.cpp:13-17,179 folded into the
@@ -144,7 +145,7 @@ struct Cfg {
     static constexpr bool ZOOM_OK = (R2 >= 8 && R2 % 4 == 0);      // bins < 128 <=> k2 < 4, k3 == 0
     static constexpr size_t smem_bytes() {           // must cover the carve-up in detect_kernel
         return BUF_BYTES + 2 * (size_t)(2 * N) + (size_t)M * 8
-               + 2 * 320 + 2 * 32 + 2 * MAX_TPL * 32 + 256 + 512 + 256 + 64;
+               + 2 * 320 + 2 * 32 + 2 * MAX_TPL * 32 + 256 + 512 + 256 + 64 + sizeof(lm::Rows);
     }
 };
 
@@ -173,6 +174,14 @@ __device__ __forceinline__ float2 cispi(float x) {
     float s, c;
     sincospif(x, &s, &c);
     return make_float2(c, s);
+}
+// Read-only global load that does not allocate in L1: the template spectrum (128 KB per block, re-read from L2 by every
+// block) would otherwise flush the few KB of L1 left beside the shared-memory carve-out, which the service warp's
+// float64 fit needs for its register spills.
+__device__ __forceinline__ float2 ldg_stream(const float2 *ptr) {
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(ptr));
+    return v;
 }
 __host__ __device__ constexpr int brev(int v, int bits) {
     int r = 0;
@@ -371,88 +380,36 @@ __device__ __forceinline__ RedOut block_reduce(float s0, float s1, unsigned long
 }
 
 // ------------------------------------------------------------------ Dirichlet-kernel fit
-// Least-squares fit of A*|D(x - d)| to 7 magnitudes at x = -3..3 (carrier_sync.py:150-196,
-// scipy curve_fit 'lm' from p0 = (y[0], 0)).  Executed by one warp: lane i (mod 8) < 7 owns
-// point i; the four groups of 8 lanes compute the same thing so control flow stays uniform.
-// D(z) = sin(aWz) / (W sin(az)), a = pi/N; every lane evaluates its own point (two sincospi per evaluation).
-struct FitSums {
-    float jaa, jad, jdd, jar, jdr, cost;
+// Least-squares fit of A*|D(x - d)| to the 7 magnitudes at x = -3..3 (carrier_sync.py:150-196: scipy curve_fit
+// 'lm' from p0 = (y[3], 0)) = MINPACK lmdif in float64, restated in dirichlet_lm.cuh.  Executed by one warp: every
+// lane runs the (scalar, warp-uniform) iteration; the 7 rows of the problem live in shared memory (lm::Rows), lane
+// r < 7 does the element-wise work of row r, lanes 8..14 evaluate the sines of the look-ahead offset.
+// y: magnitude of point (lane & 7).  Returns the offset.
+struct WarpExec {                // lm::fit on one warp: lane r < 7 owns row r of the shared lm::Rows
+    int lane;
+    template <class F>
+    __device__ __forceinline__ void each(int from, F &&f) const {
+        if (lane < lm::M && lane >= from) f(lane);
+    }
+    __device__ __forceinline__ void sync() const { __syncwarp(); }
 };
-// xi: abscissa of this lane's point (-3..3).  The sines are taken of (xi - d) directly: angle-difference
-// identities on tabulated sin/cos of xi lose the leading digits of sin(a (xi - d)) when d approaches a sample
-// point other than 0 (|d| > 0.5 happens on weak, wide peaks) and the fit then stalls 5e-4 bins off.
-__device__ __forceinline__ FitSums fit_eval(float y, bool active, float A, float d, float xi, float W,
-                                            float WoverN, float invN) {
-    const float z = xi - d;
-    float s1, c1, s2, c2;
-    sincospif(WoverN * z, &s1, &c1);                  // sin, cos of a W (x - d),  a = pi/N
-    sincospif(invN * z, &s2, &c2);                    // sin, cos of a (x - d)
-    float D, Dp;
-    if (fabsf(s2) < 1e-30f) {
-        D = 1.0f;
-        Dp = 0.0f;
-    } else {
-        const float inv = __fdividef(1.0f, W * s2);
-        D = s1 * inv;
-        const float a = 3.14159265358979f * invN;
-        Dp = a * (W * c1 * s2 - s1 * c2) * inv * __fdividef(1.0f, s2);
-    }
-    const float g = fabsf(D);
-    const float gp = D < 0.f ? -Dp : Dp;
-    const float r = y - A * g;
-    const float ja = g;
-    const float jd = -A * gp;
-    FitSums f;
-    f.jaa = active ? ja * ja : 0.f;
-    f.jad = active ? ja * jd : 0.f;
-    f.jdd = active ? jd * jd : 0.f;
-    f.jar = active ? ja * r : 0.f;
-    f.jdr = active ? jd * r : 0.f;
-    f.cost = active ? r * r : 0.f;
-#pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {   // within each group of 8 lanes (all groups identical)
-        f.jaa += __shfl_xor_sync(0xffffffffu, f.jaa, o);
-        f.jad += __shfl_xor_sync(0xffffffffu, f.jad, o);
-        f.jdd += __shfl_xor_sync(0xffffffffu, f.jdd, o);
-        f.jar += __shfl_xor_sync(0xffffffffu, f.jar, o);
-        f.jdr += __shfl_xor_sync(0xffffffffu, f.jdr, o);
-        f.cost += __shfl_xor_sync(0xffffffffu, f.cost, o);
-    }
-    return f;
-}
-
-// y: magnitude of point (lane & 7) (ignored for (lane & 7) == 7).  Returns delta, warp-uniform.
-__device__ __forceinline__ float dirichlet_fit(float y, int lane, const DetectParams &p) {
-    const int li = lane & 7;
-    const bool active = li < 7;
-    const float xi = (float)((active ? li : 0) - 3);
-    float A = __shfl_sync(0xffffffffu, y, 3);
-    float d = 0.f;
-    float lambda = 0.f;                   // Gauss-Newton first; Marquardt damping only if a step fails
-    FitSums f = fit_eval(y, active, A, d, xi, p.fit_W, p.fit_WoverN, p.fit_invN);
-    for (int it = 0; it < 30; ++it) {
-        const float a11 = f.jaa * (1.f + lambda), a22 = f.jdd * (1.f + lambda), a12 = f.jad;
-        const float det = a11 * a22 - a12 * a12;
-        if (!(fabsf(det) > 0.f)) break;
-        const float idet = 1.0f / det;
-        const float dA = (a22 * f.jar - a12 * f.jdr) * idet;
-        const float dd = (a11 * f.jdr - a12 * f.jar) * idet;
-        const bool tiny = fabsf(dd) < 2e-6f && fabsf(dA) <= 2e-6f * fabsf(A);
-        const float An = A + dA, dn = d + dd;
-        const FitSums fn = fit_eval(y, active, An, dn, xi, p.fit_W, p.fit_WoverN, p.fit_invN);
-        if (fn.cost <= f.cost * 1.000001f) {
-            A = An;
-            d = dn;
-            f = fn;
-            lambda *= 0.1f;
-            if (tiny) break;
-        } else {
-            if (tiny) break;
-            lambda = lambda * 10.f + 1e-3f;
-            if (lambda > 1e8f) break;
+__device__ __forceinline__ float dirichlet_fit(float y, int lane, const DetectParams &p, lm::Rows &w) {
+    const int li = min(lane & 7, 6);
+    const double xi = (double)(li - 3);
+    const double piW = p.fit_piW, N = p.fit_N, W = p.fit_W;
+    // lanes 0..7 evaluate the first offset of a call, lanes 8..15 the second (slot 7 is a dummy)
+    auto weights = [&](double da, double db, double *ga, double *gb) {
+        if (lane < 16) {
+            const double g = lm::weight(xi - (lane < 8 ? da : db), piW, N, W);
+            (lane < 8 ? ga : gb)[lane & 7] = g;
         }
-    }
-    return d;
+        __syncwarp();
+    };
+    if (lane < 8) w.y[lane] = (double)y;
+    __syncwarp();
+    const lm::Result res = lm::fit(WarpExec{lane}, weights, w, w.y[3], 0.0);
+    __syncwarp();                                  // the rows may be overwritten by the next fit
+    return (float)res.offset;
 }
 
 // ------------------------------------------------------------------ rawconv
@@ -604,6 +561,8 @@ detect_kernel(const __grid_constant__ DetectParams p) {
     float2 *zrho = reinterpret_cast<float2 *>(smem + off);           // W_32^{b0 n1}: row phasors of the zoom pre-shift
     off += 256;
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + off);       // 2 barriers
+    off += 64;
+    lm::Rows &fitrows = *reinterpret_cast<lm::Rows *>(smem + off);   // row workspace of the Dirichlet fit
 
     // Launch-invariant switches are re-read from the kernel parameters (constant bank, uniform
     // datapath) wherever they are used: held in registers they get spilled, and a spill reload
@@ -640,7 +599,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
         FitSlot &fs = fitslot[q];
         if (fs.carrier) {
             const float y = (lane & 7) < 7 ? fs.mags[lane & 7] : 0.f;
-            const float d = dirichlet_fit(y, lane, p);
+            const float d = dirichlet_fit(y, lane, p, fitrows);
             // mix phasors of the 32 pass-1 rows: rho[n1] = exp(-2 pi i (k+d) n1 / 32)
             const int e = (fs.kpeak * lane) & 31;
             const float turns = -((float)e * 0.03125f) - d * ((float)lane * 0.03125f);
@@ -1502,7 +1461,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
             // ---- pass 3 of FFT#2, then per template: x conj(T)/N and the inverse transform
             for (int tpl = 0; tpl < n_tpl; ++tpl) {
                 const float2 *tsp = p.tpl_spec + (size_t)tpl * N;
-                corr_stage(q, tpl, [&](int it, int, int k3) { return __ldg(&tsp[(size_t)(it * R3 + k3) * T + tid]); },
+                corr_stage(q, tpl, [&](int it, int, int k3) { return ldg_stream(&tsp[(size_t)(it * R3 + k3) * T + tid]); },
                            [&](int it, int g, uint32_t ab, float2 (&x)[R3]) {
                 if (tpl == 0) {
                     if constexpr (TW3) {    // W_M^{n3 k2} on the loads (pass 2 stored its outputs untwiddled)

@@ -40,7 +40,7 @@ struct Cfg2x {
     static constexpr size_t BUF_BYTES = (size_t)(F / 16) * 136;
     static constexpr size_t smem_bytes() {
         return BUF_BYTES + (size_t)(2 * NB) + (size_t)M * 8 + 2 * 320 + 2 * 32 + 2 * 32 + 256
-               + 2 * 128 * 8 + 512 + 256 + 64;
+               + 2 * 128 * 8 + 512 + 256 + 64 + sizeof(lm::Rows);
     }
     using Half = Cfg<14, 512, false>;                // geometry of one half (pass-3 item order)
 };
@@ -81,6 +81,8 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
     float2 *zrho = reinterpret_cast<float2 *>(smem + off);               // W_32^{b0 n1}: row phasors of the zoom pre-shift
     off += 256;
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + off);
+    off += 64;
+    lm::Rows &fitrows = *reinterpret_cast<lm::Rows *>(smem + off);       // row workspace of the Dirichlet fit
 
 #define use_raw (p.raw != nullptr)
 #define need_std_k (p.k_std != 0.f)
@@ -105,7 +107,7 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
         FitSlot &fs = fitslot[q];
         if (fs.carrier) {
             const float y = (lane & 7) < 7 ? fs.mags[lane & 7] : 0.f;
-            const float d = dirichlet_fit(y, lane, p);
+            const float d = dirichlet_fit(y, lane, p, fitrows);
             const int e = (fs.kpeak * lane) & 31;
             const float turns = -((float)e * 0.03125f) - d * ((float)lane * 0.03125f);
             fs.rho[lane] = cispi(2.f * turns);

@@ -1,0 +1,459 @@
+// dirichlet_lm.cuh -- sub-bin carrier offset: Levenberg-Marquardt fit of a Dirichlet kernel, float64.
+//
+// The reference obtains the offset with scipy.optimize.curve_fit(_fit_model, xdata, ydata, p0) on the
+// 7 spectrum magnitudes around the carrier peak (thrifty/carrier_sync.py:150-196, model :121-132).
+// curve_fit (method 'lm') is MINPACK's lmdif: forward-difference Jacobian (step sqrt(eps_machine) |x|),
+// QR with column pivoting, Levenberg-Marquardt parameter by More's lmpar, trust region `delta`, column
+// scaling diag = max column norm seen so far (mode 1), factor = 100, ftol = xtol = 1.49012e-8, gtol = 0,
+// maxfev = 200 (n + 1).  When the Dirichlet main lobe is much wider than the 7 fitted bins the cost surface
+// is nearly flat along the offset and WHERE the iteration stops decides the 4th digit of the answer, so
+// the device fit follows the same algorithm, in float64, with the same stopping tests; it then stops at the
+// same iterate as the reference.  This file restates the published MINPACK algorithm (lmdif / fdjac2 /
+// qrfac / lmpar / qrsolv, Argonne National Laboratory, 1980) for n = 2 parameters and m = 7 points.
+//
+// The code is plain scalar C++ (host + device) so that tests/native/lm_harness.cpp can run the very same
+// source on the CPU against scipy (tests/test_lm_fit.py: identical iterates, identical nfev); only the evaluation
+// of the model weights is supplied by the caller (on the device: one lane per point, see detect_kernel.cuh).
+#pragma once
+
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define THR_HD __host__ __device__ __forceinline__
+#else
+#define THR_HD inline
+#endif
+// Loops around divisions / square roots / the control flow of the iteration stay rolled on the device: a float64
+// division expands to ~25 instructions, and the code runs on one warp whose instruction footprint should stay small.
+// Loops over the two parameters are unrolled and the column permutation of the pivoted QR is a single flag, so that
+// every small array is indexed statically and stays out of local memory.
+#if defined(__CUDA_ARCH__)
+#define THR_ROLLED _Pragma("unroll 1")
+#define THR_UNROLLED _Pragma("unroll")
+#else
+#define THR_ROLLED
+#define THR_UNROLLED
+#endif
+
+namespace thr {
+namespace lm {
+
+constexpr int M = 7;                       // points (bins k-3 .. k+3)
+constexpr int NP = 2;                      // parameters (amplitude, offset)
+constexpr double EPSMCH = 2.220446049250313e-16;
+constexpr double DWARF = 2.2250738585072014e-308;
+constexpr double TOL = 1.49012e-8;         // scipy.optimize.leastsq default ftol = xtol
+constexpr double FACTOR = 100.0;
+constexpr int MAXFEV = 200 * (NP + 1);
+
+// Weight of the reference's model at z = x - offset: |sin(pi W z / N) / sin(pi z / N) / W|, evaluated in the
+// reference's operation order (carrier_sync.py:129-131, :180-183); 0/0 -> 1.  A residual is amplitude * weight - y.
+THR_HD double weight(double z, double piW, double N, double W) {
+    const double s2 = sin((3.141592653589793 * z) / N);
+    double w = sin((piW * z) / N) / s2 / W;
+    if (w != w) w = 1.0;
+    return fabs(w);
+}
+
+THR_HD double enorm2(double a, double b) { return sqrt(a * a + b * b); }
+
+// ipvt of MINPACK for n = 2 is either (0, 1) or (1, 0): `swp` says which; pv(v, j, swp) = v[ipvt[j]]
+THR_HD double pv(const double (&v)[NP], int j, bool swp) { return ((j != 0) != swp) ? v[1] : v[0]; }
+THR_HD void pset(double (&v)[NP], int j, bool swp, double val) {
+    if ((j != 0) != swp) v[1] = val; else v[0] = val;
+}
+
+// qrsolv for n = 2: r = upper triangle R (r[i][j], i <= j) of the pivoted QR, overwritten below the diagonal
+// with the transposed strict upper triangle of S; returns x (solution of the damped system) and sdiag.
+THR_HD void qrsolv2(double (&r)[NP][NP], bool swp, const double (&diag)[NP], const double (&qtb)[NP],
+                    double (&x)[NP], double (&sdiag)[NP]) {
+    double wa[NP];
+    THR_UNROLLED
+    for (int j = 0; j < NP; ++j) {
+        THR_UNROLLED
+        for (int i = j; i < NP; ++i) r[i][j] = r[j][i];
+        x[j] = r[j][j];
+        wa[j] = qtb[j];
+    }
+    THR_UNROLLED
+    for (int j = 0; j < NP; ++j) {
+        const double dl = pv(diag, j, swp);
+        if (dl != 0.0) {
+            THR_UNROLLED
+            for (int k = j; k < NP; ++k) sdiag[k] = 0.0;
+            sdiag[j] = dl;
+            double qtbpj = 0.0;
+            THR_UNROLLED
+            for (int k = j; k < NP; ++k) {
+                if (sdiag[k] == 0.0) continue;
+                double cs, sn;
+                if (fabs(r[k][k]) < fabs(sdiag[k])) {
+                    const double cotan = r[k][k] / sdiag[k];
+                    sn = 0.5 / sqrt(0.25 + 0.25 * (cotan * cotan));
+                    cs = sn * cotan;
+                } else {
+                    const double tn = sdiag[k] / r[k][k];
+                    cs = 0.5 / sqrt(0.25 + 0.25 * (tn * tn));
+                    sn = cs * tn;
+                }
+                r[k][k] = cs * r[k][k] + sn * sdiag[k];
+                const double temp = cs * wa[k] + sn * qtbpj;
+                qtbpj = -sn * wa[k] + cs * qtbpj;
+                wa[k] = temp;
+                THR_UNROLLED
+                for (int i = k + 1; i < NP; ++i) {
+                    const double t2 = cs * r[i][k] + sn * sdiag[i];
+                    sdiag[i] = -sn * r[i][k] + cs * sdiag[i];
+                    r[i][k] = t2;
+                }
+            }
+        }
+        sdiag[j] = r[j][j];
+        r[j][j] = x[j];
+    }
+    // triangular solve; a zero on the diagonal of S truncates the system (least-squares solution)
+    const bool s0 = sdiag[0] == 0.0, s1 = sdiag[1] == 0.0;
+    if (s0) {
+        wa[0] = 0.0;
+        wa[1] = 0.0;
+    } else if (s1) {
+        wa[1] = 0.0;
+        wa[0] = wa[0] / sdiag[0];
+    } else {
+        wa[1] = wa[1] / sdiag[1];
+        wa[0] = (wa[0] - r[1][0] * wa[1]) / sdiag[0];
+    }
+    THR_UNROLLED
+    for (int j = 0; j < NP; ++j) pset(x, j, swp, wa[j]);
+}
+
+// lmpar for n = 2: Levenberg-Marquardt parameter `par` such that ||diag x|| is within 10 % of delta.
+THR_HD void lmpar2(double (&r)[NP][NP], bool swp, const double (&diag)[NP], const double (&qtb)[NP], double delta,
+                   double &par, double (&x)[NP], double (&sdiag)[NP]) {
+    double wa1[NP], wa2[NP];
+    // Gauss-Newton direction (rank-deficient R: least-squares solution)
+    const bool z0 = r[0][0] == 0.0, z1 = r[1][1] == 0.0;
+    const bool full_rank = !z0 && !z1;
+    if (z0) {
+        wa1[0] = 0.0;
+        wa1[1] = 0.0;
+    } else if (z1) {
+        wa1[1] = 0.0;
+        wa1[0] = qtb[0] / r[0][0];
+    } else {
+        wa1[1] = qtb[1] / r[1][1];
+        wa1[0] = (qtb[0] - r[0][1] * wa1[1]) / r[0][0];
+    }
+    THR_UNROLLED
+    for (int j = 0; j < NP; ++j) pset(x, j, swp, wa1[j]);
+    int iter = 0;
+    THR_UNROLLED
+    for (int j = 0; j < NP; ++j) wa2[j] = diag[j] * x[j];
+    double dxnorm = enorm2(wa2[0], wa2[1]);
+    double fp = dxnorm - delta;
+    if (fp <= 0.1 * delta) {
+        par = 0.0;
+        return;
+    }
+    double parl = 0.0;
+    if (full_rank) {
+        THR_UNROLLED
+        for (int j = 0; j < NP; ++j) wa1[j] = pv(diag, j, swp) * (pv(wa2, j, swp) / dxnorm);
+        wa1[0] = wa1[0] / r[0][0];
+        wa1[1] = (wa1[1] - r[0][1] * wa1[0]) / r[1][1];
+        const double temp = enorm2(wa1[0], wa1[1]);
+        parl = ((fp / delta) / temp) / temp;
+    }
+    wa1[0] = (r[0][0] * qtb[0]) / pv(diag, 0, swp);
+    wa1[1] = (r[0][1] * qtb[0] + r[1][1] * qtb[1]) / pv(diag, 1, swp);
+    const double gnorm = enorm2(wa1[0], wa1[1]);
+    double paru = gnorm / delta;
+    if (paru == 0.0) paru = DWARF / fmin(delta, 0.1);
+    par = fmax(par, parl);
+    par = fmin(par, paru);
+    if (par == 0.0) par = gnorm / dxnorm;
+    THR_ROLLED
+    for (;;) {
+        ++iter;
+        if (par == 0.0) par = fmax(DWARF, 0.001 * paru);
+        double temp = sqrt(par);
+        THR_UNROLLED
+        for (int j = 0; j < NP; ++j) wa1[j] = temp * diag[j];
+        qrsolv2(r, swp, wa1, qtb, x, sdiag);
+        THR_UNROLLED
+        for (int j = 0; j < NP; ++j) wa2[j] = diag[j] * x[j];
+        dxnorm = enorm2(wa2[0], wa2[1]);
+        temp = fp;
+        fp = dxnorm - delta;
+        if (fabs(fp) <= 0.1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || iter == 10) break;
+        THR_UNROLLED
+        for (int j = 0; j < NP; ++j) wa1[j] = pv(diag, j, swp) * (pv(wa2, j, swp) / dxnorm);
+        wa1[0] = wa1[0] / sdiag[0];
+        wa1[1] = (wa1[1] - r[1][0] * wa1[0]) / sdiag[1];
+        temp = enorm2(wa1[0], wa1[1]);
+        const double parc = ((fp / delta) / temp) / temp;
+        if (fp > 0.0) parl = fmax(parl, par);
+        if (fp < 0.0) paru = fmin(paru, par);
+        par = fmax(parl, par + parc);
+    }
+}
+
+struct Result {
+    double amplitude, offset;
+    int nfev, info;
+};
+
+// Row data of the 7-point problem.  On the host one thread owns all of it; on the device it lives in shared memory and
+// the lanes of one warp split the element-wise work (lane r writes row r, then the warp synchronises) while every lane
+// carries the scalar state of the iteration redundantly and forms the sums over rows itself, in row order, from the
+// shared rows.  Slot 7 of each array is a dummy (the lane next to the last row evaluates a duplicate of row 6).
+struct Rows {
+    double y[8];                 // the magnitudes being fitted
+    double fvec[8], wa4[8];      // residuals at x / at the trial point (also scratch for Q^T fvec)
+    double a[NP][8];             // Jacobian columns, then Householder vectors
+    double gx[8], gh[8];         // model weights at x and at x + h e_offset
+    double gt[8], gth[8];        // the same at the trial point
+};
+
+// Execution policy of the host build: one thread, all rows.
+struct SerialExec {
+    template <class F>
+    THR_HD void each(int from, F &&f) const {
+        for (int r = from; r < M; ++r) f(r);
+    }
+    THR_HD void sync() const {}
+};
+
+// lmdif for m = 7, n = 2.  weights(da, db, ga, gb) must fill rows 0..6 of ga / gb with the model weights at the offsets
+// da / db and synchronise.  The amplitude enters the model linearly, so the forward-difference column of the amplitude
+// re-uses the weights at the current offset, and the offset column of the NEXT iterate (offset + h) is evaluated
+// together with the trial point it belongs to: one round of sines per trial step, with exactly the values lmdif /
+// fdjac2 would compute.  `ex.each(from, f)` runs f(r) for the rows r >= from (device: one lane per row),
+// `ex.sync()` orders the rows' writes before everybody's reads (device: __syncwarp()).
+template <class Exec, class Weights>
+THR_HD Result fit(Exec &&ex, Weights &&weights, Rows &w, double a0, double d0) {
+    double x[NP] = {a0, d0};
+    double diag[NP], qtf[NP], wa1[NP], wa2[NP], wa3[NP], rdiag[NP], acnorm[NP];
+    bool swp = false;                        // column permutation of the QR: (0, 1) or (1, 0)
+    Result res;
+    res.info = 0;
+    int nfev = 1;
+    const double eps = sqrt(EPSMCH);
+    auto step_of = [&](double v) {
+        const double h = eps * fabs(v);
+        return h == 0.0 ? eps : h;
+    };
+    weights(x[1], x[1] + step_of(x[1]), w.gx, w.gh);
+    ex.each(0, [&](int r) { w.fvec[r] = x[0] * w.gx[r] - w.y[r]; });
+    ex.sync();
+    double fnorm = 0.0;
+    for (int i = 0; i < M; ++i) fnorm += w.fvec[i] * w.fvec[i];
+    fnorm = sqrt(fnorm);
+    double par = 0.0, delta = 0.0, xnorm = 0.0;
+    int iter = 1;
+    THR_ROLLED
+    for (;;) {
+        // fdjac2: forward differences (x[j] + h is formed first, then (f(x + h e_j) - f(x)) / h)
+        {
+            const double h0 = step_of(x[0]), ah = x[0] + h0;
+            const double h1 = step_of(x[1]);
+            ex.each(0, [&](int r) {
+                w.a[0][r] = ((ah * w.gx[r] - w.y[r]) - w.fvec[r]) / h0;
+                w.a[1][r] = ((x[0] * w.gh[r] - w.y[r]) - w.fvec[r]) / h1;
+            });
+            ex.sync();
+        }
+        nfev += NP;
+        // qrfac with column pivoting
+        THR_UNROLLED
+        for (int j = 0; j < NP; ++j) {
+            double s2 = 0.0;
+            for (int i = 0; i < M; ++i) s2 += w.a[j][i] * w.a[j][i];
+            acnorm[j] = sqrt(s2);
+            rdiag[j] = acnorm[j];
+            wa3[j] = rdiag[j];
+        }
+        swp = rdiag[1] > rdiag[0];
+        if (swp) {                           // bring the column of largest norm into the pivot position
+            ex.sync();
+            ex.each(0, [&](int r) {
+                const double t = w.a[0][r];
+                w.a[0][r] = w.a[1][r];
+                w.a[1][r] = t;
+            });
+            ex.sync();
+            rdiag[1] = rdiag[0];
+            wa3[1] = wa3[0];
+        }
+        THR_UNROLLED
+        for (int j = 0; j < NP; ++j) {
+            double ajnorm = 0.0;
+            for (int i = j; i < M; ++i) ajnorm += w.a[j][i] * w.a[j][i];
+            ajnorm = sqrt(ajnorm);
+            if (ajnorm != 0.0) {
+                if (w.a[j][j] < 0.0) ajnorm = -ajnorm;
+                ex.sync();
+                ex.each(j, [&](int r) {
+                    double v = w.a[j][r] / ajnorm;
+                    if (r == j) v += 1.0;
+                    w.a[j][r] = v;
+                });
+                ex.sync();
+                THR_UNROLLED
+                for (int k = j + 1; k < NP; ++k) {
+                    double sum = 0.0;
+                    for (int i = j; i < M; ++i) sum += w.a[j][i] * w.a[k][i];
+                    const double temp = sum / w.a[j][j];
+                    ex.sync();
+                    ex.each(j, [&](int r) { w.a[k][r] -= temp * w.a[j][r]; });
+                    ex.sync();
+                    if (rdiag[k] != 0.0) {
+                        const double t = w.a[k][j] / rdiag[k];
+                        rdiag[k] *= sqrt(fmax(0.0, 1.0 - t * t));
+                        const double q = rdiag[k] / wa3[k];
+                        if (0.05 * (q * q) <= EPSMCH) {
+                            double s2 = 0.0;
+                            for (int i = j + 1; i < M; ++i) s2 += w.a[k][i] * w.a[k][i];
+                            rdiag[k] = sqrt(s2);
+                            wa3[k] = rdiag[k];
+                        }
+                    }
+                }
+            }
+            rdiag[j] = -ajnorm;
+        }
+        if (iter == 1) {
+            THR_UNROLLED
+            for (int j = 0; j < NP; ++j) {
+                diag[j] = acnorm[j];
+                if (acnorm[j] == 0.0) diag[j] = 1.0;
+            }
+            xnorm = enorm2(diag[0] * x[0], diag[1] * x[1]);
+            delta = FACTOR * xnorm;
+            if (delta == 0.0) delta = FACTOR;
+        }
+        // qtf = first n components of Q^T fvec; R = (rdiag on the diagonal, a[1][0] above it)
+        ex.each(0, [&](int r) { w.wa4[r] = w.fvec[r]; });
+        ex.sync();
+        THR_UNROLLED
+        for (int j = 0; j < NP; ++j) {
+            if (w.a[j][j] != 0.0) {
+                double sum = 0.0;
+                for (int i = j; i < M; ++i) sum += w.a[j][i] * w.wa4[i];
+                const double temp = -sum / w.a[j][j];
+                ex.sync();
+                ex.each(j, [&](int r) { w.wa4[r] += w.a[j][r] * temp; });
+                ex.sync();
+            }
+            qtf[j] = w.wa4[j];
+        }
+        double r[NP][NP];                    // r[i][j], i <= j: upper triangle of R
+        r[0][0] = rdiag[0];
+        r[0][1] = w.a[1][0];
+        r[1][1] = rdiag[1];
+        r[1][0] = 0.0;
+        // norm of the scaled gradient (gtol = 0: only the epsmch test further down can fire)
+        double gnorm = 0.0;
+        if (fnorm != 0.0) {
+            THR_UNROLLED
+            for (int j = 0; j < NP; ++j) {
+                const double acl = pv(acnorm, j, swp);
+                if (acl != 0.0) {
+                    double sum = 0.0;
+                    THR_UNROLLED
+                    for (int i = 0; i <= j; ++i) sum += r[i][j] * (qtf[i] / fnorm);
+                    gnorm = fmax(gnorm, fabs(sum / acl));
+                }
+            }
+        }
+        if (gnorm <= 0.0) {                  // gtol = 0
+            res.info = 4;
+            break;
+        }
+        THR_UNROLLED
+        for (int j = 0; j < NP; ++j) diag[j] = fmax(diag[j], acnorm[j]);
+        // inner loop: trial steps until one is accepted
+        double ratio;
+        THR_ROLLED
+        do {
+            double sdiag[NP];
+            lmpar2(r, swp, diag, qtf, delta, par, wa1, sdiag);
+            THR_UNROLLED
+            for (int j = 0; j < NP; ++j) {
+                wa1[j] = -wa1[j];
+                wa2[j] = x[j] + wa1[j];
+                wa3[j] = diag[j] * wa1[j];
+            }
+            const double pnorm = enorm2(wa3[0], wa3[1]);
+            if (iter == 1) delta = fmin(delta, pnorm);
+            ex.sync();
+            weights(wa2[1], wa2[1] + step_of(wa2[1]), w.gt, w.gth);
+            ++nfev;
+            ex.each(0, [&](int rr) { w.wa4[rr] = wa2[0] * w.gt[rr] - w.y[rr]; });
+            ex.sync();
+            double fnorm1 = 0.0;
+            for (int i = 0; i < M; ++i) fnorm1 += w.wa4[i] * w.wa4[i];
+            fnorm1 = sqrt(fnorm1);
+            double actred = -1.0;
+            if (0.1 * fnorm1 < fnorm) {
+                const double q = fnorm1 / fnorm;
+                actred = 1.0 - q * q;
+            }
+            // predicted reduction and directional derivative: R (P^T p)
+            double w3[NP] = {0.0, 0.0};
+            THR_UNROLLED
+            for (int j = 0; j < NP; ++j) {
+                const double temp = pv(wa1, j, swp);
+                THR_UNROLLED
+                for (int i = 0; i <= j; ++i) w3[i] += r[i][j] * temp;
+            }
+            const double temp1 = enorm2(w3[0], w3[1]) / fnorm;
+            const double temp2 = (sqrt(par) * pnorm) / fnorm;
+            const double prered = temp1 * temp1 + (temp2 * temp2) / 0.5;
+            const double dirder = -(temp1 * temp1 + temp2 * temp2);
+            ratio = 0.0;
+            if (prered != 0.0) ratio = actred / prered;
+            if (ratio <= 0.25) {
+                double temp = 0.5;
+                if (actred < 0.0) temp = 0.5 * dirder / (dirder + 0.5 * actred);
+                if (0.1 * fnorm1 >= fnorm || temp < 0.1) temp = 0.1;
+                delta = temp * fmin(delta, pnorm / 0.1);
+                par = par / temp;
+            } else if (par == 0.0 || ratio >= 0.75) {
+                delta = pnorm / 0.5;
+                par = 0.5 * par;
+            }
+            if (ratio >= 1e-4) {
+                x[0] = wa2[0];
+                x[1] = wa2[1];
+                ex.sync();
+                ex.each(0, [&](int rr) {
+                    w.fvec[rr] = w.wa4[rr];
+                    w.gx[rr] = w.gt[rr];
+                    w.gh[rr] = w.gth[rr];
+                });
+                ex.sync();
+                xnorm = enorm2(diag[0] * x[0], diag[1] * x[1]);
+                fnorm = fnorm1;
+                ++iter;
+            }
+            if (fabs(actred) <= TOL && prered <= TOL && 0.5 * ratio <= 1.0) res.info = 1;
+            if (delta <= TOL * xnorm) res.info = 2;
+            if (fabs(actred) <= TOL && prered <= TOL && 0.5 * ratio <= 1.0 && res.info == 2) res.info = 3;
+            if (res.info != 0) break;
+            if (nfev >= MAXFEV) res.info = 5;
+            if (fabs(actred) <= EPSMCH && prered <= EPSMCH && 0.5 * ratio <= 1.0) res.info = 6;
+            if (delta <= EPSMCH * xnorm) res.info = 7;
+            if (gnorm <= EPSMCH) res.info = 8;
+            if (res.info != 0) break;
+        } while (ratio < 1e-4);
+        if (res.info != 0) break;
+    }
+    res.amplitude = x[0];
+    res.offset = x[1];
+    res.nfev = nfev;
+    return res;
+}
+
+}  // namespace lm
+}  // namespace thr

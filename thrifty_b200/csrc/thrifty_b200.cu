@@ -455,10 +455,9 @@ int thr_create(const thr_config *cfg, thr_detector **out) {
     }
     p.new_len = N - H;
     {
-        const double W = cfg->carrier_len;
-        p.fit_W = (float)W;
-        p.fit_WoverN = (float)(W / N);
-        p.fit_invN = (float)(1.0 / N);
+        p.fit_W = (double)cfg->carrier_len;
+        p.fit_piW = 3.141592653589793 * (double)cfg->carrier_len;
+        p.fit_N = (double)N;
     }
     *out = d;
     return THR_OK;
