@@ -19,3 +19,18 @@ extern "C" int lm_fit_host(const double *y, double W, double N, double *amplitud
     *nfev = r.nfev;
     return r.info;
 }
+
+// the short cut (quick_fit): returns 1 if its result may stand in for lmdif's
+extern "C" int lm_quick_host(const double *y, double W, double N, double *amplitude, double *offset, double *slack) {
+    const double piW = 3.141592653589793 * W;
+    auto derivs = [&](double d, double *g, double *gd) {
+        for (int i = 0; i < thr::lm::M; ++i) thr::lm::kernel_deriv((double)(i - 3) - d, piW, N, W, g[i], gd[i]);
+    };
+    thr::lm::Rows rows;
+    for (int i = 0; i < thr::lm::M; ++i) rows.y[i] = y[i];
+    const thr::lm::Quick q = thr::lm::quick_fit(thr::lm::SerialExec(), derivs, rows, y[3], 0.0, N / W);
+    *amplitude = q.amplitude;
+    *offset = q.offset;
+    *slack = q.slack;
+    return q.ok ? 1 : 0;
+}

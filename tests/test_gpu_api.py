@@ -562,8 +562,8 @@ def test_template_and_history_geometries_with_edge_peaks(tpl_len, hist):
 def test_random_geometries_stress():
     """30 random detector configurations (block length 1024..16384, ragged template / history / carrier lengths,
     positive / negative / far / wide windows, constant + snr + stddev thresholds, weak and hard-clipped blocks)
-    against the oracle (tests/stress_parity.py; carrier-offset bar widened only where the Dirichlet fit is
-    ill-conditioned, see parity_util.carrier_offset_tolerance)."""
+    against the oracle (tests/stress_parity.py) at the one parity bar of parity_util: 1e-4 on every field of every
+    block, short-carrier geometries included."""
     import stress_parity
     assert stress_parity.main(30, 2024) == 0
 

@@ -92,3 +92,57 @@ def test_lm_degenerate_inputs(lm):
         a, d, nfev, info = lm(y, w, n)
         assert (nfev, info) == (ref[2]["nfev"], ref[4])
         assert d == ref[0][1] or (np.isnan(d) and np.isnan(ref[0][1]))
+
+
+@pytest.fixture(scope="module")
+def quick(lm):
+    lib = ctypes.CDLL(OUT)
+    lib.lm_quick_host.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.c_double] + [ctypes.c_void_p] * 3
+    lib.lm_quick_host.restype = ctypes.c_int
+
+    def run(y, carrier_len, block_len):
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        a, d, s = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+        ok = lib.lm_quick_host(y.ctypes.data, float(carrier_len), float(block_len), ctypes.byref(a), ctypes.byref(d),
+                               ctypes.byref(s))
+        return bool(ok), d.value, s.value
+    return run
+
+
+def test_short_cut_only_stands_in_where_it_agrees_with_minpack(quick):
+    """quick_fit (Gauss-Newton to the least-squares minimum) may replace lmdif only when it reports ok; wherever it does,
+    its offset must sit within a small fraction of the 1e-4 parity bar of what scipy returns."""
+    rng = np.random.default_rng(7)
+    n_ok, worst = 0, 0.0
+    for _ in range(4000):
+        n = int(rng.choice([1024, 4096, 16384, 32768]))
+        u = rng.random()
+        w = int(rng.integers(32, n // 2)) if u < 0.4 else int(n * (rng.uniform(0.02, 0.15) if u < 0.7 else rng.uniform(0.25, 0.35)))
+        amp = rng.uniform(1, 1000)
+        y = amp * np.abs(kern(XD - rng.uniform(-0.7, 0.7), w, n)) + rng.normal(0, amp * rng.choice([1e-6, 1e-4, 1e-3, 1e-2, 3e-2, 0.1]), 7)
+        y = np.abs(y).astype(np.float32).astype(np.float64)
+        ok, d, slack = quick(y, w, n)
+        if not ok:
+            continue
+        assert n / w <= 24.0 and slack < 3e-5
+        n_ok += 1
+        ref = leastsq(lambda p: p[0] * np.abs(kern(XD - p[1], w, n)) - y, (y[3], 0.0), full_output=1)
+        worst = max(worst, abs(d - ref[0][1]))
+    assert n_ok > 1500
+    assert worst < 2e-5, worst
+
+
+def test_short_cut_refuses_points_next_to_a_null(quick):
+    """A magnitude next to a null of the kernel gives |D| a kink with a local minimum on either side; the short cut must
+    either land where lmdif lands or hand the block over."""
+    n, w = 16384, 4914                       # nulls at +-3.334 bins: offsets near -+0.334 put a point on one
+    rng = np.random.default_rng(3)
+    for _ in range(1500):
+        d_true = rng.choice([-1, 1]) * rng.uniform(0.30, 0.37)
+        amp = rng.uniform(100, 1000)
+        y = amp * np.abs(kern(XD - d_true, w, n)) + rng.normal(0, amp * 0.01, 7)
+        y = np.abs(y).astype(np.float32).astype(np.float64)
+        ok, d, _ = quick(y, w, n)
+        if ok:
+            ref = leastsq(lambda p: p[0] * np.abs(kern(XD - p[1], w, n)) - y, (y[3], 0.0), full_output=1)
+            assert abs(d - ref[0][1]) < 2e-5, (y, d, ref[0])

@@ -41,6 +41,9 @@
 #ifndef THR_T128_CTAS
 #define THR_T128_CTAS 4         // resident CTAs per SM of that kernel (3: 80 x 256 = 128 x 128 + 128 x 32, no spills, but -4 %)
 #endif
+#ifndef THR_FIT_DEPTH_BIG
+#define THR_FIT_DEPTH_BIG 4     // blocks of look-ahead of stage A over stage B where shared memory allows a 5-slot ring (T >= 256)
+#endif
 #ifndef THR_TW3
 #define THR_TW3 1           // (+2 %) inter-pass twiddles W_M^{n3 k2} of FFT#2 / IFFT applied on the pass-3 side from a
                             // per-item register chain instead of the shared-memory table on the pass-2 side
@@ -123,6 +126,15 @@ struct Cfg {
     static_assert(!SERVICE || T * WORKER_REGS + 128 * 32 <= (65536 / MIN_CTAS / LAUNCH_THREADS / 8 * 8) * LAUNCH_THREADS,
                   "setmaxnreg targets exceed the CTA's register pool (the kernel would dead-lock)");
     static constexpr int MAX_TPL = 32;               // templates per detector (tail mailbox size)
+    // Stage A (FFT#1, carrier decision) runs FIT_DEPTH blocks ahead of stage B (mix, FFT#2, correlation): the float64
+    // Levenberg-Marquardt fit between them (dirichlet_lm.cuh, ~6 K dependent instructions) takes about two block
+    // periods on one warp, so the four warps of the service warpgroup take the blocks in turn: warp w fits the blocks
+    // i = w (mod 4) and, after each fit, writes the records of block i - 2 (whose stage B finished a period earlier).
+    // Stage B re-fetches its raw tile (L2-resident) instead of keeping it since stage A.
+    static constexpr int FIT_DEPTH = (SERVICE && !FASTDET_) ? (THR_FIT_DEPTH_BIG != 0 && T >= 256 ? THR_FIT_DEPTH_BIG : 3) : 1;
+    static constexpr int NSLOT = FIT_DEPTH + 1;      // FitSlot ring
+    static constexpr int NFITW = (SERVICE && !FASTDET_) ? 4 : 1;   // warps running fits
+    static_assert(NFITW == 1 || FIT_DEPTH <= NFITW, "a fit warp takes every NFITW-th block");
     // Passes 2 and 3 both work inside one k1 slab (M consecutive elements).  When every warp owns the
     // same slabs in both passes the hand-over 2 -> 3 (and 3' -> 2') only needs __syncwarp(): the warps
     // of a CTA then run the whole stretch  pass 2 -> 3 -> x conj(T) -> 3' -> 2'  without a CTA barrier
@@ -143,9 +155,9 @@ struct Cfg {
     // pruned ("zoom") FFT#1, pass 3: with T == 512 and R2 == 32 a warp finds the 8 bins of its own slabs
     static constexpr bool ZOOM_WARPLOCAL = WL23 && (T_ == 512 && R2 == 32 && R3 == 16);
     static constexpr bool ZOOM_OK = (R2 >= 8 && R2 % 4 == 0);      // bins < 128 <=> k2 < 4, k3 == 0
-    static constexpr size_t smem_bytes() {           // must cover the carve-up in detect_kernel
+    static constexpr size_t smem_bytes(bool multi) { // must cover the carve-up in detect_kernel
         return BUF_BYTES + 2 * (size_t)(2 * N) + (size_t)M * 8
-               + 2 * 320 + 2 * 32 + 2 * MAX_TPL * 32 + 256 + 512 + 256 + 64 + sizeof(lm::Rows);
+               + NSLOT * 320 + 2 * 32 + 2 * (multi ? MAX_TPL : 1) * 32 + 256 + 512 + 256 + 64 + NFITW * sizeof(lm::Rows);
     }
 };
 
@@ -180,7 +192,11 @@ __device__ __forceinline__ float2 cispi(float x) {
 // float64 fit needs for its register spills.
 __device__ __forceinline__ float2 ldg_stream(const float2 *ptr) {
     float2 v;
+#ifdef THR_EXP_LDG
+    v = __ldg(ptr);
+#else
     asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(ptr));
+#endif
     return v;
 }
 __host__ __device__ constexpr int brev(int v, int bits) {
@@ -407,6 +423,17 @@ __device__ __forceinline__ float dirichlet_fit(float y, int lane, const DetectPa
     };
     if (lane < 8) w.y[lane] = (double)y;
     __syncwarp();
+#ifndef THR_EXP_NOQUICK
+    // short cut (dirichlet_lm.cuh): Gauss-Newton to the least-squares minimum, accepted where lmdif provably stops
+    // within 3e-5 bins of it (every block of a well-conditioned geometry such as the example configuration)
+    auto derivs = [&](double d, double *g, double *gd) {
+        if (lane < 8) lm::kernel_deriv(xi - d, piW, N, W, g[lane], gd[lane]);
+        __syncwarp();
+    };
+    const lm::Quick quick = lm::quick_fit(WarpExec{lane}, derivs, w, w.y[3], 0.0, N / W);
+    if (quick.ok) return (float)quick.offset;
+    __syncwarp();
+#endif
     const lm::Result res = lm::fit(WarpExec{lane}, weights, w, w.y[3], 0.0);
     __syncwarp();                                  // the rows may be overwritten by the next fit
     return (float)res.offset;
@@ -429,7 +456,11 @@ __device__ __forceinline__ float2 rawconv(uint32_t w16) {
 // synchronise among themselves on barrier BAR_MAIN; requests to / completions from the
 // service warp use arrive/sync pairs on per-parity barrier ids, so neither side can run two
 // generations ahead on the same id.
-enum : int { BAR_FITREQ = 1, BAR_FITDONE = 3, BAR_TAILREQ = 5, BAR_MAIN = 7 };
+// Every id that a service warp waits on belongs to that warp alone: two warps waiting on one id at different
+// generations could steal each other's generation.  ids: BAR_MAIN; BAR_TAILREQ / BAR_FITREQ / BAR_FITDONE + w with
+// w = service warp (detect flow: block % 4 for the fit, (block + 2) % 4 for the records) or block & 1 (single
+// service warp: FASTDET flow, detect2x_kernel).
+enum : int { BAR_MAIN = 1, BAR_TAILREQ = 2, BAR_FITREQ = 6, BAR_FITDONE = 10 };
 __device__ __forceinline__ void bar_sync(int id, int count) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
@@ -548,12 +579,13 @@ detect_kernel(const __grid_constant__ DetectParams p) {
     off += 2 * (size_t)RAW_BYTES;
     float2 *tw2 = reinterpret_cast<float2 *>(smem + off);
     off += (size_t)M * 8;
-    FitSlot *fitslot = reinterpret_cast<FitSlot *>(smem + off);      // [2]
-    off += 2 * sizeof(FitSlot);
+    FitSlot *fitslot = reinterpret_cast<FitSlot *>(smem + off);      // [NSLOT]
+    off += C::NSLOT * sizeof(FitSlot);
     TailHdr *tailhdr = reinterpret_cast<TailHdr *>(smem + off);      // [2]
     off += 2 * sizeof(TailHdr);
-    TailSlot *tailslot = reinterpret_cast<TailSlot *>(smem + off);   // [2][MAX_TPL]
-    off += 2 * (size_t)C::MAX_TPL * sizeof(TailSlot);
+    TailSlot *tailslot = reinterpret_cast<TailSlot *>(smem + off);   // [2][TPL_SLOTS]
+    constexpr int TPL_SLOTS = MULTI ? C::MAX_TPL : 1;                // tail mailbox entries per block
+    off += 2 * (size_t)TPL_SLOTS * sizeof(TailSlot);
     uint32_t *red = reinterpret_cast<uint32_t *>(smem + off);        // 64 words reduction scratch
     off += 256;
     float *zpow = reinterpret_cast<float *>(smem + off);             // |X[b0 + k]|^2, k < 128 (zoom path)
@@ -562,7 +594,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
     off += 256;
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + off);       // 2 barriers
     off += 64;
-    lm::Rows &fitrows = *reinterpret_cast<lm::Rows *>(smem + off);   // row workspace of the Dirichlet fit
+    lm::Rows *fitrows = reinterpret_cast<lm::Rows *>(smem + off);    // [NFITW] row workspaces of the Dirichlet fit
 
     // Launch-invariant switches are re-read from the kernel parameters (constant bank, uniform
     // datapath) wherever they are used: held in registers they get spilled, and a spill reload
@@ -595,11 +627,15 @@ detect_kernel(const __grid_constant__ DetectParams p) {
     // serial work: Dirichlet fit + mix phasor table, scalar tail + record store.  Executed by
     // the service warp (SERVICE) or inline by warp 0 of the workers.
     // =====================================================================================
-    auto do_fit = [&](int q) {
+    auto do_fit = [&](int q, lm::Rows &rows) {
         FitSlot &fs = fitslot[q];
         if (fs.carrier) {
             const float y = (lane & 7) < 7 ? fs.mags[lane & 7] : 0.f;
-            const float d = dirichlet_fit(y, lane, p, fitrows);
+#ifdef THR_EXP_NOFIT            // timing experiment only (wrong offsets): what the float64 fit costs the workers
+            const float d = 0.f * y;
+#else
+            const float d = dirichlet_fit(y, lane, p, rows);
+#endif
             // mix phasors of the 32 pass-1 rows: rho[n1] = exp(-2 pi i (k+d) n1 / 32)
             const int e = (fs.kpeak * lane) & 31;
             const float turns = -((float)e * 0.03125f) - d * ((float)lane * 0.03125f);
@@ -631,7 +667,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 rec.signal_energy = h.sig_energy1;
             } else {
                 // scalar tail (soa_estimator.py:78-134,159-170); float32 except the SoA itself
-                const TailSlot &ts = tailslot[q * C::MAX_TPL + tpl];
+                const TailSlot &ts = tailslot[q * TPL_SLOTS + tpl];
                 const float pa = ts.pa, pc = ts.pc;
                 const float peak_mag_k = sqrtf(ts.peak_cp);
                 // mean |X'|^2 (soa_estimator.py:111) == sum |x|^2 == mean |X|^2 of FFT#1: the mix is a
@@ -694,7 +730,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 // corr_detector.cpp:88-101 parabolic interpolation on sqrt(power), clipped to +-0.5
                 const float ca = sqrtf(h.pad[0]), cb = sqrtf(h.peak_mag), cc = sqrtf(h.pad[1]);
                 const float coff = fminf(fmaxf((cc - ca) / (4.f * cb - 2.f * ca - 2.f * cc), -0.5f), 0.5f);
-                const TailSlot &ts = tailslot[q * C::MAX_TPL];
+                const TailSlot &ts = tailslot[q * TPL_SLOTS];
                 const float pa = ts.pa, pc = ts.pc;
                 // corr_detector.cpp:118-125: the peak power arrives as size_t (truncated), noise clamped at 0
                 float noise_pw = (h.sig_energy1 * p.tpl_energy[0] - truncf(ts.peak_cp)) / (float)N;
@@ -722,9 +758,10 @@ detect_kernel(const __grid_constant__ DetectParams p) {
 
     if constexpr (SERVICE) {
         if (tid >= T) {
-            // service warpgroup: hand registers to the workers; only its first warp works
+            // service warpgroup: hand registers to the workers (FASTDET: only its first warp works)
             asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
-            if (tid >= T + 32) return;
+            const int sw = (tid - T) >> 5;                    // warp of the service warpgroup
+            if (FASTDET && sw > 0) return;
             if constexpr (FASTDET) {
                 for (int i = 0; has_block(i); ++i) {
                     const int q = i & 1;
@@ -734,17 +771,21 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 }
                 return;
             }
-            if constexpr (!FASTDET) for (int i = -1; has_block(i < 0 ? 0 : i); ++i) {
-                if (has_block(i + 1)) {
-                    const int q = (i + 1) & 1;
-                    bar_sync(BAR_FITREQ + q, NTHREADS);               // A(i+1) posted
-                    do_fit(q);
-                    bar_arrive(BAR_FITDONE + q, NTHREADS);
-                }
-                if (i >= 0) {
-                    const int q = i & 1;
-                    bar_sync(BAR_TAILREQ + q, NTHREADS);              // B(i) (or the no-carrier shortcut) posted
-                    do_tail(i, q);
+            if constexpr (!FASTDET) {
+                // service warp sw: fit of block i = sw, sw + 4, ... (ring slot sw), then the records of block i - 2;
+                // FITDONE(sw) tells the workers both that fit(i) is there and that tail mailbox i & 1 is free again
+                for (int i = sw;; i += C::NFITW) {
+                    const bool has_fit = has_block(i), has_tail = i >= 2 && has_block(i - 2);
+                    if (!has_fit && !has_tail) break;
+                    if (has_fit) {
+                        bar_sync(BAR_FITREQ + sw, NTHREADS);              // A(i) posted
+                        do_fit(i % C::NSLOT, fitrows[sw]);
+                    }
+                    if (has_tail) {
+                        bar_sync(BAR_TAILREQ + sw, NTHREADS);             // B(i-2) (or the no-carrier shortcut) posted
+                        do_tail(i - 2, i & 1);
+                    }
+                    if (has_fit) bar_arrive(BAR_FITDONE + sw, NTHREADS);
                 }
             }
             return;
@@ -786,14 +827,18 @@ detect_kernel(const __grid_constant__ DetectParams p) {
         w4[i] = cispi(-2.0f * (float)((4 * j) & (N - 1)) / (float)N);
     }
 
-    auto issue_tile = [&](int i) {      // thread 0: TMA bulk copy of block i's raw tile into stage i&1
+    // thread 0: TMA bulk copy of block i's raw tile into raw stage `stage` (completion on mbar[stage]).
+    // FASTDET flow: stage = block parity, two blocks of read-ahead.  Detect flow: stage 0 feeds stage A (FFT#1),
+    // stage 1 feeds stage B (mix + FFT#2) FIT_DEPTH blocks later -- the tile is fetched twice (the second time from L2),
+    // so each stage is refilled with its next block as soon as pass 1 has consumed it.
+    auto issue_tile = [&](int i, int stage) {
         const int blk = (int)blockIdx.x + i * (int)gridDim.x;
-        mbar_expect_tx(&mbar[i & 1], RAW_BYTES);
-        tma_bulk_g2s(raw_s + (size_t)(i & 1) * RAW_BYTES, p.raw + (size_t)blk * (size_t)p.raw_stride, RAW_BYTES, &mbar[i & 1]);
+        mbar_expect_tx(&mbar[stage], RAW_BYTES);
+        tma_bulk_g2s(raw_s + (size_t)stage * RAW_BYTES, p.raw + (size_t)blk * (size_t)p.raw_stride, RAW_BYTES, &mbar[stage]);
     };
     if (use_raw && tid == 0) {
-        if (has_block(0)) issue_tile(0);
-        if (has_block(1)) issue_tile(1);
+        if (has_block(0)) issue_tile(0, 0);
+        if (FASTDET ? has_block(1) : has_block(0)) issue_tile(FASTDET ? 1 : 0, 1);
     }
     uint32_t par0 = 0, par1 = 0;    // phase parity of the two tile barriers
 
@@ -805,8 +850,10 @@ detect_kernel(const __grid_constant__ DetectParams p) {
     //   shift : multiply the samples by a phasor exp(-2 pi i s n/N) = rho[n1] * ph0[j] (the mix of stage B, or the
     //           integer pre-shift that moves an arbitrary narrow carrier window into the 128-bin zoom band)
     //   stageB: FFT#2 (full pass 2, raw tile released after pass 1); otherwise FFT#1 (pruned if `zoom`)
-    auto fwd_pass12 = [&](int i, bool shift, bool stageB, const float2 (&ph0)[I1], const float2 *rho, float &energy) {
-        const uint16_t *rawt = reinterpret_cast<const uint16_t *>(raw_s + (size_t)(i & 1) * RAW_BYTES);
+    //   stage / next: raw stage holding block i, and the block to fetch into it once pass 1 has consumed it
+    auto fwd_pass12 = [&](int i, int stage, int next, bool shift, bool stageB, const float2 (&ph0)[I1], const float2 *rho,
+                          float &energy) {
+        const uint16_t *rawt = reinterpret_cast<const uint16_t *>(raw_s + (size_t)stage * RAW_BYTES);
         const float2 *iqb = use_raw ? nullptr : p.iq + (size_t)((int)blockIdx.x + i * (int)gridDim.x) * N;
         // pass 1: samples (rawconv or complex64) [* mix phasor] -> radix-32 over n1 (stride M)
         //         -> twiddle W_N^{j k1} -> in-place store
@@ -864,9 +911,8 @@ detect_kernel(const __grid_constant__ DetectParams p) {
             }
         }
         bar_sync(BAR_MAIN, T);
-        // after the pass-1 barrier of the mix pass nobody reads this raw stage any more:
-        // prefetch the tile of block i+2 into it
-        if ((stageB || FASTDET) && use_raw && tid == 0 && has_block(i + 2)) issue_tile(i + 2);
+        // after the pass-1 barrier nobody reads this raw stage any more: fetch its next block
+        if (use_raw && tid == 0 && has_block(next)) issue_tile(next, stage);
         if constexpr (C::ZOOM_OK) {
             if (!stageB && zoom) {
                 // pruned pass 2: outputs k2 = 0..3 of the R2-point DFT over n2 = Q m + r (Q = R2/4):
@@ -1063,7 +1109,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
             }
             return key;
         };
-        TailSlot &ts = tailslot[q * C::MAX_TPL + tpl];
+        TailSlot &ts = tailslot[q * TPL_SLOTS + tpl];
         ArgOut rb;
         if (need_std_k) rb = main_argmax<T, true>(__float_as_uint(cbestv), c1sum, c2sum, red, tid, find_lag);
         else rb = main_argmax<T, false>(__float_as_uint(cbestv), 0.f, 0.f, red, tid, find_lag);
@@ -1110,7 +1156,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
 #pragma unroll
             for (int it = 0; it < I1; ++it) ph_unused[it] = make_float2(1.f, 0.f);
             float tenergy = 0.f;
-            fwd_pass12(i, false, false, ph_unused, nullptr, tenergy);
+            fwd_pass12(i, q, i + 2, false, false, ph_unused, nullptr, tenergy);
             // pass 3, power spectrum (fastcard.c:180), sum (cardet.c:12) and windowed maximum (cardet.c:15-19)
             float2 xk[I3][R3];
             float esum = 0.f, bestv = 0.f;
@@ -1214,13 +1260,14 @@ detect_kernel(const __grid_constant__ DetectParams p) {
         return;
     }
 
-    if constexpr (!FASTDET) for (int i = -1; has_block(i < 0 ? 0 : i); ++i) {
-        // ================================================================= A(i+1): FFT #1
-        if (has_block(i + 1)) {
-            const int ia = i + 1, q = ia & 1;
+    constexpr int FIT_DEPTH = C::FIT_DEPTH, NSLOT = C::NSLOT;
+    if constexpr (!FASTDET) for (int i = -FIT_DEPTH; has_block(i < 0 ? 0 : i); ++i) {
+        // ================================================================= A(i+FIT_DEPTH): FFT #1
+        if (has_block(i + FIT_DEPTH)) {
+            const int ia = i + FIT_DEPTH, q = ia % NSLOT;
             if (use_raw) {
-                mbar_wait(&mbar[q], q ? par1 : par0);
-                if (q) par1 ^= 1; else par0 ^= 1;
+                mbar_wait(&mbar[0], par0);
+                par0 ^= 1;
             }
             // zoom band not at bin 0: pre-shift the block by -b0 bins, folded into pass 1 like the mix of stage B
             const bool shiftA = zoom && (p.zoom_base != 0);
@@ -1234,10 +1281,10 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 }
             }
             float tenergy = 0.f;
-            if (shiftA) fwd_pass12(ia, true, false, phA, zrho, tenergy);     // two specialised copies: a run-time
-            else fwd_pass12(ia, false, false, phA, zrho, tenergy);           // flag inside pass 1 costs registers
+            if (shiftA) fwd_pass12(ia, 0, ia + 1, true, false, phA, zrho, tenergy);     // two specialised copies: a run-time
+            else fwd_pass12(ia, 0, ia + 1, false, false, phA, zrho, tenergy);           // flag inside pass 1 costs registers
 
-            FitSlot &fs = fitslot[q];
+            FitSlot &fs = fitslot[q];                   // ring slot of block ia
             // carrier decision in float32 (carrier_detect.py:99-115); returns the peak bin or -1
             auto decide = [&](const ArgOut &ra) -> int {
                 const float peak_pw = __uint_as_float(ra.vbits);
@@ -1407,19 +1454,30 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 }
             }
             if constexpr (SERVICE) {
-                bar_arrive(BAR_FITREQ + q, NTHREADS);  // service warp: fit(i+1) may start
+                // that fit warp: fit(ia) may start.  Once the pipeline is full the request is posted a few instructions
+                // later, behind the FITDONE wait of stage B below: with FIT_DEPTH == NFITW it goes to the warp whose
+                // previous fit that wait is for, so the warp can never be offered two requests at once.
+                if (i < 0) bar_arrive(BAR_FITREQ + ia % C::NFITW, NTHREADS);
             } else {
                 bar_sync(BAR_MAIN, T);
-                if (tid < 32) do_fit(q);               // visible to all after the next BAR_MAIN
+                if (tid < 32) do_fit(q, fitrows[0]);   // visible to all after the next BAR_MAIN
             }
         }
 
         // ================================================================= B(i): mix, FFT #2, correlation
         if (i >= 0) {
-            const int q = i & 1;
-            if constexpr (SERVICE) bar_sync(BAR_FITDONE + q, NTHREADS);   // fit(i) finished
-            else bar_sync(BAR_MAIN, T);
-            const FitSlot &fs = fitslot[q];
+            const int q = i & 1;                        // tail mailbox
+            if constexpr (SERVICE) {
+                bar_sync(BAR_FITDONE + i % C::NFITW, NTHREADS);           // fit(i) finished, tail(i-2) has read mailbox q
+                if (has_block(i + FIT_DEPTH)) bar_arrive(BAR_FITREQ + (i + FIT_DEPTH) % C::NFITW, NTHREADS);
+            } else {
+                bar_sync(BAR_MAIN, T);
+            }
+            if (use_raw) {                              // the re-fetched raw tile of block i (stage 1)
+                mbar_wait(&mbar[1], par1);
+                par1 ^= 1;
+            }
+            const FitSlot &fs = fitslot[i % NSLOT];
             const int kpeak = fs.kpeak;
             const bool carrier = fs.carrier != 0;
             if (tid == 0) {
@@ -1432,10 +1490,14 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 h.delta = fs.delta;
             }
             if (!carrier) {
-                // raw stage i&1 is free (A(i) finished long ago): prefetch block i+2 into it
-                if (use_raw && tid == 0 && has_block(i + 2)) issue_tile(i + 2);
+                // the mix does not run: stage 1 goes straight to the next block -- once every thread has seen this
+                // block's tile arrive (a thread that is still to wait on the tile barrier must not find it a phase ahead)
+                if (use_raw) {
+                    bar_sync(BAR_MAIN, T);
+                    if (tid == 0 && has_block(i + 1)) issue_tile(i + 1, 1);
+                }
                 if constexpr (SERVICE) {
-                    bar_arrive(BAR_TAILREQ + q, NTHREADS);
+                    bar_arrive(BAR_TAILREQ + (i + 2) % C::NFITW, NTHREADS);   // the warp that will fit block i + 2
                 } else {
                     bar_sync(BAR_MAIN, T);
                     if (tid < 32) do_tail(i, q);
@@ -1456,7 +1518,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 ph0[it] = cispi(2.f * turns);
             }
             float unused_energy = 0.f;
-            fwd_pass12(i, true, true, ph0, fs.rho, unused_energy);
+            fwd_pass12(i, 1, i + 1, true, true, ph0, fs.rho, unused_energy);
 
             // ---- pass 3 of FFT#2, then per template: x conj(T)/N and the inverse transform
             for (int tpl = 0; tpl < n_tpl; ++tpl) {
@@ -1497,7 +1559,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 // next template reuses the FFT buffer: all pass-1' loads are done (reduction barriers)
             }
             if constexpr (SERVICE) {
-                bar_arrive(BAR_TAILREQ + q, NTHREADS); // service warp: tail(i) may start
+                bar_arrive(BAR_TAILREQ + (i + 2) % C::NFITW, NTHREADS);   // that service warp: tail(i) may start
             } else {
                 bar_sync(BAR_MAIN, T);
                 if (tid < 32) do_tail(i, q);

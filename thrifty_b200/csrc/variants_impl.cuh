@@ -24,7 +24,7 @@ static Variant make_variant(const char *name) {
     v.p3_item = [](int tid, int it) { return C::p3_item(tid, it); };
     v.launch_threads = C::LAUNCH_THREADS;
     v.worker_regs = C::SERVICE ? C::WORKER_REGS : 0;
-    v.smem = C::smem_bytes();
+    v.smem = C::smem_bytes(THR_MULTI != 0);
     v.fn = (const void *)&detect_kernel<LOG2N, T, GMEM, (THR_MULTI != 0), (THR_FASTDET != 0)>;
     v.name = name;
     return v;
