@@ -197,6 +197,25 @@ int thr_detect_batch_device_c64(thr_detector *det, const float *d_iq, const int6
 int thr_detect_block_data(thr_detector *det, const uint8_t *raw, const float *iq, int64_t block_idx,
                           thr_record *out, float *shifted_fft, float *corr, float *fft_mag);
 
+/* ---- the stage boundary of the reference's plug-in seam ----
+ * The reference's other callers use the two halves of Detector.detect on their own
+ * (scripts/chip_rate_search.py:44-55,121-127, thrifty/template_extract.py:36-58):
+ *   thr_sync_batch  == thrifty/carrier_sync.py:52-76,82-118 DefaultSynchronizer(thresh, window, block_len, carrier_len)(block)
+ *                      -> (shifted_fft, CarrierSyncInfo): carrier decision, Dirichlet fit, mix, FFT#2.  One record per
+ *                      block with the carrier fields filled (flags & THR_FLAG_CARRIER_DETECTED; corr fields NaN / -1) and
+ *                      the shifted spectrum, N complex64 in natural bin order per block (all zeros where no carrier was
+ *                      found: the reference returns None there).  raw (uint8 I/Q) or iq (complex64), the other NULL.
+ *   thr_soa_batch   == thrifty/soa_estimator.py:42-92 SoaEstimator(template, thresh, block_len, history_len)(fft)
+ *                      -> (detected, CorrDetectionInfo, corr): x conj(FFT(template)), IFFT, windowed peak, noise,
+ *                      threshold, Gaussian interpolation.  fft: n_blocks * N complex64 shifted spectra (host); one record
+ *                      per block with the corr fields filled (flags & THR_FLAG_CORR_DETECTED, soa = (N-H) block_idx +
+ *                      sample + offset) and, if corr != NULL, the correlation c[0 .. N-L] as complex64 per block.
+ * Both run the same kernel code as thr_detect_batch, cut at the boundary; one-template detectors. */
+int thr_sync_batch(thr_detector *det, const uint8_t *raw, const float *iq, const int64_t *block_idx, int64_t n_blocks,
+                   thr_record *out, float *shifted_fft);
+int thr_soa_batch(thr_detector *det, const float *fft, const int64_t *block_idx, int64_t n_blocks, thr_record *out,
+                  float *corr);
+
 /* ---- stream / timing plumbing ---- */
 int thr_set_stream(thr_detector *det, void *cuda_stream);   /* NULL -> handle's own stream */
 int thr_synchronize(thr_detector *det);

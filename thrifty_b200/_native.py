@@ -60,7 +60,7 @@ EXPORTS = [
     "thr_detect_batch_device_c64", "thr_detect_block_data", "thr_set_stream", "thr_synchronize",
     "thr_timer_start", "thr_timer_stop", "thr_host_alloc", "thr_host_free", "thr_device_alloc",
     "thr_device_free", "thr_memcpy_h2d", "thr_memcpy_d2h", "thr_card_scan", "thr_detect_card",
-    "thr_detect_stream", "thr_detect_stream_device",
+    "thr_detect_stream", "thr_detect_stream_device", "thr_sync_batch", "thr_soa_batch",
 ]
 
 _lib = None
@@ -109,6 +109,10 @@ def load_library(path=None):
     lib.thr_detect_stream.restype = c_int
     lib.thr_detect_stream_device.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_void_p]
     lib.thr_detect_stream_device.restype = c_int
+    lib.thr_sync_batch.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]
+    lib.thr_sync_batch.restype = c_int
+    lib.thr_soa_batch.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]
+    lib.thr_soa_batch.restype = c_int
     lib.thr_set_stream.argtypes = [c_void_p, c_void_p]
     lib.thr_set_stream.restype = c_int
     lib.thr_synchronize.argtypes = [c_void_p]
@@ -276,6 +280,47 @@ class NativeDetector(object):
         self._check(self._lib.thr_detect_block_data(self._h, raw_ptr, iq_ptr, int(block_idx), out.ctypes.data,
                                                     sfft.ctypes.data, corr.ctypes.data, mag.ctypes.data))
         return out, sfft, corr, mag
+
+    # -- stage boundaries (carrier_sync.Synchronizer / soa_estimator.SoaEstimator)
+    def sync_batch(self, raw=None, iq=None, block_idx=None):
+        """Blocks -> (records [B] with the carrier fields, shifted spectra complex64 [B, N]) (thr_sync_batch)."""
+        n = self.block_len
+        raw_ptr = iq_ptr = None
+        if raw is not None:
+            raw = np.ascontiguousarray(raw, dtype=np.uint8)
+            assert raw.ndim == 2 and raw.shape[1] == 2 * n
+            nblk, raw_ptr = raw.shape[0], raw.ctypes.data
+        else:
+            iq = np.ascontiguousarray(iq, dtype=np.complex64)
+            assert iq.ndim == 2 and iq.shape[1] == n
+            nblk, iq_ptr = iq.shape[0], iq.ctypes.data
+        idx_ptr = None
+        if block_idx is not None:
+            idx = np.ascontiguousarray(block_idx, dtype=np.int64)
+            assert idx.shape == (nblk,)
+            idx_ptr = idx.ctypes.data
+        out = np.zeros(nblk, dtype=RECORD_DTYPE)
+        sfft = np.zeros((nblk, n), dtype=np.complex64)
+        self._check(self._lib.thr_sync_batch(self._h, raw_ptr, iq_ptr, idx_ptr, nblk, out.ctypes.data, sfft.ctypes.data))
+        return out, sfft
+
+    def soa_batch(self, fft, block_idx=None, want_corr=True):
+        """Shifted spectra complex64 [B, N] -> (records [B] with the corr fields, corr complex64 [B, N-L+1] or None)
+        (thr_soa_batch)."""
+        n = self.block_len
+        fft = np.ascontiguousarray(fft, dtype=np.complex64)
+        assert fft.ndim == 2 and fft.shape[1] == n
+        nblk = fft.shape[0]
+        idx_ptr = None
+        if block_idx is not None:
+            idx = np.ascontiguousarray(block_idx, dtype=np.int64)
+            assert idx.shape == (nblk,)
+            idx_ptr = idx.ctypes.data
+        out = np.zeros(nblk, dtype=RECORD_DTYPE)
+        corr = np.zeros((nblk, n - self.template_len + 1), dtype=np.complex64) if want_corr else None
+        self._check(self._lib.thr_soa_batch(self._h, fft.ctypes.data, idx_ptr, nblk, out.ctypes.data,
+                                            corr.ctypes.data if want_corr else None))
+        return out, corr
 
     def detect_stream(self, stream, first_block):
         """Contiguous uint8 I/Q stream that starts with the history of block `first_block`.

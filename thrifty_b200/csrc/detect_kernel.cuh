@@ -79,9 +79,12 @@ struct DetectParams {
                                // order (the integer roll of fastdet/corr_detector.cpp:13-17,179 folded into the
                                // template), or nullptr -> gather from tpl_nat
     const float2 *tpl_nat;     // [N] conj(FFT(template))/N in natural order
-    float2 *dbg_shifted_fft;   // optional [N], natural order (single-block debug launches)
-    float2 *dbg_corr;          // optional [corr_len]
-    float  *dbg_fft_mag;       // optional [N]
+    float2 *dbg_shifted_fft;   // optional: shifted spectrum X' (FFT#2), natural order, block b at + b * dbg_sfft_stride
+    float2 *dbg_corr;          // optional: correlation c[0 .. corr_len), block b at + b * dbg_corr_stride (template 0)
+    float  *dbg_fft_mag;       // optional [N] (single-block debug launches)
+    int64_t dbg_sfft_stride;   // elements between blocks (0: single-block debug launch; N: thr_sync_batch)
+    int64_t dbg_corr_stride;   // (0, or corr_len: thr_soa_batch)
+    const float2 *in_sfft;     // STAGES == 2 kernels: [n_blocks][N] shifted spectra, natural order (the input)
 };
 
 template <int LOG2N_, int T_, bool GMEM_, bool FASTDET_ = false>
@@ -550,9 +553,13 @@ __device__ __forceinline__ ArgOut main_argmax(uint32_t vbits, float s0, float s1
 // FASTDET = true: the semantics of the reference's native twin (fastcard + fastdet): decisions on powers,
 // integer-bin carrier shift folded into the template spectrum (so FFT #2 disappears: 2 transforms per
 // block), parabolic carrier offset, +-0.5 clip -- see the FASTDET section below.
-template <int LOG2N, int T, bool GMEM, bool MULTI, bool FASTDET = false>
+// STAGES: 0 = the whole chain; 1 = stop at the stage boundary of the reference's Synchronizer (carrier_sync.py:52-76:
+// carrier decision, fit, mix, FFT#2 -> shifted spectrum + carrier fields of the record; thr_sync_batch); 2 = start
+// there (soa_estimator.py:78-92: shifted spectrum in -> correlation, peak, threshold, interpolation; thr_soa_batch).
+template <int LOG2N, int T, bool GMEM, bool MULTI, bool FASTDET = false, int STAGES = 0>
 __global__ void __launch_bounds__(Cfg<LOG2N, T, GMEM, FASTDET>::LAUNCH_THREADS, Cfg<LOG2N, T, GMEM, FASTDET>::MIN_CTAS)
 detect_kernel(const __grid_constant__ DetectParams p) {
+    static_assert(STAGES == 0 || !FASTDET, "stage-boundary kernels follow the Python path's semantics");
     using C = Cfg<LOG2N, T, GMEM, FASTDET>;
     constexpr bool SERVICE = C::SERVICE;
     constexpr bool TW3 = (THR_TW3 != 0) && (!MULTI || THR_TW3_MULTI != 0) && !FASTDET && C::R3 == 16 && C::R2 > 1;
@@ -629,7 +636,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
     // =====================================================================================
     auto do_fit = [&](int q, lm::Rows &rows) {
         FitSlot &fs = fitslot[q];
-        if (fs.carrier) {
+        if (STAGES != 2 && fs.carrier) {
             const float y = (lane & 7) < 7 ? fs.mags[lane & 7] : 0.f;
 #ifdef THR_EXP_NOFIT            // timing experiment only (wrong offsets): what the float64 fit costs the workers
             const float d = 0.f * y;
@@ -656,14 +663,14 @@ detect_kernel(const __grid_constant__ DetectParams p) {
             rec.carrier_noise = h.noise_c;
             rec.template_idx = tpl;
             rec.reserved = 0.f;
-            if (!h.carrier) {
+            if (!h.carrier || STAGES == 1) {      // no correlation ran for this block
                 rec.soa = __longlong_as_double(0x7ff8000000000000ll);
-                rec.carrier_offset = 0.f;
+                rec.carrier_offset = h.carrier ? h.delta : 0.f;
                 rec.corr_sample = -1;
                 rec.corr_offset = __int_as_float(0x7fc00000);
                 rec.corr_energy = __int_as_float(0x7fc00000);
                 rec.corr_noise = __int_as_float(0x7fc00000);
-                rec.flags = 0u;
+                rec.flags = h.carrier ? THR_FLAG_CARRIER_DETECTED : 0u;
                 rec.signal_energy = h.sig_energy1;
             } else {
                 // scalar tail (soa_estimator.py:78-134,159-170); float32 except the SoA itself
@@ -695,7 +702,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 rec.corr_offset = offset;
                 rec.corr_energy = peak_mag_k;
                 rec.corr_noise = noise_k;
-                rec.flags = THR_FLAG_CARRIER_DETECTED | (detected ? THR_FLAG_CORR_DETECTED : 0u);
+                rec.flags = (STAGES == 2 ? 0u : THR_FLAG_CARRIER_DETECTED) | (detected ? THR_FLAG_CORR_DETECTED : 0u);
                 rec.signal_energy = sig_energy;
             }
             p.out[(size_t)blk * n_tpl + tpl] = rec;
@@ -994,6 +1001,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
         cur[3] = cmul(cur[1], cur[1]);
         cur3w4 = cur[3];
     };
+    int corr_blk = 0;                // block being correlated (offset of the optional per-block correlation output)
     auto corr_stage = [&](int q, int tpl, auto &&get_tv, auto &&get_x) {
 #pragma unroll
         for (int it = 0; it < I3; ++it) {
@@ -1092,9 +1100,10 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 }
             }
             if (p.dbg_corr && tpl == 0) {
+                float2 *corr_out = p.dbg_corr + (size_t)corr_blk * (size_t)p.dbg_corr_stride;
 #pragma unroll
                 for (int n1 = 0; n1 < 32; ++n1)
-                    if (n1 * M + j < p.corr_len) p.dbg_corr[n1 * M + j] = x[n1];
+                    if (n1 * M + j < p.corr_len) corr_out[n1 * M + j] = x[n1];
             }
         }
         // block arg-max: first maximum of |c|^2 over the window (soa_estimator.py:137-143)
@@ -1265,6 +1274,18 @@ detect_kernel(const __grid_constant__ DetectParams p) {
         // ================================================================= A(i+FIT_DEPTH): FFT #1
         if (has_block(i + FIT_DEPTH)) {
             const int ia = i + FIT_DEPTH, q = ia % NSLOT;
+            if constexpr (STAGES == 2) {
+                // no stage A: the caller supplies the shifted spectrum.  The mailbox protocol stays (slot says "go")
+                if (tid == 0) {
+                    FitSlot &fs0 = fitslot[q];
+                    fs0.kpeak = 0;
+                    fs0.carrier = 1;
+                    fs0.peak_mag = 0.f;
+                    fs0.noise_c = 0.f;
+                    fs0.sig_energy1 = 0.f;
+                    fs0.delta = 0.f;
+                }
+            } else {
             if (use_raw) {
                 mbar_wait(&mbar[0], par0);
                 par0 ^= 1;
@@ -1453,6 +1474,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                     }
                 }
             }
+            }   // STAGES != 2
             if constexpr (SERVICE) {
                 // that fit warp: fit(ia) may start.  Once the pipeline is full the request is posted a few instructions
                 // later, behind the FITDONE wait of stage B below: with FIT_DEPTH == NFITW it goes to the warp whose
@@ -1506,49 +1528,92 @@ detect_kernel(const __grid_constant__ DetectParams p) {
             }
             const float delta = fs.delta;
 
+            const int blk_b = (int)blockIdx.x + i * (int)gridDim.x;
+            corr_blk = blk_b;
+            float2 *sfft_out = p.dbg_shifted_fft ? p.dbg_shifted_fft + (size_t)blk_b * (size_t)p.dbg_sfft_stride : nullptr;
             // ---- mix + FFT #2 (carrier_sync.py:222-238)
             // x'[n] = x[n] exp(2 pi i shift (n/N - 1/2)), shift = -(k + delta); n = n1*M + j
-            float2 ph0[I1];
+            if constexpr (STAGES != 2) {
+                float2 ph0[I1];
 #pragma unroll
-            for (int it = 0; it < I1; ++it) {
-                const int j = tid + T * it;
-                const int e = (int)(((long long)kpeak * j) & (N - 1));
-                float turns = -((float)e / (float)N) - delta * ((float)j / (float)N);
-                turns += 0.5f * (float)(kpeak & 1) + 0.5f * delta;
-                ph0[it] = cispi(2.f * turns);
+                for (int it = 0; it < I1; ++it) {
+                    const int j = tid + T * it;
+                    const int e = (int)(((long long)kpeak * j) & (N - 1));
+                    float turns = -((float)e / (float)N) - delta * ((float)j / (float)N);
+                    turns += 0.5f * (float)(kpeak & 1) + 0.5f * delta;
+                    ph0[it] = cispi(2.f * turns);
+                }
+                float unused_energy = 0.f;
+                fwd_pass12(i, 1, i + 1, true, true, ph0, fs.rho, unused_energy);
             }
-            float unused_energy = 0.f;
-            fwd_pass12(i, 1, i + 1, true, true, ph0, fs.rho, unused_energy);
+            // pass 3 of FFT#2 for one item: this thread's R3 outputs X'[kb + S k3]
+            auto load_x = [&](int it, int g, uint32_t ab, float2 (&x)[R3]) {
+                if constexpr (TW3) {    // W_M^{n3 k2} on the loads (pass 2 stored its outputs untwiddled)
+                    float2 cur[4];
+                    tw3_seed(g, cur);
+                    x[0] = ld8(ab);
+#pragma unroll
+                    for (int n3 = 1; n3 < R3; ++n3) {
+                        if (n3 > 4) cur[(n3 - 1) & 3] = cmul(cur[(n3 - 1) & 3], cur3w4);
+                        x[brev(n3, LOG2R3)] = cmul(ld8(ab + (uint32_t)n3 * 8u), cur[(n3 - 1) & 3]);
+                    }
+                } else {
+#pragma unroll
+                    for (int n3 = 0; n3 < R3; ++n3) x[brev(n3, LOG2R3)] = ld8(ab + (uint32_t)n3 * 8u);
+                }
+                fft_dit<R3, false>(x);
+                if (sfft_out) {
+                    const int kb = (g >> LOG2R2) + 32 * (g & (R2 - 1));
+#pragma unroll
+                    for (int k3 = 0; k3 < R3; ++k3) sfft_out[kb + S * k3] = x[k3];
+                }
+            };
 
-            // ---- pass 3 of FFT#2, then per template: x conj(T)/N and the inverse transform
+            if constexpr (STAGES == 1) {
+                // the Synchronizer's output is the shifted spectrum: finish FFT#2 and stop
+#pragma unroll
+                for (int it = 0; it < I3; ++it) {
+                    const int g = C::p3_item(tid, it);
+                    float2 x[R3];
+                    load_x(it, g, a3_base(g), x);
+                }
+            } else if constexpr (STAGES == 2) {
+                // the SoaEstimator's input is a shifted spectrum: X' comes from global memory, and with it the signal
+                // energy mean |X'|^2 of the noise estimate (soa_estimator.py:108-120)
+                const float2 *src = p.in_sfft + (size_t)blk_b * N;
+                float esum = 0.f;
+                for (int tpl = 0; tpl < n_tpl; ++tpl) {
+                    const float2 *tsp = p.tpl_spec + (size_t)tpl * N;
+                    corr_stage(q, tpl, [&](int it, int, int k3) { return ldg_stream(&tsp[(size_t)(it * R3 + k3) * T + tid]); },
+                               [&](int, int g, uint32_t, float2 (&x)[R3]) {
+                        const int kb = (g >> LOG2R2) + 32 * (g & (R2 - 1));
+#pragma unroll
+                        for (int k3 = 0; k3 < R3; ++k3) {
+                            x[k3] = __ldg(&src[kb + S * k3]);
+                            if (tpl == 0) esum += x[k3].x * x[k3].x + x[k3].y * x[k3].y;
+                        }
+                    });
+                }
+                esum = warp_sum(esum);
+                if (lane == 0) red[16 + (tid >> 5)] = __float_as_uint(esum);
+                bar_sync(BAR_MAIN, T);
+                if (tid == 0) {
+                    float tot = 0.f;
+                    for (int w = 0; w < T / 32; ++w) tot += __uint_as_float(red[16 + w]);
+                    tailhdr[q].sig_energy1 = tot / (float)N;
+                }
+            } else {
+            // ---- per template: x conj(T)/N and the inverse transform
             for (int tpl = 0; tpl < n_tpl; ++tpl) {
                 const float2 *tsp = p.tpl_spec + (size_t)tpl * N;
                 corr_stage(q, tpl, [&](int it, int, int k3) { return ldg_stream(&tsp[(size_t)(it * R3 + k3) * T + tid]); },
                            [&](int it, int g, uint32_t ab, float2 (&x)[R3]) {
                 if (tpl == 0) {
-                    if constexpr (TW3) {    // W_M^{n3 k2} on the loads (pass 2 stored its outputs untwiddled)
-                        float2 cur[4];
-                        tw3_seed(g, cur);
-                        x[0] = ld8(ab);
-#pragma unroll
-                        for (int n3 = 1; n3 < R3; ++n3) {
-                            if (n3 > 4) cur[(n3 - 1) & 3] = cmul(cur[(n3 - 1) & 3], cur3w4);
-                            x[brev(n3, LOG2R3)] = cmul(ld8(ab + (uint32_t)n3 * 8u), cur[(n3 - 1) & 3]);
-                        }
-                    } else {
-#pragma unroll
-                        for (int n3 = 0; n3 < R3; ++n3) x[brev(n3, LOG2R3)] = ld8(ab + (uint32_t)n3 * 8u);
-                    }
-                    fft_dit<R3, false>(x);
+                    load_x(it, g, ab, x);
                     if (MULTI && p.n_templates > 1) {
 #pragma unroll
                         for (int k3 = 0; k3 < R3; ++k3)
                             p.xsave[(size_t)blockIdx.x * N + (size_t)(it * R3 + k3) * T + tid] = x[k3];
-                    }
-                    if (p.dbg_shifted_fft) {
-                        const int kb = (g >> LOG2R2) + 32 * (g & (R2 - 1));
-#pragma unroll
-                        for (int k3 = 0; k3 < R3; ++k3) p.dbg_shifted_fft[kb + S * k3] = x[k3];
                     }
                 } else {
 #pragma unroll
@@ -1557,6 +1622,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 }
                 });
                 // next template reuses the FFT buffer: all pass-1' loads are done (reduction barriers)
+            }
             }
             if constexpr (SERVICE) {
                 bar_arrive(BAR_TAILREQ + (i + 2) % C::NFITW, NTHREADS);   // that service warp: tail(i) may start

@@ -77,6 +77,12 @@ struct thr_detector {
     float2 *d_scratch = nullptr;
     float2 *d_xsave = nullptr;
     unsigned int *d_bad = nullptr;       // invalid base64 character counter (.card ingest)
+    // stage-boundary entry points (thr_sync_batch / thr_soa_batch): kernels and staging, set up on first use
+    Variant var_stage[3];                // [1] = stop after FFT#2, [2] = start at the shifted spectrum
+    int grid_stage[3] = {0, 0, 0};
+    float2 *d_stage_fft = nullptr;       // [stage_chunk][N] shifted spectra
+    float2 *d_stage_corr = nullptr;      // [stage_chunk][corr_len] correlations
+    int stage_chunk = 0;
     Slot slot[2];
     int c64_chunk = 0;
     int host_chunk = 0;                  // blocks per pipelined chunk of the host-buffer API
@@ -220,6 +226,8 @@ void thr_destroy(thr_detector *d) {
     cudaFree(d->d_scratch);
     cudaFree(d->d_xsave);
     cudaFree(d->d_bad);
+    cudaFree(d->d_stage_fft);
+    cudaFree(d->d_stage_corr);
     delete d;
 }
 
@@ -733,6 +741,132 @@ int thr_detect_block_data(thr_detector *d, const uint8_t *raw, const float *iq, 
     CUD(cudaGetLastError());
     return done(THR_OK);
 #undef CUD
+}
+
+// ---- stage boundaries of the reference's plug-in seam ---------------------------------------------------------
+// thrifty/carrier_sync.py:52-76 Synchronizer.sync: block -> (shifted_fft, CarrierSyncInfo);
+// thrifty/soa_estimator.py:78-92 SoaEstimator.soa_estimate: shifted_fft -> (detected, CorrDetectionInfo, corr).
+static int stage_setup(thr_detector *d, int st) {
+    const int N = d->cfg.block_len;
+    if (!d->grid_stage[st]) {
+        Variant v;
+        if (!thr::pick_variant_stage(N, st, &v))
+            return fail(d, THR_ERR_INVALID, "no stage-boundary kernel for block_len %d in this build", N);
+        CU(d, cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem));
+        int occ = 0;
+        CU(d, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v.fn, v.launch_threads, v.smem));
+        if (occ < 1) return fail(d, THR_ERR_CUDA, "kernel %s does not fit on an SM (smem %zu)", v.name, v.smem);
+        int grid = d->sm_count * occ;
+        if (v.gmem) {                                            // global-scratch kernel (block_len 32768)
+            if (!d->d_scratch) CU(d, cudaMalloc(&d->d_scratch, (size_t)d->grid * N * sizeof(float2)));
+            d->base.scratch = d->d_scratch;
+            if (grid > d->grid) grid = d->grid;                  // the scratch is sized for the main kernel's grid
+        }
+        if (const char *cap = std::getenv("THRIFTY_B200_MAX_GRID")) {
+            const int g = std::atoi(cap);
+            if (g >= 1 && g < grid) grid = g;
+        }
+        d->var_stage[st] = v;
+        d->grid_stage[st] = grid;
+    }
+    if (!d->stage_chunk) {
+        int64_t c = ((int64_t)64 << 20) / ((int64_t)N * 8);      // 64 MiB of spectra per chunk at most
+        if (c > d->cfg.max_batch) c = d->cfg.max_batch;
+        if (c < 1) c = 1;
+        d->stage_chunk = (int)c;
+    }
+    if (!d->d_stage_fft) CU(d, cudaMalloc(&d->d_stage_fft, (size_t)d->stage_chunk * N * sizeof(float2)));
+    return THR_OK;
+}
+
+static int launch_stage(thr_detector *d, int st, cudaStream_t stream, const uint8_t *d_raw, const float *d_iq,
+                        const int64_t *d_idx, int nb, thr_record *d_out, bool want_corr) {
+    const int N = d->cfg.block_len, corr_len = N - d->cfg.template_len + 1;
+    DetectParams p = d->base;
+    p.raw = d_raw;
+    p.raw_stride = 2 * (int64_t)N;
+    p.iq = reinterpret_cast<const float2 *>(d_iq);
+    p.block_idx = d_idx;
+    p.out = d_out;
+    p.n_blocks = nb;
+    p.n_templates = 1;                                           // the stage kernels are one-template kernels
+    if (d->has_generic) p.tpl_spec = d->d_tpl_generic;           // 2 x 16384 detectors: the generic kernel's template order
+    if (st == 1) {
+        p.dbg_shifted_fft = d->d_stage_fft;
+        p.dbg_sfft_stride = N;
+    } else {
+        p.in_sfft = d->d_stage_fft;
+        p.dbg_corr = want_corr ? d->d_stage_corr : nullptr;
+        p.dbg_corr_stride = corr_len;
+    }
+    const Variant &v = d->var_stage[st];
+    void *args[] = {&p};
+    cudaLaunchConfig_t lc;
+    std::memset(&lc, 0, sizeof lc);
+    lc.gridDim = dim3(nb < d->grid_stage[st] ? nb : d->grid_stage[st]);
+    lc.blockDim = dim3(v.launch_threads);
+    lc.dynamicSmemBytes = v.smem;
+    lc.stream = stream;
+    CU(d, cudaLaunchKernelExC(&lc, v.fn, args));
+    d->launches++;
+    return THR_OK;
+}
+
+int thr_sync_batch(thr_detector *d, const uint8_t *raw, const float *iq, const int64_t *block_idx, int64_t n_blocks,
+                   thr_record *out, float *shifted_fft) {
+    if (!d || (!raw && !iq) || !out || !shifted_fft || n_blocks < 0)
+        return d ? fail(d, THR_ERR_INVALID, "null/negative argument") : THR_ERR_INVALID;
+    if (d->cfg.flags & THR_CFG_FASTDET_SEMANTICS) return fail(d, THR_ERR_INVALID, "thr_sync_batch follows the Python path's semantics");
+    CU(d, cudaSetDevice(d->device));
+    if (int rc = stage_setup(d, 1)) return rc;
+    if (int rc = slots_reset(d)) return rc;
+    const int N = d->cfg.block_len;
+    Slot &s = d->slot[0];
+    if (iq && !s.d_iq) CU(d, cudaMalloc(&s.d_iq, (size_t)d->c64_chunk * N * 8));
+    const int64_t chunk = iq ? (d->stage_chunk < d->c64_chunk ? d->stage_chunk : d->c64_chunk) : d->stage_chunk;
+    for (int64_t b0 = 0; b0 < n_blocks; b0 += chunk) {
+        const int nb = (int)((n_blocks - b0) < chunk ? (n_blocks - b0) : chunk);
+        if (raw) CU(d, cudaMemcpyAsync(s.d_in, raw + (size_t)b0 * 2 * N, (size_t)nb * 2 * N, cudaMemcpyHostToDevice, s.stream));
+        else CU(d, cudaMemcpyAsync(s.d_iq, iq + (size_t)b0 * 2 * N, (size_t)nb * N * 8, cudaMemcpyHostToDevice, s.stream));
+        for (int i = 0; i < nb; ++i) s.h_idx[i] = block_idx ? block_idx[b0 + i] : b0 + i;
+        CU(d, cudaMemcpyAsync(s.d_idx, s.h_idx, (size_t)nb * sizeof(int64_t), cudaMemcpyHostToDevice, s.stream));
+        CU(d, cudaMemsetAsync(d->d_stage_fft, 0, (size_t)nb * N * sizeof(float2), s.stream));   // rows without a carrier: zeros
+        if (int rc = launch_stage(d, 1, s.stream, raw ? s.d_in : nullptr, raw ? nullptr : s.d_iq, s.d_idx, nb, s.d_out, false)) return rc;
+        CU(d, cudaMemcpyAsync(out + (size_t)b0, s.d_out, (size_t)nb * sizeof(thr_record), cudaMemcpyDeviceToHost, s.stream));
+        CU(d, cudaMemcpyAsync(shifted_fft + (size_t)b0 * 2 * N, d->d_stage_fft, (size_t)nb * N * sizeof(float2),
+                              cudaMemcpyDeviceToHost, s.stream));
+        CU(d, cudaStreamSynchronize(s.stream));
+    }
+    CU(d, cudaGetLastError());
+    return THR_OK;
+}
+
+int thr_soa_batch(thr_detector *d, const float *fft, const int64_t *block_idx, int64_t n_blocks, thr_record *out,
+                  float *corr) {
+    if (!d || !fft || !out || n_blocks < 0) return d ? fail(d, THR_ERR_INVALID, "null/negative argument") : THR_ERR_INVALID;
+    if (d->cfg.flags & THR_CFG_FASTDET_SEMANTICS) return fail(d, THR_ERR_INVALID, "thr_soa_batch follows the Python path's semantics");
+    if (d->cfg.n_templates != 1) return fail(d, THR_ERR_INVALID, "thr_soa_batch takes a one-template detector");
+    CU(d, cudaSetDevice(d->device));
+    if (int rc = stage_setup(d, 2)) return rc;
+    if (int rc = slots_reset(d)) return rc;
+    const int N = d->cfg.block_len, corr_len = N - d->cfg.template_len + 1;
+    if (corr && !d->d_stage_corr) CU(d, cudaMalloc(&d->d_stage_corr, (size_t)d->stage_chunk * corr_len * sizeof(float2)));
+    Slot &s = d->slot[0];
+    const int64_t chunk = d->stage_chunk;
+    for (int64_t b0 = 0; b0 < n_blocks; b0 += chunk) {
+        const int nb = (int)((n_blocks - b0) < chunk ? (n_blocks - b0) : chunk);
+        CU(d, cudaMemcpyAsync(d->d_stage_fft, fft + (size_t)b0 * 2 * N, (size_t)nb * N * sizeof(float2), cudaMemcpyHostToDevice, s.stream));
+        for (int i = 0; i < nb; ++i) s.h_idx[i] = block_idx ? block_idx[b0 + i] : b0 + i;
+        CU(d, cudaMemcpyAsync(s.d_idx, s.h_idx, (size_t)nb * sizeof(int64_t), cudaMemcpyHostToDevice, s.stream));
+        if (int rc = launch_stage(d, 2, s.stream, nullptr, nullptr, s.d_idx, nb, s.d_out, corr != nullptr)) return rc;
+        CU(d, cudaMemcpyAsync(out + (size_t)b0, s.d_out, (size_t)nb * sizeof(thr_record), cudaMemcpyDeviceToHost, s.stream));
+        if (corr)
+            CU(d, cudaMemcpyAsync(corr + (size_t)b0 * 2 * corr_len, d->d_stage_corr, (size_t)nb * corr_len * sizeof(float2),
+                                  cudaMemcpyDeviceToHost, s.stream));
+        CU(d, cudaStreamSynchronize(s.stream));
+    }
+    CU(d, cudaGetLastError());
+    return THR_OK;
 }
 
 // ---- .card text ingest ------------------------------------------------------------------

@@ -8,6 +8,9 @@
 #ifndef THR_FASTDET
 #define THR_FASTDET 0
 #endif
+#ifndef THR_STAGES
+#define THR_STAGES 0
+#endif
 
 namespace thr {
 
@@ -25,12 +28,18 @@ static Variant make_variant(const char *name) {
     v.launch_threads = C::LAUNCH_THREADS;
     v.worker_regs = C::SERVICE ? C::WORKER_REGS : 0;
     v.smem = C::smem_bytes(THR_MULTI != 0);
-    v.fn = (const void *)&detect_kernel<LOG2N, T, GMEM, (THR_MULTI != 0), (THR_FASTDET != 0)>;
+    v.fn = (const void *)&detect_kernel<LOG2N, T, GMEM, (THR_MULTI != 0), (THR_FASTDET != 0), THR_STAGES>;
     v.name = name;
     return v;
 }
 
-#if THR_FASTDET
+#if THR_STAGES == 1
+#define THR_PICK pick_variant_stage1
+#define THR_SUFFIX ",sync>"
+#elif THR_STAGES == 2
+#define THR_PICK pick_variant_stage2
+#define THR_SUFFIX ",soa>"
+#elif THR_FASTDET
 #define THR_PICK pick_variant_fastdet
 #define THR_SUFFIX ",fastdet>"
 #elif THR_MULTI
