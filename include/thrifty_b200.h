@@ -216,6 +216,32 @@ int thr_sync_batch(thr_detector *det, const uint8_t *raw, const float *iq, const
 int thr_soa_batch(thr_detector *det, const float *fft, const int64_t *block_idx, int64_t n_blocks, thr_record *out,
                   float *corr);
 
+/* ---- several GPUs behind one handle (thrifty/detect.py:217-223: the loop over blocks is the seam) ----
+ * The detect path has no cross-block state, so a batch shards into contiguous stripes, one per GPU, with no data-path
+ * collective: one thr_detector + one host thread per device; stripe g = blocks [g * ceil(B/G), (g+1) * ceil(B/G)); every
+ * stripe's records land in its slice of the caller's array, so `out` is in input order exactly as from one GPU (and
+ * byte-identical to it).  Raw streams are striped with an H-sample halo at each stripe start, `.card` text at line
+ * boundaries.  `devices` are CUDA ordinals; the config's own `device` field is ignored.  Worker threads pin themselves to
+ * the CPUs of their GPU's NUMA node when sysfs exposes it; thr_group_host_alloc returns page-locked memory of
+ * n_devices * bytes_per_device bytes whose g-th part lives on the g-th GPU's node (part size rounded up to the page size:
+ * use thr_group_size() * bytes_per_device only when bytes_per_device is a multiple of 4096). */
+typedef struct thr_group thr_group;
+int  thr_group_create(const thr_config *cfg, const int32_t *devices, int32_t n_devices, thr_group **out);
+void thr_group_destroy(thr_group *grp);
+const char *thr_group_last_error(const thr_group *grp);     /* grp == NULL: last failed thr_group_create */
+int  thr_group_size(const thr_group *grp);
+thr_detector *thr_group_member(thr_group *grp, int32_t i);  /* the i-th device's handle (thr_get_info, ...) */
+int  thr_group_numa_node(const thr_group *grp, int32_t i, int32_t *thread_bound);   /* -1: unknown */
+int  thr_group_detect_batch(thr_group *grp, const uint8_t *raw, const int64_t *block_idx, int64_t n_blocks,
+                            thr_record *out);
+int  thr_group_detect_stream(thr_group *grp, const uint8_t *stream, int64_t n_stream_bytes, int64_t first_block,
+                             thr_record *out, int64_t *n_blocks);
+int  thr_group_detect_card(thr_group *grp, const char *text, size_t len, int32_t final_chunk, int64_t max_blocks,
+                           double *timestamps, int64_t *block_idx, thr_record *out, int64_t *n_blocks,
+                           int64_t *consumed);
+void *thr_group_host_alloc(thr_group *grp, size_t bytes_per_device);
+void  thr_group_host_free(thr_group *grp, void *p, size_t bytes_per_device);
+
 /* ---- stream / timing plumbing ---- */
 int thr_set_stream(thr_detector *det, void *cuda_stream);   /* NULL -> handle's own stream */
 int thr_synchronize(thr_detector *det);

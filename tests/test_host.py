@@ -317,3 +317,125 @@ def test_bench_numa_binding_is_a_no_op_without_locality_information():
     before = os.sched_getaffinity(0)
     assert bench.bind_to_gpu_numa_node(0) is None
     assert os.sched_getaffinity(0) == before
+
+
+# ---- Detector.detect_raw_stream host logic with a fake native layer (no GPU): block count, block indices and the exact
+# ---- byte windows handed to thr_detect_stream, including history_len > block_len / 2 (negative slice)
+class _FakeStreamNative(object):
+    def __init__(self, block_len, history_len, expected_blocks):
+        self.block_len, self.history_len, self.n_templates = block_len, history_len, 1
+        self.expected = expected_blocks          # block index -> complex64 block (reference block_reader semantics)
+        self.calls = []
+
+    def detect_stream(self, stream, first_block):
+        from thrifty_b200._native import RECORD_DTYPE
+        from thrifty_b200.block_data import raw_to_complex
+        n, h = self.block_len, self.history_len
+        new = 2 * (n - h)
+        nblk = (len(stream) - 2 * n) // new + 1
+        assert nblk >= 1 and (len(stream) - 2 * n) % new == 0
+        out = np.zeros((nblk, 1), dtype=RECORD_DTYPE)
+        for k in range(nblk):
+            got = raw_to_complex(stream[k * new:k * new + 2 * n])
+            np.testing.assert_array_equal(got, self.expected[first_block + k])
+            out[k, 0]["block_idx"] = first_block + k
+        self.calls.append((first_block, nblk))
+        return out
+
+
+@pytest.mark.parametrize("n,h,nblk,chunk", [(64, 16, 10, 4), (64, 40, 10, 3), (64, 50, 12, 4), (64, 63, 9, 2), (64, 0, 5, 2),
+                                            (64, 32, 7, 100)])
+@pytest.mark.parametrize("read_size", [None, 37])
+def test_raw_stream_windows_and_indices(n, h, nblk, chunk, read_size):
+    import io
+    from collections import namedtuple
+    from oracle import thrifty_oracle as orc
+    from thrifty_b200 import detect as det_mod
+    rng = np.random.default_rng(n * 1000 + h)
+    new = n - h
+    data = rng.integers(0, 256, size=2 * (nblk * new) + min(11, 2 * new - 1), dtype=np.uint8).tobytes()   # + a partial block
+    expected = {i: b for i, b in orc.block_reader(io.BytesIO(data), n, h)}
+    assert len(expected) == nblk
+    d = object.__new__(det_mod.Detector)
+    St = namedtuple("St", "block_len history_len")
+    d.settings, d.rxid, d.batch = St(n, h), 7, chunk
+    d.native = _FakeStreamNative(n, h, expected)
+    seen = []
+
+    def fake_detect(timestamp, block_idx, block):       # the complex path (zero history)
+        np.testing.assert_array_equal(np.asarray(block, dtype=np.complex64), expected[block_idx])
+        seen.append(block_idx)
+        return False, det_mod.toads_data.DetectionResult(timestamp, block_idx, None, det_mod.toads_data.CarrierSyncInfo(0, 0, 0., 0.), None, 7)
+    d.detect = fake_detect
+
+    class Slow(io.BytesIO):                              # a pipe that hands out a few bytes at a time
+        def read1(self, size=-1):
+            return io.BytesIO.read(self, min(size, read_size) if read_size else size)
+    results = list(d.detect_raw_stream(Slow(data), chunk_blocks=chunk))
+    assert [r.block for _, r in results] == list(range(nblk))
+    n_zero_hist = min(nblk, -(-h // new)) if h else 0
+    assert seen == list(range(n_zero_hist))              # only blocks reaching before the stream take the complex path
+    assert sum(c[1] for c in d.native.calls) == nblk - n_zero_hist
+    assert all(c[1] <= chunk for c in d.native.calls)
+
+
+def test_card_stream_short_prefix_lines_are_not_dropped():
+    """lines with short '<t> <i>' prefixes ('1.0 3 <payload>') used to overflow the max_blocks estimate and the
+    rest of the chunk was dropped on the final call.  Host logic only: a fake native layer that consumes a limited number
+    of lines per call."""
+    import io
+    from collections import namedtuple
+    from thrifty_b200 import detect as det_mod
+    from thrifty_b200._native import RECORD_DTYPE
+    n = 12
+    pay = "A" * (((2 * n + 2) // 3) * 4)
+    lines = ["%d.0 %d %s\n" % (i, i, pay) for i in range(57)]
+    text = ("# header\n" + "".join(lines)).encode()
+
+    class FakeNative(object):
+        n_templates = 1
+
+        def __init__(self):
+            self.calls = 0
+
+        def detect_card_ptr(self, ptr, length, final=True, max_blocks=None):
+            import ctypes
+            raw = ctypes.string_at(ptr, length)
+            self.calls += 1
+            done, ts, idx = 0, [], []
+            for ln in raw.split(b"\n")[:-1] if not raw.endswith(b"\n") or True else []:
+                if done + len(ln) + 1 > length:
+                    break
+                if len(idx) >= 5:                        # consumes at most 5 lines per call
+                    break
+                done += len(ln) + 1
+                if ln.startswith(b"#") or not ln:
+                    continue
+                t, i, _ = ln.split(b" ")
+                ts.append(float(t))
+                idx.append(int(i))
+            recs = np.zeros((len(idx), 1), dtype=RECORD_DTYPE)
+            recs["block_idx"][:, 0] = idx
+            return np.array(ts), np.array(idx, dtype=np.int64), recs, done
+
+    d = object.__new__(det_mod.Detector)
+    St = namedtuple("St", "block_len history_len")
+    d.settings, d.rxid, d.batch = St(n, 4), 0, 4
+    d.native = FakeNative()
+    orig = det_mod.__dict__.get("PinnedBuffer")
+
+    class FakePinned(object):
+        def __init__(self, nbytes):
+            self.array = np.zeros(nbytes, dtype=np.uint8)
+            self.ptr = self.array.ctypes.data
+
+        def close(self):
+            pass
+    import thrifty_b200._native as nat
+    saved = nat.PinnedBuffer
+    nat.PinnedBuffer = FakePinned
+    try:
+        out = list(d.detect_card_stream(io.BytesIO(text), chunk_bytes=1))      # clamps to 4 lines' worth
+    finally:
+        nat.PinnedBuffer = saved
+    assert [r.block for _, r in out] == list(range(57))

@@ -61,6 +61,9 @@ EXPORTS = [
     "thr_timer_start", "thr_timer_stop", "thr_host_alloc", "thr_host_free", "thr_device_alloc",
     "thr_device_free", "thr_memcpy_h2d", "thr_memcpy_d2h", "thr_card_scan", "thr_detect_card",
     "thr_detect_stream", "thr_detect_stream_device", "thr_sync_batch", "thr_soa_batch",
+    "thr_group_create", "thr_group_destroy", "thr_group_last_error", "thr_group_size", "thr_group_member",
+    "thr_group_numa_node", "thr_group_detect_batch", "thr_group_detect_stream", "thr_group_detect_card",
+    "thr_group_host_alloc", "thr_group_host_free",
 ]
 
 _lib = None
@@ -113,6 +116,29 @@ def load_library(path=None):
     lib.thr_sync_batch.restype = c_int
     lib.thr_soa_batch.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]
     lib.thr_soa_batch.restype = c_int
+    lib.thr_group_create.argtypes = [POINTER(ThrConfig), POINTER(c_int32), c_int32, POINTER(c_void_p)]
+    lib.thr_group_create.restype = c_int
+    lib.thr_group_destroy.argtypes = [c_void_p]
+    lib.thr_group_destroy.restype = None
+    lib.thr_group_last_error.argtypes = [c_void_p]
+    lib.thr_group_last_error.restype = c_char_p
+    lib.thr_group_size.argtypes = [c_void_p]
+    lib.thr_group_size.restype = c_int
+    lib.thr_group_member.argtypes = [c_void_p, c_int32]
+    lib.thr_group_member.restype = c_void_p
+    lib.thr_group_numa_node.argtypes = [c_void_p, c_int32, POINTER(c_int32)]
+    lib.thr_group_numa_node.restype = c_int
+    lib.thr_group_detect_batch.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]
+    lib.thr_group_detect_batch.restype = c_int
+    lib.thr_group_detect_stream.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_void_p, POINTER(c_int64)]
+    lib.thr_group_detect_stream.restype = c_int
+    lib.thr_group_detect_card.argtypes = [c_void_p, c_char_p, c_size_t, c_int32, c_int64, c_void_p, c_void_p, c_void_p,
+                                          POINTER(c_int64), POINTER(c_int64)]
+    lib.thr_group_detect_card.restype = c_int
+    lib.thr_group_host_alloc.argtypes = [c_void_p, c_size_t]
+    lib.thr_group_host_alloc.restype = c_void_p
+    lib.thr_group_host_free.argtypes = [c_void_p, c_void_p, c_size_t]
+    lib.thr_group_host_free.restype = None
     lib.thr_set_stream.argtypes = [c_void_p, c_void_p]
     lib.thr_set_stream.restype = c_int
     lib.thr_synchronize.argtypes = [c_void_p]
@@ -162,6 +188,42 @@ class PinnedBuffer(object):
             pass
 
 
+def _make_config(self, block_len, history_len, templates, carrier_len, carrier_window, carrier_thresh, corr_thresh,
+                 device, max_batch, overlap_launches, fastdet, generic_kernel):
+    """Fill a ThrConfig (and the matching attributes of `self`); returns (cfg, template array to keep alive)."""
+    tpl = np.ascontiguousarray(np.atleast_2d(np.asarray(templates, dtype=np.float64)))
+    self.n_templates, self.template_len = tpl.shape
+    self.block_len = int(block_len)
+    self.history_len = int(history_len)
+    self.max_batch = int(max_batch)
+    self.device = int(device)
+    cfg = ThrConfig()
+    cfg.block_len = self.block_len
+    cfg.history_len = self.history_len
+    cfg.template_len = self.template_len
+    cfg.n_templates = self.n_templates
+    cfg.templates = tpl.ctypes.data_as(POINTER(c_double))
+    cfg.carrier_len = int(carrier_len)
+    win = (0, -1) if carrier_window is None else carrier_window
+    cfg.window_start, cfg.window_stop = int(win[0]), int(win[1])
+    cfg.carrier_thresh = (c_double * 3)(*[float(v) for v in carrier_thresh])
+    cfg.corr_thresh = (c_double * 3)(*[float(v) for v in corr_thresh])
+    cfg.device = self.device
+    cfg.max_batch = self.max_batch
+    # THR_CFG_OVERLAP_LAUNCHES | THR_CFG_FASTDET_SEMANTICS (the native twin's semantics:
+    # thresholds (constant, snr) apply to POWERS, fastcard/parse.c:54-99 '<c>c<s>s')
+    # THR_CFG_GENERIC_KERNEL: block_len 32768 on the generic global-scratch kernel (comparisons)
+    cfg.flags = (1 if overlap_launches else 0) | (2 if fastdet else 0) | (4 if generic_kernel else 0)
+    self.fastdet = bool(fastdet)
+    return cfg, tpl
+
+
+def _raise_create_error(what, rc, msg):
+    if ("out of range" in msg and "window" in msg) or "window range not supported" in msg:
+        raise ValueError(msg)            # carrier_detect.py:47-49 raises ValueError
+    raise NativeError("%s failed (%d): %s" % (what, rc, msg))
+
+
 class NativeDetector(object):
     """Thin owner of a thr_detector handle."""
 
@@ -170,37 +232,14 @@ class NativeDetector(object):
                  fastdet=False, generic_kernel=False):
         self._lib = load_library()
         self._h = c_void_p()
-        tpl = np.ascontiguousarray(np.atleast_2d(np.asarray(templates, dtype=np.float64)))
-        self.n_templates, self.template_len = tpl.shape
-        self.block_len = int(block_len)
-        self.history_len = int(history_len)
-        self.max_batch = int(max_batch)
-        self.device = int(device)
-        cfg = ThrConfig()
-        cfg.block_len = self.block_len
-        cfg.history_len = self.history_len
-        cfg.template_len = self.template_len
-        cfg.n_templates = self.n_templates
-        cfg.templates = tpl.ctypes.data_as(POINTER(c_double))
-        cfg.carrier_len = int(carrier_len)
-        win = (0, -1) if carrier_window is None else carrier_window
-        cfg.window_start, cfg.window_stop = int(win[0]), int(win[1])
-        cfg.carrier_thresh = (c_double * 3)(*[float(v) for v in carrier_thresh])
-        cfg.corr_thresh = (c_double * 3)(*[float(v) for v in corr_thresh])
-        cfg.device = self.device
-        cfg.max_batch = self.max_batch
-        # THR_CFG_OVERLAP_LAUNCHES | THR_CFG_FASTDET_SEMANTICS (the native twin's semantics:
-        # thresholds (constant, snr) apply to POWERS, fastcard/parse.c:54-99 '<c>c<s>s')
-        # THR_CFG_GENERIC_KERNEL: block_len 32768 on the generic global-scratch kernel (comparisons)
-        cfg.flags = (1 if overlap_launches else 0) | (2 if fastdet else 0) | (4 if generic_kernel else 0)
-        self.fastdet = bool(fastdet)
+        self._owned = True
+        cfg, _tpl = _make_config(self, block_len, history_len, templates, carrier_len, carrier_window, carrier_thresh,
+                                 corr_thresh, device, max_batch, overlap_launches, fastdet, generic_kernel)
         rc = self._lib.thr_create(byref(cfg), byref(self._h))
         if rc != THR_OK:
             msg = self._lib.thr_last_error(None).decode()
             self._h = c_void_p()
-            if ("out of range" in msg and "window" in msg) or "window range not supported" in msg:
-                raise ValueError(msg)            # carrier_detect.py:47-49 raises ValueError
-            raise NativeError("thr_create failed (%d): %s" % (rc, msg))
+            _raise_create_error("thr_create", rc, msg)
 
     # -- helpers
     def _check(self, rc):
@@ -220,7 +259,8 @@ class NativeDetector(object):
 
     def close(self):
         if self._h:
-            self._lib.thr_destroy(self._h)
+            if self._owned:
+                self._lib.thr_destroy(self._h)
             self._h = c_void_p()
 
     def __del__(self):
@@ -342,16 +382,18 @@ class NativeDetector(object):
         With final=False an unterminated last line is left for the next call (see `consumed`)."""
         if not isinstance(text, (bytes, bytearray)):
             raise TypeError("text must be bytes")
-        line_len = ((2 * self.block_len + 2) // 3) * 4 + 16
         if max_blocks is None:
-            max_blocks = len(text) // line_len + 1
+            max_blocks = len(text) // self._min_card_line() + 1
         return self.detect_card_ptr(bytes(text), len(text), final, max_blocks)
+
+    def _min_card_line(self):
+        """Shortest possible data line: '<t> <i> <payload>\\n' with one-character time and index."""
+        return ((2 * self.block_len + 2) // 3) * 4 + 5
 
     def detect_card_ptr(self, ptr, length, final=True, max_blocks=None):
         """Same as detect_card for text at a raw address (e.g. a PinnedBuffer: full-speed H2D copies)."""
-        line_len = ((2 * self.block_len + 2) // 3) * 4 + 16
         if max_blocks is None:
-            max_blocks = length // line_len + 1
+            max_blocks = length // self._min_card_line() + 1
         ts = np.zeros(max_blocks, dtype=np.float64)
         idx = np.zeros(max_blocks, dtype=np.int64)
         out = np.zeros((max_blocks, self.n_templates), dtype=RECORD_DTYPE)
@@ -384,3 +426,100 @@ class NativeDetector(object):
         ms = c_float()
         self._check(self._lib.thr_timer_stop(self._h, byref(ms)))
         return ms.value
+
+
+class NativeGroup(NativeDetector):
+    """Several GPUs behind one handle (thr_group_*): every batch is cut into contiguous stripes, one per device, and the
+    records come back in input order, byte-identical to one GPU's.  Same host-buffer methods as NativeDetector
+    (detect_raw / detect_stream / detect_card[_ptr]); complex64 blocks, single-block debug outputs and the device-buffer
+    entry points go to the first member."""
+
+    def __init__(self, devices, block_len, history_len, templates, carrier_len, carrier_window, carrier_thresh,
+                 corr_thresh, max_batch=4096, fastdet=False):
+        self._lib = load_library()
+        self._g = c_void_p()
+        self._h = c_void_p()
+        self._owned = False
+        self.devices = [int(d) for d in devices]
+        cfg, _tpl = _make_config(self, block_len, history_len, templates, carrier_len, carrier_window, carrier_thresh,
+                                 corr_thresh, self.devices[0], max_batch, False, fastdet, False)
+        dev = (c_int32 * len(self.devices))(*self.devices)
+        rc = self._lib.thr_group_create(byref(cfg), dev, len(self.devices), byref(self._g))
+        if rc != THR_OK:
+            msg = self._lib.thr_group_last_error(None).decode()
+            self._g = c_void_p()
+            _raise_create_error("thr_group_create", rc, msg)
+        self._h = c_void_p(self._lib.thr_group_member(self._g, 0))      # borrowed: first member
+
+    def _gcheck(self, rc):
+        if rc != THR_OK:
+            raise NativeError("thrifty_b200 group call failed (%d): %s" % (rc, self._lib.thr_group_last_error(self._g).decode()))
+
+    def close(self):
+        if self._g:
+            self._lib.thr_group_destroy(self._g)
+            self._g = c_void_p()
+            self._h = c_void_p()
+
+    def numa_nodes(self):
+        out = []
+        for i in range(len(self.devices)):
+            bound = c_int32(0)
+            out.append((self._lib.thr_group_numa_node(self._g, i, byref(bound)), bool(bound.value)))
+        return out
+
+    def info(self):
+        info = NativeDetector.info(self)
+        info["devices"] = list(self.devices)
+        launches = 0
+        for i in range(len(self.devices)):
+            m = ThrInfo()
+            self._check(self._lib.thr_get_info(c_void_p(self._lib.thr_group_member(self._g, i)), byref(m)))
+            launches += m.launches
+        info["launches"] = launches
+        return info
+
+    def detect_raw(self, raw, block_idx=None):
+        raw = np.ascontiguousarray(raw, dtype=np.uint8)
+        if raw.ndim != 2 or raw.shape[1] != 2 * self.block_len:
+            raise ValueError("raw must have shape [B, %d]" % (2 * self.block_len))
+        nblk = raw.shape[0]
+        out = np.zeros((nblk, self.n_templates), dtype=RECORD_DTYPE)
+        idx_ptr = None
+        if block_idx is not None:
+            idx = np.ascontiguousarray(block_idx, dtype=np.int64)
+            assert idx.shape == (nblk,)
+            idx_ptr = idx.ctypes.data
+        self._gcheck(self._lib.thr_group_detect_batch(self._g, raw.ctypes.data, idx_ptr, nblk, out.ctypes.data))
+        return out
+
+    def detect_raw_ptr(self, ptr, n_blocks, idx_ptr, out_ptr):
+        """Raw addresses (page-locked buffers): no NumPy copies."""
+        self._gcheck(self._lib.thr_group_detect_batch(self._g, ptr, idx_ptr, int(n_blocks), out_ptr))
+
+    def detect_stream(self, stream, first_block):
+        stream = np.ascontiguousarray(stream, dtype=np.uint8)
+        new = 2 * (self.block_len - self.history_len)
+        nblk = (len(stream) - 2 * self.block_len) // new + 1 if len(stream) >= 2 * self.block_len else 0
+        out = np.zeros((max(nblk, 0), self.n_templates), dtype=RECORD_DTYPE)
+        got = c_int64(0)
+        self._gcheck(self._lib.thr_group_detect_stream(self._g, stream.ctypes.data, len(stream), int(first_block),
+                                                       out.ctypes.data, byref(got)))
+        assert got.value == len(out)
+        return out
+
+    def detect_card_ptr(self, ptr, length, final=True, max_blocks=None):
+        line_len = ((2 * self.block_len + 2) // 3) * 4 + 5
+        if max_blocks is None:
+            max_blocks = length // line_len + 1
+        ts = np.zeros(max_blocks, dtype=np.float64)
+        idx = np.zeros(max_blocks, dtype=np.int64)
+        out = np.zeros((max_blocks, self.n_templates), dtype=RECORD_DTYPE)
+        nblk, consumed = c_int64(0), c_int64(0)
+        if not isinstance(ptr, (bytes, bytearray)):
+            ptr = ctypes.cast(ptr, c_char_p)
+        self._gcheck(self._lib.thr_group_detect_card(self._g, ptr, length, 1 if final else 0, max_blocks,
+                                                     ts.ctypes.data, idx.ctypes.data, out.ctypes.data,
+                                                     byref(nblk), byref(consumed)))
+        n = nblk.value
+        return ts[:n], idx[:n], out[:n], consumed.value

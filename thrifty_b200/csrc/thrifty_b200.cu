@@ -13,8 +13,17 @@
 #include <emmintrin.h>
 #endif
 
+#include <sched.h>
+#include <sys/mman.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
 #include <cmath>
 #include <complex>
+#include <condition_variable>
+#include <functional>
+#include <memory>
+#include <mutex>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -890,7 +899,10 @@ static int card_scan_lines(const char *text, size_t len, int32_t block_len, int3
     while (p < end && n < max_blocks) {
         // Fast path: a data line's payload has a known length, so after the two numbers the end of the
         // line is found by a jump instead of a scan over 43.7 KB of base64 text.
-        if (*p != '#' && *p != '\n' && *p != '\r' && *p != 'U' && *p != 'l') {
+        // (the number parsers stop at the first character that is not part of a number: a space inside the next 40
+        // bytes guarantees that they stay inside [p, end) even when the text is not NUL-terminated)
+        const size_t look = (size_t)(end - p) < 40 ? (size_t)(end - p) : 40;
+        if (*p != '#' && *p != '\n' && *p != '\r' && *p != 'U' && *p != 'l' && std::memchr(p, ' ', look)) {
             char *q = nullptr;
             const double ts = std::strtod(p, &q);
             if (q != p && q < end && *q == ' ') {
@@ -927,6 +939,12 @@ static int card_scan_lines(const char *text, size_t len, int32_t block_len, int3
             continue;
         }
         char *q = nullptr;
+        if (!std::memchr(p, ' ', (size_t)(le - p))) {                  // no separator at all: malformed, and strtod must
+            if (bad_line) *bad_line = line_no;                         // not run off an unterminated buffer
+            *n_found = n;
+            *consumed = p - text;
+            return THR_ERR_INVALID;
+        }
         const double ts = std::strtod(p, &q);
         bool ok = q != p && q < le && *q == ' ';
         long long idx = 0;
@@ -1120,6 +1138,305 @@ int thr_detect_stream(thr_detector *d, const uint8_t *stream, int64_t n_stream_b
     return THR_OK;
 }
 
+
+// ---- several GPUs behind one handle ---------------------------------------------------------------------------
+// The detect path has no cross-block state (thrifty/detect.py:40-58) and every .card block carries its own history, so a
+// batch shards into contiguous stripes with no data-path collective: one thr_detector + one host thread per GPU, stripe g
+// = blocks [g * ceil(B/G), ...), every stripe's records land in its slice of the caller's array, block order preserved
+// (the seam is the loop at thrifty/detect.py:217-223).  Each worker thread first moves to the CPUs of its GPU's NUMA node
+// (sysfs; best effort) so that its page-locked staging is node-local.
+namespace {
+
+int gpu_numa_node(int dev) {
+    char busid[32] = {0};
+    if (cudaDeviceGetPCIBusId(busid, (int)sizeof busid, dev) != cudaSuccess) return -1;
+    for (char *c = busid; *c; ++c) *c = (char)std::tolower(*c);
+    const std::string path = std::string("/sys/bus/pci/devices/") + busid + "/numa_node";
+    FILE *f = std::fopen(path.c_str(), "r");
+    if (!f) return -1;
+    int node = -1;
+    if (std::fscanf(f, "%d", &node) != 1) node = -1;
+    std::fclose(f);
+    return node;
+}
+
+bool bind_thread_to_node(int node) {
+    if (node < 0) return false;
+    char path[128];
+    std::snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    FILE *f = std::fopen(path, "r");
+    if (!f) return false;
+    char buf[2048] = {0};
+    const bool ok = std::fgets(buf, sizeof buf, f) != nullptr;
+    std::fclose(f);
+    if (!ok) return false;
+    cpu_set_t set, allowed;
+    CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof allowed, &allowed) != 0) return false;
+    int n = 0;
+    char *save = nullptr;
+    for (char *tok = strtok_r(buf, ",\n", &save); tok; tok = strtok_r(nullptr, ",\n", &save)) {
+        int lo = 0, hi = 0;
+        const int got = std::sscanf(tok, "%d-%d", &lo, &hi);
+        if (got == 1) hi = lo;
+        if (got < 1) continue;
+        for (int c = lo; c <= hi && c < CPU_SETSIZE; ++c)
+            if (CPU_ISSET(c, &allowed)) { CPU_SET(c, &set); ++n; }
+    }
+    return n > 0 && sched_setaffinity(0, sizeof set, &set) == 0;
+}
+
+struct GroupWorker {
+    std::thread th;
+    std::mutex m;
+    std::condition_variable cv;
+    std::function<int(thr_detector *)> job;
+    bool has_job = false, done = false, quit = false;
+    int rc = THR_OK;
+    thr_detector *det = nullptr;
+    int device = 0, numa = -1;
+    bool bound = false;
+    std::string err;
+};
+
+}  // namespace
+
+struct thr_group {
+    std::vector<std::unique_ptr<GroupWorker>> w;
+    thr_config cfg;
+    std::string err;
+};
+
+namespace {
+
+void group_worker_main(GroupWorker *w, const thr_config *cfg0) {
+    w->numa = gpu_numa_node(w->device);
+    w->bound = bind_thread_to_node(w->numa);
+    thr_config cfg = *cfg0;
+    cfg.device = w->device;
+    int rc = thr_create(&cfg, &w->det);
+    if (rc != THR_OK) w->err = thr_last_error(nullptr);
+    {
+        std::lock_guard<std::mutex> lk(w->m);
+        w->rc = rc;
+        w->done = true;
+    }
+    w->cv.notify_all();
+    for (;;) {
+        std::unique_lock<std::mutex> lk(w->m);
+        w->cv.wait(lk, [&] { return w->has_job || w->quit; });
+        if (w->quit) break;
+        auto job = w->job;
+        w->has_job = false;
+        lk.unlock();
+        const int r = job(w->det);
+        lk.lock();
+        w->rc = r;
+        w->done = true;
+        lk.unlock();
+        w->cv.notify_all();
+    }
+    if (w->det) thr_destroy(w->det);
+    w->det = nullptr;
+}
+
+// run job(g, det) on every worker and wait; returns the first non-zero status
+int group_run(thr_group *g, const std::function<int(int, thr_detector *)> &job) {
+    const int n = (int)g->w.size();
+    for (int i = 0; i < n; ++i) {
+        GroupWorker *w = g->w[i].get();
+        std::lock_guard<std::mutex> lk(w->m);
+        w->job = [i, &job](thr_detector *d) { return job(i, d); };
+        w->done = false;
+        w->has_job = true;
+        w->cv.notify_all();
+    }
+    int rc = THR_OK;
+    for (int i = 0; i < n; ++i) {
+        GroupWorker *w = g->w[i].get();
+        std::unique_lock<std::mutex> lk(w->m);
+        w->cv.wait(lk, [&] { return w->done; });
+        if (w->rc != THR_OK && rc == THR_OK) {
+            rc = w->rc;
+            g->err = std::string("device ") + std::to_string(w->device) + ": " + thr_last_error(w->det);
+        }
+    }
+    return rc;
+}
+
+}  // namespace
+
+void thr_group_destroy(thr_group *g) {
+    if (!g) return;
+    for (auto &w : g->w) {
+        {
+            std::lock_guard<std::mutex> lk(w->m);
+            w->quit = true;
+        }
+        w->cv.notify_all();
+        if (w->th.joinable()) w->th.join();
+    }
+    delete g;
+}
+
+int thr_group_create(const thr_config *cfg, const int32_t *devices, int32_t n_devices, thr_group **out) {
+    if (!cfg || !devices || !out || n_devices < 1 || n_devices > 64) return fail(nullptr, THR_ERR_INVALID, "bad group arguments");
+    *out = nullptr;
+    for (int i = 0; i < n_devices; ++i)
+        for (int j = 0; j < i; ++j)
+            if (devices[i] == devices[j]) return fail(nullptr, THR_ERR_INVALID, "device %d listed twice", devices[i]);
+    thr_group *g = new thr_group();
+    g->cfg = *cfg;
+    for (int i = 0; i < n_devices; ++i) {
+        g->w.emplace_back(new GroupWorker());
+        GroupWorker *w = g->w.back().get();
+        w->device = devices[i];
+        w->th = std::thread(group_worker_main, w, cfg);        // cfg->templates stays valid until every create has returned
+    }
+    int rc = THR_OK;
+    for (auto &w : g->w) {
+        std::unique_lock<std::mutex> lk(w->m);
+        w->cv.wait(lk, [&] { return w->done; });
+        if (w->rc != THR_OK && rc == THR_OK) {
+            rc = w->rc;
+            g_create_error = "device " + std::to_string(w->device) + ": " + w->err;
+        }
+    }
+    g->cfg.templates = nullptr;
+    if (rc != THR_OK) {
+        const std::string keep = g_create_error;
+        thr_group_destroy(g);
+        g_create_error = keep;
+        return rc;
+    }
+    *out = g;
+    return THR_OK;
+}
+
+const char *thr_group_last_error(const thr_group *g) { return g ? g->err.c_str() : g_create_error.c_str(); }
+int thr_group_size(const thr_group *g) { return g ? (int)g->w.size() : 0; }
+thr_detector *thr_group_member(thr_group *g, int32_t i) {
+    return (g && i >= 0 && i < (int)g->w.size()) ? g->w[i]->det : nullptr;
+}
+int thr_group_numa_node(const thr_group *g, int32_t i, int32_t *bound) {
+    if (!g || i < 0 || i >= (int)g->w.size()) return -1;
+    if (bound) *bound = g->w[i]->bound ? 1 : 0;
+    return g->w[i]->numa;
+}
+
+// stripe g of n items over G devices: [lo, hi)
+static inline void stripe_of(int64_t n, int G, int g, int64_t *lo, int64_t *hi) {
+    const int64_t per = (n + G - 1) / G;
+    *lo = per * g < n ? per * g : n;
+    *hi = per * (g + 1) < n ? per * (g + 1) : n;
+}
+
+int thr_group_detect_batch(thr_group *g, const uint8_t *raw, const int64_t *block_idx, int64_t n_blocks, thr_record *out) {
+    if (!g || !raw || !out || n_blocks < 0) return THR_ERR_INVALID;
+    const int G = (int)g->w.size();
+    const int64_t N = g->cfg.block_len, NT = g->cfg.n_templates;
+    return group_run(g, [&](int i, thr_detector *d) -> int {
+        int64_t lo, hi;
+        stripe_of(n_blocks, G, i, &lo, &hi);
+        if (hi <= lo) return THR_OK;
+        std::vector<int64_t> idx;
+        const int64_t *ip = block_idx ? block_idx + lo : nullptr;
+        if (!ip) {                                   // default indices are global positions, not positions in the stripe
+            idx.resize((size_t)(hi - lo));
+            for (int64_t b = lo; b < hi; ++b) idx[(size_t)(b - lo)] = b;
+            ip = idx.data();
+        }
+        return thr_detect_batch(d, raw + (size_t)lo * 2 * N, ip, hi - lo, out + (size_t)lo * NT);
+    });
+}
+
+int thr_group_detect_stream(thr_group *g, const uint8_t *stream, int64_t n_stream_bytes, int64_t first_block,
+                            thr_record *out, int64_t *n_blocks_out) {
+    if (!g || !stream || !out || !n_blocks_out) return THR_ERR_INVALID;
+    const int G = (int)g->w.size();
+    const int64_t N = g->cfg.block_len, H = g->cfg.history_len, stride = 2 * (N - H), NT = g->cfg.n_templates;
+    const int64_t nb_total = n_stream_bytes >= 2 * N ? (n_stream_bytes - 2 * N) / stride + 1 : 0;
+    *n_blocks_out = nb_total;
+    // each stripe starts with the H samples of history of its first block (the halo): no exchange between GPUs
+    return group_run(g, [&](int i, thr_detector *d) -> int {
+        int64_t lo, hi;
+        stripe_of(nb_total, G, i, &lo, &hi);
+        if (hi <= lo) return THR_OK;
+        int64_t got = 0;
+        const int64_t bytes = (hi - lo - 1) * stride + 2 * N;
+        const int rc = thr_detect_stream(d, stream + lo * stride, bytes, first_block + lo, out + (size_t)lo * NT, &got);
+        if (rc == THR_OK && got != hi - lo) return fail(d, THR_ERR_INVALID, "stripe of %lld blocks returned %lld", (long long)(hi - lo), (long long)got);
+        return rc;
+    });
+}
+
+int thr_group_detect_card(thr_group *g, const char *text, size_t len, int32_t final_chunk, int64_t max_blocks,
+                          double *timestamps, int64_t *block_idx, thr_record *out, int64_t *n_blocks, int64_t *consumed) {
+    if (!g || !text || !timestamps || !block_idx || !out || !n_blocks || !consumed || max_blocks < 0) return THR_ERR_INVALID;
+    const int G = (int)g->w.size();
+    const int64_t N = g->cfg.block_len, NT = g->cfg.n_templates;
+    *n_blocks = 0;
+    *consumed = 0;
+    // one pass over the line headers fixes where every data line starts; the stripes are cut at line boundaries
+    std::vector<int64_t> off((size_t)max_blocks);
+    int64_t found = 0, used = 0, bad_line = -1;
+    const int rc0 = card_scan_lines(text, len, (int32_t)N, final_chunk, max_blocks, timestamps, block_idx, off.data(), &found,
+                                    &used, &bad_line, nullptr);
+    if (rc0 != THR_OK) {
+        g->err = ".card data line " + std::to_string(bad_line) + " is malformed";
+        return rc0;
+    }
+    *consumed = used;
+    if (found == 0) return THR_OK;
+    const int64_t want = ((2 * N + 2) / 3) * 4;
+    const int rc = group_run(g, [&](int i, thr_detector *d) -> int {
+        int64_t lo, hi;
+        stripe_of(found, G, i, &lo, &hi);
+        if (hi <= lo) return THR_OK;
+        // text range of the stripe: from the start of line lo's header (searched backwards from its payload) to the end of
+        // line hi-1's payload; the per-stripe call re-parses its own headers
+        const char *p0 = text + off[(size_t)lo];
+        while (p0 > text && p0[-1] != '\n') --p0;
+        const char *p1 = text + off[(size_t)(hi - 1)] + want;
+        int64_t nb = 0, cons = 0;
+        const int r = thr_detect_card(d, p0, (size_t)(p1 - p0), 1, hi - lo, timestamps + lo, block_idx + lo,
+                                      out + (size_t)lo * NT, &nb, &cons);
+        if (r == THR_OK && nb != hi - lo) return fail(d, THR_ERR_INVALID, "stripe of %lld lines returned %lld", (long long)(hi - lo), (long long)nb);
+        return r;
+    });
+    if (rc == THR_OK) *n_blocks = found;
+    return rc;
+}
+
+// Page-locked host buffer of n_devices * bytes_per_device bytes whose g-th part is placed on the NUMA node of the group's
+// g-th GPU (mbind before first touch, then cudaHostRegister); a plain page-locked allocation where the host shows one node.
+void *thr_group_host_alloc(thr_group *g, size_t bytes_per_device) {
+    if (!g || !bytes_per_device) return nullptr;
+    const size_t G = g->w.size(), page = (size_t)sysconf(_SC_PAGESIZE);
+    const size_t part = (bytes_per_device + page - 1) / page * page, total = part * G;
+    void *base = mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (base == MAP_FAILED) return nullptr;
+    for (size_t i = 0; i < G; ++i) {
+        const int node = g->w[i]->numa;
+        if (node >= 0 && node < 64) {
+            unsigned long mask = 1ul << node;
+            syscall(SYS_mbind, (char *)base + i * part, part, 2 /* MPOL_BIND */, &mask, 65ul, 0u);   // best effort
+        }
+        std::memset((char *)base + i * part, 0, part);                                              // first touch
+    }
+    if (cudaHostRegister(base, total, cudaHostRegisterPortable) != cudaSuccess) {
+        munmap(base, total);
+        return nullptr;
+    }
+    return base;
+}
+void thr_group_host_free(thr_group *g, void *p, size_t bytes_per_device) {
+    if (!g || !p) return;
+    const size_t page = (size_t)sysconf(_SC_PAGESIZE);
+    const size_t part = (bytes_per_device + page - 1) / page * page;
+    cudaHostUnregister(p);
+    munmap(p, part * g->w.size());
+}
 
 void *thr_host_alloc(size_t bytes) {
     void *p = nullptr;

@@ -26,7 +26,7 @@ from collections import namedtuple
 import numpy as np
 
 from thrifty_b200 import toads_data, util
-from thrifty_b200._native import FLAG_CARRIER, FLAG_CORR, NativeDetector
+from thrifty_b200._native import FLAG_CARRIER, FLAG_CORR, NativeDetector, NativeGroup
 from thrifty_b200.block_data import block_reader, card_reader
 from thrifty_b200.setting_parsers import normalize_freq_range
 from thrifty_b200.settings import load_args
@@ -111,11 +111,13 @@ class Detector(object):
     """All-in-one carrier detect / sync / correlate / SoA estimate on the GPU.
 
     Parameters follow thrifty/detect.py:40; extras: ``batch`` = blocks per kernel launch
-    (read-ahead of the iterator), ``device`` = CUDA ordinal.  ``block`` arguments may be
-    complex arrays of length block_len (reference behaviour) or uint8 arrays of length
-    2*block_len (raw I/Q, conversion then runs on the GPU)."""
+    (read-ahead of the iterator), ``device`` = CUDA ordinal, ``devices`` = list of CUDA ordinals:
+    every batch is then cut into contiguous stripes, one per GPU (one host thread each, no
+    collective), and the results come back in input order exactly as from one GPU.  ``block``
+    arguments may be complex arrays of length block_len (reference behaviour) or uint8 arrays of
+    length 2*block_len (raw I/Q, conversion then runs on the GPU)."""
 
-    def __init__(self, settings, blocks=None, rxid=-1, yield_data=False, batch=256, device=0):
+    def __init__(self, settings, blocks=None, rxid=-1, yield_data=False, batch=256, device=0, devices=None):
         self.settings = settings
         self.blocks = iter(blocks) if blocks is not None else None
         self.rxid = rxid
@@ -125,10 +127,16 @@ class Detector(object):
         if template.ndim != 1:
             raise ValueError("Detector takes a single 1-D template; see MultiTemplateDetector")
         assert settings.history_len >= len(template) - 1     # soa_estimator.py:33
-        self.native = NativeDetector(
-            settings.block_len, settings.history_len, template, settings.carrier_len,
-            settings.carrier_window, settings.carrier_thresh, settings.corr_thresh,
-            device=device, max_batch=self.batch)
+        if devices is not None and len(devices) > 1:
+            self.native = NativeGroup(
+                devices, settings.block_len, settings.history_len, template, settings.carrier_len,
+                settings.carrier_window, settings.carrier_thresh, settings.corr_thresh,
+                max_batch=self.batch)
+        else:
+            self.native = NativeDetector(
+                settings.block_len, settings.history_len, template, settings.carrier_len,
+                settings.carrier_window, settings.carrier_thresh, settings.corr_thresh,
+                device=device if not devices else devices[0], max_batch=self.batch)
         self.new_len = settings.block_len - settings.history_len
         self._pending = []
 
@@ -180,89 +188,108 @@ class Detector(object):
         return records_to_results(recs[:, 0], [it[0] for it in items], self.rxid)
 
     # ---- whole `.card` streams: scan on the host, base64 decode + detect on the GPU
-    def detect_card_stream(self, stream, chunk_bytes=64 << 20):
+    def detect_card_stream(self, stream, chunk_bytes=64 << 20, min_lines=None):
         """Yield (detected, DetectionResult) for every data line of a binary `.card` stream.
 
         Same results as iterating Detector(settings, card_reader(stream)) (block_data.py:101-131),
-        but the text goes to the GPU as is (thr_detect_card): no host-side base64 or rawconv."""
+        but the text goes to the GPU as is (thr_detect_card): no host-side base64 or rawconv.
+        Reads are accumulated until `min_lines` lines' worth of text (default: min(batch, 8)) or the
+        end of the stream is buffered, so a pipe that hands out 64 KB at a time does not cost one
+        launch per read; lower it (or --batch) for latency on live inputs."""
         from thrifty_b200._native import PinnedBuffer
         line_len = ((2 * self.settings.block_len + 2) // 3) * 4 + 64
         chunk_bytes = max(int(chunk_bytes), 4 * line_len)
-        buf = PinnedBuffer(chunk_bytes)          # page-locked: the text is DMA'd straight from here
-        view = buf.array
+        if min_lines is None:
+            min_lines = max(1, min(self.batch, 8))
+        want = min(chunk_bytes, min_lines * line_len)
+        buf = PinnedBuffer(chunk_bytes + 1)      # page-locked: the text is DMA'd straight from here; one spare byte
+        view = buf.array                         # keeps the C number parser inside the allocation
+        view[chunk_bytes] = 0
         fill = 0
         read_into = getattr(stream, "readinto1", None) or getattr(stream, "readinto", None)
         try:
-            while True:
-                if read_into is not None:
-                    got = read_into(memoryview(view)[fill:]) or 0
-                else:
-                    data = stream.read(chunk_bytes - fill)
-                    if isinstance(data, str):
-                        data = data.encode("ascii")
-                    got = len(data)
-                    view[fill:fill + got] = np.frombuffer(data, dtype=np.uint8)
-                final = got == 0
-                total = fill + got
-                if total == 0:
+            eof = False
+            while not eof or fill:
+                while not eof and fill < want:
+                    if read_into is not None:
+                        got = read_into(memoryview(view)[fill:chunk_bytes]) or 0
+                    else:
+                        data = stream.read(chunk_bytes - fill)
+                        if isinstance(data, str):
+                            data = data.encode("ascii")
+                        got = len(data)
+                        view[fill:fill + got] = np.frombuffer(data, dtype=np.uint8)
+                    eof = got == 0
+                    fill += got
+                if fill == 0:
                     break
-                ts, idx, recs, consumed = self.native.detect_card_ptr(buf.ptr, total, final=final)
+                view[fill] = 0
+                ts, idx, recs, consumed = self.native.detect_card_ptr(buf.ptr, fill, final=eof)
                 for pair in records_to_results(recs[:, 0], ts, self.rxid):
                     yield pair
-                fill = total - consumed
-                if fill:
-                    view[:fill] = view[consumed:total].copy()
-                if final:
-                    break
-                if fill >= chunk_bytes:
+                rest = fill - consumed
+                if rest:
+                    view[:rest] = view[consumed:fill].copy()
+                if eof and consumed == 0:
+                    break                        # nothing but an unparsable remainder is left
+                if not eof and consumed == 0 and fill >= chunk_bytes:
                     raise ValueError(".card line longer than the %d-byte chunk buffer" % chunk_bytes)
+                if not eof and consumed == 0:
+                    want = min(chunk_bytes, fill + line_len)     # an incomplete line: read on
+                else:
+                    want = min(chunk_bytes, max(rest + 1, min_lines * line_len))
+                fill = rest
         finally:
             buf.close()
 
     # ---- raw sample streams (`thrifty detect --raw`): no host-side re-blocking
     def detect_raw_stream(self, stream, chunk_blocks=4096):
         """Yield (detected, DetectionResult) for every block of a raw uint8 I/Q stream
-        (block_data.py:70-98 semantics: block b = H samples of history + N-H new samples; the first
-        block's history is zeros; a trailing partial block is dropped).  The overlapping windows are
-        read in place on the GPU (thr_detect_stream), only new samples are copied."""
+        (block_data.py:70-98 semantics: block b = H samples of history + N-H new samples; the history
+        that precedes the stream is complex zeros; a trailing partial block is dropped).  The
+        overlapping windows are read in place on the GPU (thr_detect_stream), only new samples are
+        copied.  The first ceil(H / (N-H)) blocks reach back before the start of the stream: their
+        zero history has no uint8 representation, so they go through the complex64 entry point.
+        Whatever a read returns is processed (at most `chunk_blocks` blocks per launch): on a live
+        pipe the latency is one block, not one batch."""
         import time
-        n, h = self.settings.block_len, self.settings.history_len
-        new = 2 * (n - h)
-        read = getattr(stream, "read1", stream.read)
-
-        def read_exact(nbytes):
-            parts, got = [], 0
-            while got < nbytes:
-                data = read(nbytes - got)
-                if not data:
-                    break
-                parts.append(data)
-                got += len(data)
-            return b"".join(parts)
-
-        first = read_exact(new)
-        if len(first) < new:
-            return
         from thrifty_b200.block_data import raw_to_complex
-        block0 = np.concatenate([np.zeros(h, dtype=np.complex64),
-                                 raw_to_complex(np.frombuffer(first, dtype=np.uint8))])
-        yield self.detect(time.time(), 0, block0)[:2]
-        tail = np.frombuffer(first, dtype=np.uint8)[new - 2 * h:] if h else np.zeros(0, dtype=np.uint8)
-        next_block = 1
-        while True:
-            data = read_exact(chunk_blocks * new)
-            nblk = len(data) // new
-            if nblk == 0:
-                break
-            buf = np.concatenate([tail, np.frombuffer(data[:nblk * new], dtype=np.uint8)])
-            recs = self.native.detect_stream(buf, next_block)
-            now = time.time()
-            for pair in records_to_results(recs[:nblk, 0], now, self.rxid):
-                yield pair
-            tail = buf[len(buf) - 2 * h:] if h else np.zeros(0, dtype=np.uint8)
-            next_block += nblk
-            if len(data) < chunk_blocks * new:
-                break
+        n, h = self.settings.block_len, self.settings.history_len
+        new_s = n - h                                # new samples per block
+        read = getattr(stream, "read1", None) or stream.read
+        buf = np.zeros(0, dtype=np.uint8)            # stream bytes from sample `pos` on
+        pos = 0                                      # global index of the first sample held in buf
+        blk = 0                                      # next block to emit
+        eof = False
+        while not eof:
+            data = read(2 * new_s * chunk_blocks)
+            if not data:
+                eof = True
+            else:
+                buf = np.concatenate([buf, np.frombuffer(data, dtype=np.uint8)])
+            n_avail = (pos + len(buf) // 2) // new_s - blk          # complete blocks not yet emitted
+            # blocks whose history starts before the stream: explicit zero history, complex path
+            while n_avail > 0 and blk * new_s - h < 0:
+                assert pos == 0
+                real = raw_to_complex(buf[:2 * (blk + 1) * new_s])
+                block = np.concatenate([np.zeros(n - len(real), dtype=np.complex64), real])
+                yield self.detect(time.time(), blk, block)[:2]
+                blk += 1
+                n_avail -= 1
+            while n_avail > 0:
+                nb = min(n_avail, chunk_blocks)
+                first = blk * new_s - h                              # first sample of block blk
+                sub = buf[2 * (first - pos):2 * ((blk + nb) * new_s - pos)]
+                recs = self.native.detect_stream(sub, blk)
+                now = time.time()
+                for pair in records_to_results(recs[:nb, 0], now, self.rxid):
+                    yield pair
+                blk += nb
+                n_avail -= nb
+            keep = max(pos, blk * new_s - h)                         # history of the next block stays
+            if keep > pos:
+                buf = buf[2 * (keep - pos):]
+                pos = keep
 
     # ---- iterator protocol (detect.py:80-91)
     def next(self):
@@ -373,6 +400,9 @@ def detector_cli(detector_class, parser=None, extra_args=None, argv=None):
     parser.add_argument("--batch", dest="batch", type=int, default=256,
                         help="blocks per GPU launch (read-ahead) [default: 256]")
     parser.add_argument("--device", dest="device", type=int, default=0, help="CUDA device ordinal")
+    parser.add_argument("--devices", dest="devices", type=parse_devices, default=None,
+                        help="several GPUs, e.g. 0-7 or 0,2,3: every batch is striped across them "
+                             "(same output, same order)")
     parser.add_argument("--host-decode", dest="host_decode", action="store_true",
                         help="decode the .card base64 payloads on the host (reference behaviour) "
                              "instead of on the GPU")
@@ -383,7 +413,27 @@ def detector_cli(detector_class, parser=None, extra_args=None, argv=None):
                        help="Output file to append to (.toad)")
     setting_keys = ["sample_rate", "block_size", "block_history", "carrier_window",
                     "carrier_threshold", "corr_threshold", "template", "rxid"]
-    config, args = load_args(parser, setting_keys, argv=argv)
+    # `--template a.npy --template b.npy ...`: the setting itself takes one file (the first); repeating the option
+    # correlates against all of them jointly (one .toad line per template that detects, txid = position of the template)
+    argv = list(sys.argv[1:] if argv is None else argv)
+    templates, kept, i = [], [], 0
+    while i < len(argv):
+        arg = argv[i]
+        if arg in ("--template", "-z") and i + 1 < len(argv):
+            templates.append(argv[i + 1])
+            if len(templates) == 1:
+                kept += argv[i:i + 2]
+            i += 2
+            continue
+        if arg.startswith("--template="):
+            templates.append(arg.split("=", 1)[1])
+            if len(templates) == 1:
+                kept.append(arg)
+            i += 1
+            continue
+        kept.append(arg)
+        i += 1
+    config, args = load_args(parser, setting_keys, argv=kept)
 
     kwargs = {}
     if extra_args is not None:
@@ -404,6 +454,11 @@ def detector_cli(detector_class, parser=None, extra_args=None, argv=None):
     if issubclass(detector_class, Detector):
         kwargs.setdefault("batch", args.batch)
         kwargs.setdefault("device", args.device)
+        if args.devices:
+            kwargs.setdefault("devices", args.devices)
+    if detector_class is Detector and len(templates) > 1:
+        _multi_template_cli(settings, [np.load(t) for t in templates], blocks, config, args, output_file, info_out)
+        return
     detections = detector_class(settings, blocks, rxid=config.rxid, **kwargs)
     if detector_class is Detector and not args.raw and not args.host_decode:
         # fast path: the `.card` text is decoded on the GPU (same records, same order)
@@ -420,6 +475,48 @@ def detector_cli(detector_class, parser=None, extra_args=None, argv=None):
             print(summary_liner(detected, result), file=info_out)
     if output_file is not None:
         output_file.flush()
+
+
+def parse_devices(text):
+    """'0-7' / '0,2,3' / '1' -> list of CUDA ordinals."""
+    out = []
+    for part in str(text).split(","):
+        lo, sep, hi = part.strip().partition("-")
+        out.extend(range(int(lo), int(hi) + 1) if sep else [int(lo)])
+    if not out or len(set(out)) != len(out):
+        raise argparse.ArgumentTypeError("bad device list %r" % (text,))
+    return out
+
+
+def _multi_template_cli(settings, templates, blocks, config, args, output_file, info_out):
+    """`detect --template a.npy --template b.npy ...`: joint correlation (MultiTemplateDetector); every template that
+    detects writes its own .toad line with txid = position of the template on the command line."""
+    lens = set(len(t) for t in templates)
+    if len(lens) != 1:
+        raise SystemExit("all templates must have the same length (got %s)" % sorted(lens))
+    det = MultiTemplateDetector(settings, np.stack(templates), rxid=config.rxid, batch=args.batch,
+                                device=args.devices[0] if args.devices else args.device)
+    summary_liner = SummaryLineFormatter(config.sample_rate, config.block_size, add_dt=True)
+    items = []
+
+    def flush():
+        for per_tpl in det.detect_many(items):
+            for detected, result in per_tpl:
+                if detected and output_file is not None:
+                    print(result.serialize(), file=output_file)
+                if not args.quiet:
+                    print("tpl=%d; %s" % (result.txid, summary_liner(detected, result)), file=info_out)
+        del items[:]
+
+    for item in blocks:
+        items.append(item)
+        if len(items) >= args.batch:
+            flush()
+    if items:
+        flush()
+    if output_file is not None:
+        output_file.flush()
+    det.close()
 
 
 def _main(argv=None):
