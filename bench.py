@@ -7,8 +7,12 @@
 
 A "step" is one pass of the detect hot path over one batch (4096 blocks of 16384 complex
 samples) of synthetic .card payloads.  `value` = blocks/s x block_len / 1e6 with the inputs
-resident in HBM; `e2e` = the same through thr_detect_batch() with pinned HOST buffers (H2D of
-raw blocks + D2H of records inside the timed region).
+resident in HBM; `e2e` = the same through the product API with pinned HOST buffers (H2D of raw
+blocks + D2H of records inside the timed region): thr_detect_batch() on one GPU, and with N GPUs
+the multi-GPU handle (thr_group_detect_batch: rank 0 drives all N GPUs, one host thread and one
+contiguous stripe per GPU).  `sustained` repeats `value` over >= 1.2 s of launches; `cli_e2e` is
+the wall clock of the `detect` command line on a synthetic .card; with N GPUs `stripe_parity`
+says that a probe striped over the ranks and all-gathered over NCCL equals one GPU's records.
 
 The oracle (oracle/thrifty_oracle.py, NumPy restatement of the reference) is executed here ONLY
 for the `cpu_baseline` leg and the `--impl reference` arm.
@@ -41,6 +45,21 @@ def workload_name(args):
     return ("detect: synthetic .card payloads, block_len=%d, history=%d, example template L=4914, "
             "window 7-110, thresholds 15*snr, batch=%d, %d%% burst blocks"
             % (args.block_len, HISTORY, args.batch, round(100 * args.p_signal)))
+
+
+def bench_config(args):
+    """`config` of the JSON line: the same keys and values on both arms (ours and --impl reference)."""
+    return {"workload": workload_name(args), "block_len": args.block_len, "history_len": HISTORY, "batch": args.batch,
+            "p_signal": args.p_signal, "template": "example (L=4914)", "window": list(WINDOW), "thresholds": "15*snr / 15*snr"}
+
+
+def port_vs_reference():
+    """profiles/port_vs_reference.json (written in the build container by oracle/port_vs_reference.py): how the NumPy
+    restatement timed here compares with the reference's own Detector on the same blocks."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "port_vs_reference.json")))
+    except Exception:
+        return None
 
 
 def make_unique_blocks(n_unique, p_signal, seed):
@@ -184,19 +203,27 @@ def run_reference_arm(args):
         dt = time.perf_counter() - t0
     ms_per_step = dt / args.steps * 1e3
     value = sample * BLOCK_LEN / (ms_per_step / 1e3) / 1e6
+    pvr = port_vs_reference()
     line = {
         "impl": "reference",
         "metric": "detect Msamples/s (block_len=16384)", "value": value, "unit": "Msamples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64 (numpy)",
         "data": "synthetic",
-        "config": {"workload": workload_name(args), "block_len": BLOCK_LEN, "batch": args.batch,
-                   "sample_blocks_per_step": sample},
+        "config": bench_config(args),
+        "details": {"sample_blocks_per_step": sample},
         "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": "port",
                          "sample": "%d blocks per step x %d steps of the same synthetic workload, "
                                    "NumPy/SciPy restatement of thrifty.detect.Detector.detect "
-                                   "(numpy %s pocketfft), %d worker processes"
-                                   % (sample, args.steps, np.__version__, cores)},
+                                   "(numpy %s pocketfft), %d worker processes; port vs the reference's own Detector in the "
+                                   "build container: %s"
+                                   % (sample, args.steps, np.__version__, cores,
+                                      ("%.2f ms vs %.2f ms per block (port %.0f %% %s)" % (
+                                          pvr["port_ms_per_block"], pvr["reference_ms_per_block"],
+                                          abs(pvr["reference_ms_per_block"] / pvr["port_ms_per_block"] - 1) * 100,
+                                          "faster" if pvr["port_ms_per_block"] < pvr["reference_ms_per_block"] else "slower"))
+                                      if pvr else "not recorded"),
+                         "port_vs_reference": pvr},
         "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -232,10 +259,69 @@ def bind_to_gpu_numa_node(local_rank):
         return None
 
 
+PROBE_BLOCKS = 4096        # fixed probe of the stripe-parity check (multi-GPU)
+
+
+def load_profile_json(name):
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", name)))
+    except Exception:
+        return None
+
+
+def h2d_ceiling(n_gpus):
+    """profiles/r02_h2d_concurrent.jsonl (tools/microbench/h2d_concurrent.cu on the scaling node): best aggregate pinned
+    host->device bandwidth measured with n_gpus GPUs copying at once, or None."""
+    best = None
+    try:
+        for line in open(os.path.join(ROOT, "profiles", "r02_h2d_concurrent.jsonl")):
+            line = line.strip()
+            if line.startswith("{"):
+                row = json.loads(line)
+                if row.get("gpus") == n_gpus:
+                    best = max(best or 0.0, float(row["aggregate_h2d_gbs"]))
+    except Exception:
+        return None
+    return best
+
+
+def cli_e2e(tpl, raw_unique, n_blocks, device):
+    """Wall-clock blocks/s of the command line (`python -m thrifty_b200 detect file.card -o out.toad --quiet`) on a
+    synthetic .card of n_blocks lines; interpreter start-up and imports excluded (detector_cli is called in-process),
+    everything else -- opening the file, reading text, GPU base64 decode + detect, .toad text -- included."""
+    import tempfile
+    from thrifty_b200 import block_data
+    from thrifty_b200.detect import Detector, detector_cli
+    tmp = tempfile.mkdtemp(prefix="thrifty_b200_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        card, toad, cfg, tplf = (os.path.join(tmp, f) for f in ("x.card", "x.toad", "d.cfg", "t.npy"))
+        np.save(tplf, tpl)
+        with open(card, "w") as f:
+            block_data.write_card(f, raw_unique[np.arange(n_blocks) % len(raw_unique)])
+        with open(cfg, "w") as f:
+            f.write("block_size: %d\nblock_history: %d\ncarrier_window: %d - %d\ncarrier_threshold: 15*snr\n"
+                    "corr_threshold: 15*snr\ntemplate: %s\n" % (BLOCK_LEN, HISTORY, WINDOW[0], WINDOW[1], tplf))
+        argv = [card, "-c", cfg, "-o", toad, "--quiet", "--batch", "4096", "--device", str(device)]
+        detector_cli(Detector, argv=argv)                       # warm-up: page cache, CUDA context, staging buffers
+        t0 = time.perf_counter()
+        detector_cli(Detector, argv=argv)
+        dt = time.perf_counter() - t0
+        n_lines = sum(1 for _ in open(toad))
+        return {"value": n_blocks / dt, "unit": "blocks/s", "msamples_per_s": n_blocks * BLOCK_LEN / dt / 1e6,
+                "blocks": n_blocks, "seconds": dt, "card_bytes": os.path.getsize(card), "toad_lines": n_lines,
+                "what": "thrifty_b200.detect.detector_cli(Detector) in-process on a synthetic .card in /dev/shm: file read + "
+                        "GPU base64 decode + detect + .toad text; interpreter start-up and imports excluded"}
+    except Exception as e:      # noqa: BLE001  (the bench line must still come out)
+        return {"error": "%s: %s" % (type(e).__name__, e)}
+    finally:
+        import shutil
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from thrifty_b200._native import NativeDetector, PinnedBuffer, RECORD_DTYPE
+    from thrifty_b200._native import NativeDetector, NativeGroup, PinnedBuffer, RECORD_DTYPE
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -245,6 +331,7 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
+    cpu_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL / c10d print their version banner on stdout when the communicator is created:
@@ -256,6 +343,7 @@ def run_ours(args):
             dist.init_process_group("nccl", device_id=dev)
             dist.all_reduce(torch.zeros(1, device=dev))
             torch.cuda.synchronize()
+            cpu_group = dist.new_group(backend="gloo")      # host-side barriers (no kernel spinning on the GPUs)
         finally:
             sys.stdout.flush()
             os.dup2(saved_stdout, 1)
@@ -300,6 +388,11 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def host_barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=cpu_group)
+
     def timed(k, gather=True):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
@@ -341,38 +434,125 @@ def run_ours(args):
     # kernel-only timing for the roofline (same launches, no gather)
     ms_kernel = timed(args.steps, gather=False) / args.steps if world > 1 else ms_per_step
 
+    # ---- sustained: at least args.sustained_seconds of back-to-back launches with its own clock record
+    sustained = None
+    if args.sustained_seconds > 0:
+        k_sus = max(args.steps, int(args.sustained_seconds * 1e3 / ms_per_step) + 1)
+        s2 = ClockSampler(local_rank)
+        s2.start()
+        time.sleep(0.25)
+        t0w = time.time()
+        ms_sus = timed(k_sus, gather=True)
+        t1w = time.time()
+        clk2 = s2.stop(t0w, t1w)
+        sustained = {"value": world * batch * n * k_sus / (ms_sus * 1e-3) / 1e6, "unit": "Msamples/s", "steps": k_sus,
+                     "seconds": ms_sus * 1e-3, "ms_per_step": ms_sus / k_sus, "clocks": clk2}
+
     # records sanity: every block of the last batch must carry a decision
     torch.cuda.synchronize()
     recs = np.frombuffer(recs2[(args.steps - 1) % GATHER_EVERY].cpu().numpy().tobytes(), dtype=RECORD_DTYPE)
     n_det = int(((recs["flags"] & 2) != 0).sum())
     n_car = int(((recs["flags"] & 1) != 0).sum())
 
-    # ---- e2e: host (pinned) buffers through thr_detect_batch, copies inside the timed region
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    hbuf = [PinnedBuffer(batch * 2 * n) for _ in range(2)]
-    hidx = [PinnedBuffer(batch * 8) for _ in range(2)]
-    hout = [PinnedBuffer(batch * 64) for _ in range(2)]
-    lib = det._lib
-    for b in range(2):
-        src = uniq[(np.arange(batch) + b * 7) % len(uniq)]
-        hbuf[b].array[:] = src.reshape(-1)
-        hidx[b].array.view(np.int64)[:] = np.arange(batch) + b * batch
-    for b in range(2):   # warm-up
-        det._check(lib.thr_detect_batch(det.handle, hbuf[b].ptr, hidx[b].ptr, batch, hout[b].ptr))
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        b = i & 1
-        det._check(lib.thr_detect_batch(det.handle, hbuf[b].ptr, hidx[b].ptr, batch, hout[b].ptr))
-    torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    # ---- stripe parity (multi-GPU): one fixed probe striped over the ranks, records all-gathered over NCCL, compared
+    # byte for byte with rank 0's single-GPU records of the whole probe
+    stripe_parity = None
+    identify_leg = None
     if world > 1:
-        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-    e2e_value = world * batch * n / (e2e_ms * 1e-3) / 1e6
-    e2e_recs = hout[(e2e_steps - 1) & 1].array.view(RECORD_DTYPE)
-    e2e_det = int(((e2e_recs["flags"] & 2) != 0).sum())
+        _, probe_u = make_unique_blocks(256, 0.7, synth.SEED0 + 424242)           # same probe on every rank
+        probe = probe_u[np.arange(PROBE_BLOCKS) % len(probe_u)]
+        per = (PROBE_BLOCKS + world - 1) // world
+        lo, hi = min(per * rank, PROBE_BLOCKS), min(per * (rank + 1), PROBE_BLOCKS)
+        part = torch.from_numpy(np.ascontiguousarray(probe[lo:hi])).to(dev)
+        pidx = torch.arange(lo, hi, dtype=torch.int64, device=dev)
+        mine = torch.zeros(per * 64, dtype=torch.uint8, device=dev)
+        if hi > lo:
+            det.detect_device(part.data_ptr(), pidx.data_ptr(), hi - lo, mine.data_ptr())
+        allrec = torch.zeros(world * per * 64, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allrec, mine)
+        torch.cuda.synchronize()
+        if rank == 0:
+            whole = det.detect_raw(probe, np.arange(PROBE_BLOCKS))[:, 0]
+            got = np.frombuffer(allrec.cpu().numpy().tobytes(), dtype=RECORD_DTYPE)[:PROBE_BLOCKS]
+            stripe_parity = bool(got.tobytes() == whole.tobytes())
+            # the consumer of the gathered records: `identify` on the device (txid by carrier-bin window, duplicate
+            # filter over adjacent blocks) must give the same survivors from the gathered records as from one GPU's
+            from thrifty_b200 import identify as dev_identify
+            ts_probe = 1000.0 + 0.0047767 * np.arange(PROBE_BLOCKS)
+            sel_g, tx_g = dev_identify.integrate_records(got, ts_probe, 0, None, device=local_rank)
+            sel_1, tx_1 = dev_identify.integrate_records(whole, ts_probe, 0, None, device=local_rank)
+            identify_leg = {"detections": int(((got["flags"] & 2) != 0).sum()), "kept": int(len(sel_g)),
+                            "transmitters": int(len(set(tx_g.tolist()))),
+                            "equal_single_gpu": bool(np.array_equal(sel_g, sel_1) and np.array_equal(tx_g, tx_1))}
+        del part, pidx, mine, allrec
+
+    # ---- e2e: HOST buffers through the product API, copies inside the timed region.
+    # 1 GPU: thr_detect_batch with pinned buffers.  N GPUs: rank 0 drives all N through the multi-GPU handle
+    # (thr_group_detect_batch: one host thread + stripe per GPU, NUMA-placed pinned input), the other ranks idle at a
+    # host-side barrier -- this is the product's multi-GPU path, not N independent benchmarks.
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    e2e_extra = {}
+    host_barrier()
+    if world == 1:
+        hbuf = [PinnedBuffer(batch * 2 * n) for _ in range(2)]
+        hidx = [PinnedBuffer(batch * 8) for _ in range(2)]
+        hout = [PinnedBuffer(batch * 64) for _ in range(2)]
+        lib = det._lib
+        for b in range(2):
+            src = uniq[(np.arange(batch) + b * 7) % len(uniq)]
+            hbuf[b].array[:] = src.reshape(-1)
+            hidx[b].array.view(np.int64)[:] = np.arange(batch) + b * batch
+        for b in range(2):   # warm-up
+            det._check(lib.thr_detect_batch(det.handle, hbuf[b].ptr, hidx[b].ptr, batch, hout[b].ptr))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            b = i & 1
+            det._check(lib.thr_detect_batch(det.handle, hbuf[b].ptr, hidx[b].ptr, batch, hout[b].ptr))
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+        e2e_recs = hout[(e2e_steps - 1) & 1].array.view(RECORD_DTYPE)
+        e2e_det = int(((e2e_recs["flags"] & 2) != 0).sum())
+        e2e_api = "thr_detect_batch (pinned host buffers)"
+        for b in hbuf + hidx + hout:
+            b.close()
+    elif rank == 0:
+        grp = NativeGroup(list(range(world)), n, HISTORY, tpl, len(tpl), WINDOW, THRESH, THRESH, max_batch=batch)
+        lib = grp._lib
+        total = world * batch
+        bufs = []
+        for b in range(2):
+            ptr = lib.thr_group_host_alloc(grp._g, batch * 2 * n)
+            assert ptr, "thr_group_host_alloc failed"
+            arr = np.ctypeslib.as_array((ctypes_u8() * (total * 2 * n)).from_address(ptr))
+            arr[:] = uniq[(np.arange(total) + b * 7) % len(uniq)].reshape(-1)
+            bufs.append((ptr, arr))
+        hidx = [PinnedBuffer(total * 8) for _ in range(2)]
+        hout = [PinnedBuffer(total * 64) for _ in range(2)]
+        for b in range(2):
+            hidx[b].array.view(np.int64)[:] = np.arange(total) + b * total
+        for b in range(2):   # warm-up
+            grp.detect_raw_ptr(bufs[b][0], total, hidx[b].ptr, hout[b].ptr)
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            b = i & 1
+            grp.detect_raw_ptr(bufs[b][0], total, hidx[b].ptr, hout[b].ptr)
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+        e2e_recs = hout[(e2e_steps - 1) & 1].array.view(RECORD_DTYPE)
+        e2e_det = int(((e2e_recs["flags"] & 2) != 0).sum())
+        # the striped records must be what one GPU returns for the same blocks
+        chk = det.detect_raw(bufs[(e2e_steps - 1) & 1][1].reshape(total, 2 * n)[:batch],
+                             hidx[(e2e_steps - 1) & 1].array.view(np.int64)[:batch])[:, 0]
+        e2e_extra["group_records_equal_single_gpu"] = bool(chk.tobytes() == e2e_recs[:batch].tobytes())
+        e2e_extra["numa_nodes"] = grp.numa_nodes()
+        e2e_api = "thr_group_detect_batch (rank 0 drives %d GPUs: one host thread + stripe per GPU, pinned host buffers)" % world
+        for ptr, arr in bufs:
+            del arr
+            lib.thr_group_host_free(grp._g, ptr, batch * 2 * n)
+        for b in hidx + hout:
+            b.close()
+        grp.close()
+    host_barrier()
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -383,63 +563,90 @@ def run_ours(args):
             peak, peak_src = 6650.0, "fallback from B200_PROFILING.md"
         alg_bytes = batch * (2 * n + 64)                   # raw u8 in + 64-B record out, per launch
         achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
-        traffic = None
-        prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if os.path.exists(prof):
-            try:
-                traffic = json.load(open(prof)).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
-        # the binding resource is the FP32 pipe, not HBM: algorithmic flops = 3 FFTs x 5 N log2 N + 40 N
-        # pointwise per block, against 148 SMs x 128 lanes x 2 flop x the SM clock sampled during the timed region
+        traffic = (load_profile_json("ncu_traffic.json") or {}).get("dram_bytes_per_launch")
+        # the binding resource is the FP32 pipe, not HBM.  Two flop counts per launch:
+        #   algorithmic = 3 FFTs x 5 N log2 N + 40 N pointwise per block (the SURVEY's convention; FFT#1 counted in full
+        #                 although this configuration prunes it)
+        #   executed    = what the kernel's instruction stream really performs (ncu opcode mix of the same command:
+        #                 32 lanes x (4 per FFMA2, 2 per FADD2/FMUL2/FFMA/DFMA, 1 per FADD/FMUL), profiles/r02_opcode_mix.json)
+        # against 148 SMs x 128 lanes x 2 flop x the SM clock sampled during the timed region
         alg_flops = batch * (3 * 5 * n * int(np.log2(n)) + 40 * n)
         fp32_peak = 148 * 128 * 2 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e12
         fp32_ach = alg_flops / (ms_kernel * 1e-3) / 1e12
+        mix = load_profile_json("r02_opcode_mix.json")
+        exe_flops = batch * mix["executed_flops_per_block"] if mix else None
         fma_pipe = None
         try:
-            m = json.load(open(os.path.join(ROOT, "profiles", "r01b_final_ncu_summary.json")))["metrics"]
+            m = load_profile_json("r02_final_ncu_summary.json")["metrics"]
             fma_pipe = float(m["sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"]["value"]) / 100.0
         except Exception:
             pass
+        e2e_bytes = world * batch * (2 * n + 8)
+        ceiling = h2d_ceiling(world)
+        e2e_gbs = e2e_bytes / (e2e_ms * 1e-3) / 1e9
         line = {
             "metric": "detect Msamples/s (block_len=16384)", "value": value, "unit": "Msamples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "precision_note": "float32 transforms and decisions throughout (the reference: float32 FFT#1, complex128 from the "
+                              "mix on), float64 Dirichlet fit (MINPACK lmdif, as the reference); within the 1e-4 parity bar",
             "data": "synthetic",
-            "config": {"workload": workload_name(args), "block_len": n, "batch": batch,
-                       "pool_blocks_per_gpu": pool_blocks,
-                       "l2_policy": "inputs larger than L2: %d MiB raw pool cycled per GPU" % (pool_blocks * 2 * n >> 20),
-                       "kernel": info["kernel"], "grid": info["grid"], "threads": info["threads"],
-                       "smem_bytes": info["smem_bytes"], "parallelism": "stripe%d" % world, "numa_node_rank0": numa_node, "record_gather": ("all_gather of the 64-B record ring every %d steps" % GATHER_EVERY) if world > 1 else "none (1 GPU)",
-                       "carrier_detected_last_batch": n_car, "corr_detected_last_batch": n_det,
-                       "blocks_per_s": world * batch / (ms_per_step * 1e-3)},
+            "config": bench_config(args),
+            "details": {"pool_blocks_per_gpu": pool_blocks,
+                        "l2_policy": "inputs larger than L2: %d MiB raw pool cycled per GPU" % (pool_blocks * 2 * n >> 20),
+                        "kernel": info["kernel"], "grid": info["grid"], "threads": info["threads"],
+                        "smem_bytes": info["smem_bytes"], "parallelism": "stripe%d" % world, "numa_node_rank0": numa_node,
+                        "record_gather": ("all_gather of the 64-B record ring every %d steps" % GATHER_EVERY) if world > 1 else "none (1 GPU)",
+                        "carrier_detected_last_batch": n_car, "corr_detected_last_batch": n_det,
+                        "blocks_per_s": world * batch / (ms_per_step * 1e-3)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "kernel_ms_per_launch": ms_kernel,
                          "fp32": {"achieved": fp32_ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_ach / fp32_peak,
                                   "algorithmic_flops_per_launch": alg_flops,
+                                  "executed_flops_per_launch": exe_flops,
+                                  "executed_achieved": (exe_flops / (ms_kernel * 1e-3) / 1e12) if exe_flops else None,
+                                  "executed_frac": (exe_flops / (ms_kernel * 1e-3) / 1e12 / fp32_peak) if exe_flops else None,
+                                  "executed_source": "profiles/r02_opcode_mix.json (tools/ncu_opcodes.py on the ncu capture of this command)",
                                   "fma_pipe_cycles_active_ncu": fma_pipe},
                          "note": "fused kernel is FP32-issue/shared-memory bound (~125 FLOP/B), see DESIGN.md"},
-            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": batch * (2 * n + 8),
-                    "d2h_bytes_per_step": batch * 64, "ms_per_step": e2e_ms, "steps": e2e_steps,
-                    "api": "thr_detect_batch (pinned host buffers)", "corr_detected_last_batch": e2e_det},
+            "e2e": dict({"value": world * batch * n / (e2e_ms * 1e-3) / 1e6, "unit": "Msamples/s",
+                         "h2d_bytes_per_step": e2e_bytes, "d2h_bytes_per_step": world * batch * 64,
+                         "ms_per_step": e2e_ms, "steps": e2e_steps, "api": e2e_api, "corr_detected_last_batch": e2e_det,
+                         "h2d_gbs": e2e_gbs, "h2d_ceiling_gbs": ceiling,
+                         "frac_of_h2d_ceiling": (e2e_gbs / ceiling) if ceiling else None,
+                         "h2d_ceiling_source": "profiles/r02_h2d_concurrent.jsonl (tools/microbench/h2d_concurrent.cu, "
+                                               "%d GPUs copying at once)" % world}, **e2e_extra),
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if sustained:
+            line["sustained"] = sustained
+        if stripe_parity is not None:
+            line["stripe_parity"] = stripe_parity
+            line["identify_on_gathered_records"] = identify_leg
+        if args.cli and world == 1:
+            line["cli_e2e"] = cli_e2e(tpl, uniq, args.cli_blocks, local_rank)
         if args.cpu_baseline and world == 1:
             rate, done = cpu_oracle_rate_single(uniq[np.arange(4096) % len(uniq)], max_seconds=args.cpu_seconds)
+            pvr = port_vs_reference()
             line["cpu_baseline"] = {
                 "value": rate * n / 1e6, "unit": "Msamples/s", "cores": 1, "kind": "port",
                 "sample": "%d blocks (~%.0f s) of the same workload, single process, NumPy/SciPy restatement of "
-                          "thrifty.detect.Detector.detect (numpy %s pocketfft, scipy curve_fit)" % (done, args.cpu_seconds, np.__version__),
-                "blocks_per_s": rate, "host_cores_available": os.cpu_count()}
+                          "thrifty.detect.Detector.detect (numpy %s pocketfft, scipy curve_fit); the reference's own Detector "
+                          "takes %s x the port's time per block (profiles/port_vs_reference.json)"
+                          % (done, args.cpu_seconds, np.__version__, ("%.2f" % pvr["reference_over_port"]) if pvr else "?"),
+                "blocks_per_s": rate, "host_cores_available": os.cpu_count(), "port_vs_reference": pvr}
         print(json.dumps(line))
-    for b in hbuf + hidx + hout:
-        b.close()
     det.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def ctypes_u8():
+    import ctypes
+    return ctypes.c_uint8
 
 
 def main():
@@ -457,6 +664,10 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=16)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--sustained-seconds", type=float, default=1.2,
+                    help="length of the extra back-to-back run reported as `sustained` (0: skip)")
+    ap.add_argument("--no-cli", dest="cli", action="store_false", help="skip the command-line wall-clock leg (cli_e2e)")
+    ap.add_argument("--cli-blocks", type=int, default=4096)
     args = ap.parse_args()
     if args.block_len != BLOCK_LEN:
         raise SystemExit("bench.py measures the headline config (block_len=16384); use tools/sweep.py for others")

@@ -217,11 +217,11 @@ int thr_soa_batch(thr_detector *det, const float *fft, const int64_t *block_idx,
                   float *corr);
 
 /* ---- several GPUs behind one handle (thrifty/detect.py:217-223: the loop over blocks is the seam) ----
- * The detect path has no cross-block state, so a batch shards into contiguous stripes, one per GPU, with no data-path
- * collective: one thr_detector + one host thread per device; stripe g = blocks [g * ceil(B/G), (g+1) * ceil(B/G)); every
- * stripe's records land in its slice of the caller's array, so `out` is in input order exactly as from one GPU (and
- * byte-identical to it).  Raw streams are striped with an H-sample halo at each stripe start, `.card` text at line
- * boundaries.  `devices` are CUDA ordinals; the config's own `device` field is ignored.  Worker threads pin themselves to
+ * The detect path has no cross-block state, so a batch shards into contiguous pieces with no data-path collective: one
+ * thr_detector + one host thread per device.  thr_group_detect_batch hands out chunks of the batch from one counter (a GPU
+ * behind a slower PCIe path takes fewer), raw streams are cut into one stripe per GPU with an H-sample halo at each stripe
+ * start, `.card` text into one stripe per GPU at line boundaries.  Every piece's records land at its blocks' positions in
+ * the caller's array, so `out` is in input order exactly as from one GPU (and byte-identical to it).  `devices` are CUDA ordinals; the config's own `device` field is ignored.  Worker threads pin themselves to
  * the CPUs of their GPU's NUMA node when sysfs exposes it; thr_group_host_alloc returns page-locked memory of
  * n_devices * bytes_per_device bytes whose g-th part lives on the g-th GPU's node (part size rounded up to the page size:
  * use thr_group_size() * bytes_per_device only when bytes_per_device is a multiple of 4096). */
@@ -241,6 +241,31 @@ int  thr_group_detect_card(thr_group *grp, const char *text, size_t len, int32_t
                            int64_t *consumed);
 void *thr_group_host_alloc(thr_group *grp, size_t bytes_per_device);
 void  thr_group_host_free(thr_group *grp, void *p, size_t bytes_per_device);
+
+/* ---- `identify`: the step after detect (thrifty/identify.py:26-166) on the GPU ----
+ * Columns of detections (one value per detection; any order, any number of receivers), host pointers in and out:
+ *   thr_identify_classify       identify.py:106-118 classify_transmitters: txid = the last frequency-map range
+ *                               (map_rxid, map_txid, [map_start, map_stop] in bins, receiver offset already added) that
+ *                               contains carrier_bin + carrier_offset, else -1
+ *   thr_identify_bin_histogram  identify.py:39-41: carrier-bin histogram of one receiver (first_bin = its smallest bin);
+ *                               counts == NULL only queries first_bin / n_bins.  The caller scans the counts for peaks
+ *                               (identify.py:43-61, a sequential pass over ~100 bins) and passes the edges to
+ *   thr_identify_digitize       identify.py:98-99: txid = np.digitize(carrier_bin, edges) - 1 for that receiver's rows
+ *   thr_identify_duplicates     identify.py:134-164 identify_duplicates: keep[i] = 0 for unidentified detections and for
+ *                               the weaker of two detections in adjacent blocks that are neighbours in (rxid, txid, block,
+ *                               timestamp) order (cyclic neighbours, as np.roll; `block` is int32 as in toads_array)
+ * Errors: negative status, message from thr_identify_last_error(). */
+int thr_identify_classify(int32_t device, int64_t n, const int32_t *rxid, const int32_t *carrier_bin,
+                          const double *carrier_offset, int32_t n_map, const int32_t *map_rxid, const int32_t *map_txid,
+                          const double *map_start, const double *map_stop, int32_t *txid_out);
+int thr_identify_bin_histogram(int32_t device, int64_t n, const int32_t *rxid, const int32_t *carrier_bin,
+                               int32_t which_rxid, int32_t *first_bin, int32_t *n_bins, uint32_t *counts,
+                               int32_t counts_cap);
+int thr_identify_digitize(int32_t device, int64_t n, const int32_t *rxid, const int32_t *carrier_bin, int32_t which_rxid,
+                          int32_t n_edges, const int64_t *edges, int32_t *txid_inout);
+int thr_identify_duplicates(int32_t device, int64_t n, const int32_t *rxid, const int32_t *txid, const int32_t *block,
+                            const double *timestamp, const double *energy, uint8_t *keep_out);
+const char *thr_identify_last_error(void);
 
 /* ---- stream / timing plumbing ---- */
 int thr_set_stream(thr_detector *det, void *cuda_stream);   /* NULL -> handle's own stream */

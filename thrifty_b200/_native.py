@@ -64,6 +64,8 @@ EXPORTS = [
     "thr_group_create", "thr_group_destroy", "thr_group_last_error", "thr_group_size", "thr_group_member",
     "thr_group_numa_node", "thr_group_detect_batch", "thr_group_detect_stream", "thr_group_detect_card",
     "thr_group_host_alloc", "thr_group_host_free",
+    "thr_identify_classify", "thr_identify_bin_histogram", "thr_identify_digitize", "thr_identify_duplicates",
+    "thr_identify_last_error",
 ]
 
 _lib = None

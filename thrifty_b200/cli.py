@@ -8,7 +8,7 @@ HELP = """usage: thrifty_b200 <command> [<args>]
 
     detect   Detect positioning signals in .card / raw data and estimate SoA (GPU)
     fastdet  Same job with the semantics and options of the reference's native `fastdet` (GPU)
-    identify Merge .toad files, identify transmitters by carrier bin, drop duplicates -> .toads (host)
+    identify Merge .toad files, identify transmitters by carrier bin, drop duplicates -> .toads (CUDA kernels)
     synth    Write a synthetic .card file (see SURVEY.md 8d)
 
 Use 'thrifty_b200 help <command>' for a command's arguments."""

@@ -18,6 +18,7 @@
 #include <sys/syscall.h>
 #include <unistd.h>
 
+#include <atomic>
 #include <cmath>
 #include <complex>
 #include <condition_variable>
@@ -654,8 +655,11 @@ static int slot_queue_records(thr_detector *d, Slot &s, thr_record *dst, size_t 
     return THR_OK;
 }
 
+// cursor != NULL: the chunks of this call are drawn from a counter shared with other handles (thr_group_detect_batch: the
+// GPUs of a group take chunks of one batch as fast as their PCIe paths deliver them); records still land at their
+// block's position in `out`.
 static int detect_host(thr_detector *d, const uint8_t *raw, const float *iq, const int64_t *block_idx,
-                       int64_t n_blocks, thr_record *out) {
+                       int64_t n_blocks, thr_record *out, std::atomic<int64_t> *cursor = nullptr) {
     if (!d || (!raw && !iq) || !out || n_blocks < 0) return d ? fail(d, THR_ERR_INVALID, "null/negative argument") : THR_ERR_INVALID;
     CU(d, cudaSetDevice(d->device));
     const int N = d->cfg.block_len, NT = d->cfg.n_templates;
@@ -669,7 +673,8 @@ static int detect_host(thr_detector *d, const uint8_t *raw, const float *iq, con
     const bool pageable = is_pageable(raw ? (const void *)raw : (const void *)iq);
     if (int rc0 = slots_reset(d)) return rc0;
     int c = 0;
-    for (int64_t b0 = 0; b0 < n_blocks; b0 += chunk, ++c) {
+    for (int64_t b0 = cursor ? cursor->fetch_add(chunk) : 0; b0 < n_blocks;
+         b0 = cursor ? cursor->fetch_add(chunk) : b0 + chunk, ++c) {
         Slot &s = d->slot[c & 1];
         const int nb = (int)((n_blocks - b0) < chunk ? (n_blocks - b0) : chunk);
         int rc = slot_flush(d, s);                 // chunk c-2 done: its records go to the caller, staging is free
@@ -1333,20 +1338,12 @@ static inline void stripe_of(int64_t n, int G, int g, int64_t *lo, int64_t *hi) 
 
 int thr_group_detect_batch(thr_group *g, const uint8_t *raw, const int64_t *block_idx, int64_t n_blocks, thr_record *out) {
     if (!g || !raw || !out || n_blocks < 0) return THR_ERR_INVALID;
-    const int G = (int)g->w.size();
-    const int64_t N = g->cfg.block_len, NT = g->cfg.n_templates;
-    return group_run(g, [&](int i, thr_detector *d) -> int {
-        int64_t lo, hi;
-        stripe_of(n_blocks, G, i, &lo, &hi);
-        if (hi <= lo) return THR_OK;
-        std::vector<int64_t> idx;
-        const int64_t *ip = block_idx ? block_idx + lo : nullptr;
-        if (!ip) {                                   // default indices are global positions, not positions in the stripe
-            idx.resize((size_t)(hi - lo));
-            for (int64_t b = lo; b < hi; ++b) idx[(size_t)(b - lo)] = b;
-            ip = idx.data();
-        }
-        return thr_detect_batch(d, raw + (size_t)lo * 2 * N, ip, hi - lo, out + (size_t)lo * NT);
+    // Contiguous chunks handed out from one counter: a GPU behind a slower PCIe path (or busy with something else) simply
+    // takes fewer of them, so the batch finishes when the host link is saturated, not when the slowest stripe is done.
+    // Every chunk's records are written at its blocks' positions in `out`: input order, whoever computed them.
+    std::atomic<int64_t> cursor(0);
+    return group_run(g, [&](int, thr_detector *d) -> int {
+        return detect_host(d, raw, nullptr, block_idx, n_blocks, out, &cursor);
     });
 }
 
