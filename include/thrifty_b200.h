@@ -267,6 +267,15 @@ int thr_identify_duplicates(int32_t device, int64_t n, const int32_t *rxid, cons
                             const double *timestamp, const double *energy, uint8_t *keep_out);
 const char *thr_identify_last_error(void);
 
+/* ---- .toad text (thrifty/toads_data.py:47-61 DetectionResult.serialize; detect.py:218-219 writes detected blocks only) ----
+ * Formats the records with THR_FLAG_CORR_DETECTED among recs[0], recs[stride], ... (n blocks; stride = n_templates) as
+ * "{rxid} [{txid} ]{t:.6f} {block} {soa:.8f} {sample} {offset} {energy} {noise} {bin} {offset} {energy} {noise}\n", the
+ * free-format fields exactly as Python prints them (shortest round-trip digits, CPython's layout).  txids == NULL writes
+ * a .toad; otherwise a .toads line with txids[i] (toads_data.py:57-60).  cap must hold 1024 bytes per detected record;
+ * THR_ERR_NOMEM with *used = that size otherwise.  Host-side; several threads for large n. */
+int thr_format_toad(const thr_record *recs, const double *timestamps, int64_t n, int64_t stride, int32_t rxid,
+                    const int32_t *txids, char *buf, size_t cap, size_t *used);
+
 /* ---- stream / timing plumbing ---- */
 int thr_set_stream(thr_detector *det, void *cuda_stream);   /* NULL -> handle's own stream */
 int thr_synchronize(thr_detector *det);

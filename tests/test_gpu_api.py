@@ -218,6 +218,17 @@ def test_cli_card_to_toad(tmp_path):
         assert abs(float(fg[5]) - float(fw[5])) < 1e-4 and abs(float(fg[9]) - float(fw[9])) < 1e-4
         for i in (6, 7, 10, 11):
             assert abs(float(fg[i]) / float(fw[i]) - 1) < 1e-4
+    # --quiet: no result objects, native .toad text (thr_format_toad), reader thread -- the same file, byte for byte
+    out = subprocess.run([sys.executable, "-m", "thrifty_b200", "detect", "rx.card", "-o", "rx_quiet.toad", "--batch", "16",
+                          "--quiet"], cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout == "", out.stderr
+    assert open(str(tmp_path / "rx_quiet.toad")).read() == open(str(tmp_path / "rx.toad")).read()
+    # ... and from a pipe (no seekable file: sequential reads, small pieces)
+    with open(str(tmp_path / "rx.card"), "rb") as f:
+        out = subprocess.run([sys.executable, "-m", "thrifty_b200", "detect", "-", "-o", "rx_pipe.toad", "--batch", "16",
+                              "--quiet"], cwd=str(tmp_path), env=env, stdin=f, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert open(str(tmp_path / "rx_pipe.toad")).read() == open(str(tmp_path / "rx.toad")).read()
 
 
 @pytest.mark.parametrize("block_len,n_blocks,seed", [(16384, 192, 1), (8192, 128, 2), (4096, 128, 3),
@@ -459,6 +470,42 @@ def test_multi_template_n16384_gold11x4_vs_reference_golden():
         assert np.all(recs[:, t]["template_idx"] == t)
         parity.compare_records(recs[:, t], ref[t], what="gold11x4 records template %d" % t)
     det.close()
+
+
+def test_raw_stream_card_export(tmp_path):
+    """`detect --raw --card-out`: every carrier-positive block of the stream is re-exported as a .card line
+    (fastcard/fastcard_cli.c:171-193); detecting that .card gives the same records as the stream did."""
+    from thrifty_b200.detect import Detector, DetectorSettings
+    tpl = synth.gold_template(9)
+    n, hist = 4096, len(tpl) + 6
+    new = n - hist
+    nblk = 60
+    rng = np.random.default_rng(77)
+    total = nblk * new
+    x = 0.02 * (rng.standard_normal(total) + 1j * rng.standard_normal(total))
+    pos = 900
+    while pos + len(tpl) < total:
+        t = np.arange(len(tpl))
+        x[pos:pos + len(tpl)] += 0.3 * (tpl + 1) / 2 * np.exp(2j * np.pi * rng.uniform(8, 109) * (t + pos) / n)
+        pos += int(rng.uniform(2.2, 4.0) * new)
+    stream = synth.complex_to_raw(x).tobytes()
+    st = DetectorSettings(n, hist, len(tpl), (0., 15., 0.), (7, 110), tpl, (0., 15., 0.))
+    det = Detector(st, rxid=0, batch=16)
+    card = io.StringIO()
+    from_stream = list(det.detect_raw_stream(io.BytesIO(stream), chunk_blocks=16, card_out=card))
+    det.close()
+    assert len(from_stream) == nblk
+    with_carrier = [r for _, r in from_stream if r.corr_info is not None]
+    assert 10 <= len(with_carrier) < nblk
+    lines = card.getvalue().splitlines()
+    assert len(lines) == len(with_carrier)
+    det2 = Detector(st, block_data.card_reader(io.StringIO(card.getvalue()), raw=True), rxid=0, batch=16)
+    from_card = list(det2)
+    det2.close()
+    assert [r.block for _, r in from_card] == [r.block for r in with_carrier]
+    for (d1, r1), r0 in zip(from_card, with_carrier):
+        assert r1.corr_info is not None and r1.soa == r0.soa and r1.carrier_info.bin == r0.carrier_info.bin
+        assert r1.corr_info == r0.corr_info
 
 
 def test_smoke_entry():

@@ -439,3 +439,43 @@ def test_card_stream_short_prefix_lines_are_not_dropped():
     finally:
         nat.PinnedBuffer = saved
     assert [r.block for _, r in out] == list(range(57))
+
+
+def test_native_toad_text_equals_python_serialize():
+    """thr_format_toad (host code of the library, no GPU involved) writes, character for character, what
+    DetectionResult.serialize() (toads_data.py:47-61) gives for the result objects built from the same records --
+    including numpy.float32's own switch to exponent notation at 1e6, nan / inf, zero, and .toads lines with a txid."""
+    from thrifty_b200 import _native
+    from thrifty_b200.detect import records_to_results
+    rng = np.random.default_rng(5)
+    n = 30000
+    recs = np.zeros(n, dtype=_native.RECORD_DTYPE)
+    recs["flags"] = rng.choice([0, 1, 3], n, p=[0.1, 0.1, 0.8])
+    recs["block_idx"] = rng.integers(-5, 1 << 40, n)
+
+    def mix(dt):
+        v = np.exp(rng.uniform(-25, 40, n)) * rng.choice([-1, 1], n)
+        sel = rng.random(n) < 0.1
+        v[sel] = np.round(v[sel])
+        v[rng.random(n) < 0.02] = 0
+        return v.astype(dt)
+    recs["soa"] = mix(np.float64) * 1e3
+    for f in ("carrier_offset", "carrier_energy", "carrier_noise", "corr_offset", "corr_energy", "corr_noise"):
+        recs[f] = mix(np.float32)
+    edge = np.array([1e-4, 1e6, 999999.94, 1e-5, 1e16, 9.999999e15, 123.0, 0.5, 1e22, 2.5e-5, np.inf, -np.inf, np.nan])
+    for f in ("carrier_offset", "carrier_energy", "corr_energy", "corr_noise"):
+        recs[f][:len(edge)] = edge.astype(np.float32)
+    recs["soa"][:len(edge)] = edge
+    recs["flags"][:len(edge)] = 3
+    recs["carrier_bin"] = rng.integers(0, 16384, n)
+    recs["corr_sample"] = rng.integers(0, 16384, n)
+    ts = 1.48e9 + np.cumsum(rng.uniform(0, 0.01, n))
+    results = [r for d, r in records_to_results(recs, ts, 7) if d]
+    want = "".join(r.serialize() + "\n" for r in results).encode()
+    assert _native.format_toad(recs, ts, 7) == want
+    assert _native.format_toad(np.stack([recs, recs], axis=1), ts, 7) == want        # [B, T]: template 0
+    tx = rng.integers(-1, 5, n).astype(np.int32)
+    for r, t in zip(results, tx[(recs["flags"] & 2) != 0]):
+        r.txid = int(t)
+    assert _native.format_toad(recs, ts, 7, txids=tx) == "".join(r.serialize() + "\n" for r in results).encode()
+    assert _native.format_toad(recs[:0], ts[:0], 7) == b""

@@ -65,7 +65,7 @@ EXPORTS = [
     "thr_group_numa_node", "thr_group_detect_batch", "thr_group_detect_stream", "thr_group_detect_card",
     "thr_group_host_alloc", "thr_group_host_free",
     "thr_identify_classify", "thr_identify_bin_histogram", "thr_identify_digitize", "thr_identify_duplicates",
-    "thr_identify_last_error",
+    "thr_identify_last_error", "thr_format_toad",
 ]
 
 _lib = None
@@ -114,33 +114,44 @@ def load_library(path=None):
     lib.thr_detect_stream.restype = c_int
     lib.thr_detect_stream_device.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_void_p]
     lib.thr_detect_stream_device.restype = c_int
-    lib.thr_sync_batch.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]
-    lib.thr_sync_batch.restype = c_int
-    lib.thr_soa_batch.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]
-    lib.thr_soa_batch.restype = c_int
-    lib.thr_group_create.argtypes = [POINTER(ThrConfig), POINTER(c_int32), c_int32, POINTER(c_void_p)]
-    lib.thr_group_create.restype = c_int
-    lib.thr_group_destroy.argtypes = [c_void_p]
-    lib.thr_group_destroy.restype = None
-    lib.thr_group_last_error.argtypes = [c_void_p]
-    lib.thr_group_last_error.restype = c_char_p
-    lib.thr_group_size.argtypes = [c_void_p]
-    lib.thr_group_size.restype = c_int
-    lib.thr_group_member.argtypes = [c_void_p, c_int32]
-    lib.thr_group_member.restype = c_void_p
-    lib.thr_group_numa_node.argtypes = [c_void_p, c_int32, POINTER(c_int32)]
-    lib.thr_group_numa_node.restype = c_int
-    lib.thr_group_detect_batch.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]
-    lib.thr_group_detect_batch.restype = c_int
-    lib.thr_group_detect_stream.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_void_p, POINTER(c_int64)]
-    lib.thr_group_detect_stream.restype = c_int
-    lib.thr_group_detect_card.argtypes = [c_void_p, c_char_p, c_size_t, c_int32, c_int64, c_void_p, c_void_p, c_void_p,
-                                          POINTER(c_int64), POINTER(c_int64)]
-    lib.thr_group_detect_card.restype = c_int
-    lib.thr_group_host_alloc.argtypes = [c_void_p, c_size_t]
-    lib.thr_group_host_alloc.restype = c_void_p
-    lib.thr_group_host_free.argtypes = [c_void_p, c_void_p, c_size_t]
-    lib.thr_group_host_free.restype = None
+    try:
+        lib.thr_format_toad.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p, c_size_t,
+                                        POINTER(c_size_t)]
+        lib.thr_format_toad.restype = c_int
+    except AttributeError:
+        if path == LIB_PATH:
+            raise
+    try:        # entry points added in round 2 (an older experiment build selected by THRIFTY_B200_LIB may lack them)
+        lib.thr_sync_batch.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]
+        lib.thr_sync_batch.restype = c_int
+        lib.thr_soa_batch.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]
+        lib.thr_soa_batch.restype = c_int
+        lib.thr_group_create.argtypes = [POINTER(ThrConfig), POINTER(c_int32), c_int32, POINTER(c_void_p)]
+        lib.thr_group_create.restype = c_int
+        lib.thr_group_destroy.argtypes = [c_void_p]
+        lib.thr_group_destroy.restype = None
+        lib.thr_group_last_error.argtypes = [c_void_p]
+        lib.thr_group_last_error.restype = c_char_p
+        lib.thr_group_size.argtypes = [c_void_p]
+        lib.thr_group_size.restype = c_int
+        lib.thr_group_member.argtypes = [c_void_p, c_int32]
+        lib.thr_group_member.restype = c_void_p
+        lib.thr_group_numa_node.argtypes = [c_void_p, c_int32, POINTER(c_int32)]
+        lib.thr_group_numa_node.restype = c_int
+        lib.thr_group_detect_batch.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]
+        lib.thr_group_detect_batch.restype = c_int
+        lib.thr_group_detect_stream.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_void_p, POINTER(c_int64)]
+        lib.thr_group_detect_stream.restype = c_int
+        lib.thr_group_detect_card.argtypes = [c_void_p, c_char_p, c_size_t, c_int32, c_int64, c_void_p, c_void_p, c_void_p,
+                                              POINTER(c_int64), POINTER(c_int64)]
+        lib.thr_group_detect_card.restype = c_int
+        lib.thr_group_host_alloc.argtypes = [c_void_p, c_size_t]
+        lib.thr_group_host_alloc.restype = c_void_p
+        lib.thr_group_host_free.argtypes = [c_void_p, c_void_p, c_size_t]
+        lib.thr_group_host_free.restype = None
+    except AttributeError:
+        if path == LIB_PATH:
+            raise
     lib.thr_set_stream.argtypes = [c_void_p, c_void_p]
     lib.thr_set_stream.restype = c_int
     lib.thr_synchronize.argtypes = [c_void_p]
@@ -164,6 +175,27 @@ def load_library(path=None):
     if path == LIB_PATH:
         _lib = lib
     return lib
+
+
+def format_toad(records, timestamps, rxid, txids=None):
+    """thr_record array [B] or [B, T] (template 0 is used) + timestamps [B] -> bytes of .toad lines for the detected
+    blocks (thr_format_toad: the text DetectionResult.serialize() would give, formatted natively)."""
+    lib = load_library()
+    records = np.ascontiguousarray(records)
+    stride = 1 if records.ndim == 1 else records.shape[1]
+    n = records.shape[0]
+    ts = np.ascontiguousarray(np.broadcast_to(np.asarray(timestamps, dtype=np.float64), (n,)))
+    tx = None if txids is None else np.ascontiguousarray(txids, dtype=np.int32)
+    if n == 0:
+        return b""
+    n_det = int(((records.reshape(n, -1)[:, 0]["flags"] & FLAG_CORR) != 0).sum())
+    buf = ctypes.create_string_buffer(max(1, n_det * 1024))
+    used = c_size_t(0)
+    rc = lib.thr_format_toad(records.ctypes.data, ts.ctypes.data, n, stride, int(rxid),
+                             None if tx is None else tx.ctypes.data, buf, len(buf), byref(used))
+    if rc != THR_OK:
+        raise NativeError("thr_format_toad failed (%d)" % rc)
+    return buf.raw[:used.value]
 
 
 class PinnedBuffer(object):

@@ -475,7 +475,13 @@ constexpr double QUICK_MAX_LOBE = 24.0;    // short cut only for N / W <= 24 bin
 // D(z) = sin(pi W z / N) / (W sin(pi z / N)) and dD/dz at z = x - offset (carrier_sync.py:121-132); z == 0: (1, 0)
 THR_HD void kernel_deriv(double z, double piW, double N, double W, double &D, double &Dz) {
     const double t1 = (piW * z) / N, t2 = (3.141592653589793 * z) / N;
-    const double s1 = sin(t1), c1 = cos(t1), s2 = sin(t2), c2 = cos(t2);
+    double s1, c1, s2, c2;
+#if defined(__CUDA_ARCH__)
+    sincos(t1, &s1, &c1);           // one range reduction per angle
+    sincos(t2, &s2, &c2);
+#else
+    s1 = sin(t1), c1 = cos(t1), s2 = sin(t2), c2 = cos(t2);
+#endif
     D = s1 / s2 / W;
     Dz = ((piW / N) * c1 * s2 - (3.141592653589793 / N) * s1 * c2) / (s2 * s2) / W;
     if (D != D) {

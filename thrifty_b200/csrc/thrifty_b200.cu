@@ -19,6 +19,7 @@
 #include <unistd.h>
 
 #include <atomic>
+#include <charconv>
 #include <cmath>
 #include <complex>
 #include <condition_variable>
@@ -33,6 +34,8 @@
 #include <thread>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>            // header-only NVTX v3: ranges show up in Nsight Systems / ncu --nvtx, cost ~nothing otherwise
+
 #include "../../include/thrifty_b200.h"
 #include "detect_kernel.cuh"
 #include "variants.h"
@@ -42,6 +45,12 @@ using thr::DetectParams;
 using thr::Variant;
 
 namespace {
+
+// NVTX range for one phase of a host-buffer call (stage / H2D / launch / D2H + records), closed at scope exit
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 thread_local std::string g_create_error;
 
@@ -617,6 +626,7 @@ static bool is_pageable(const void *p) {
 // ~10 GB/s and blocks the calling thread.  Copying the chunk into page-locked staging ourselves (several threads) runs at
 // 25+ GB/s and leaves the DMA truly asynchronous, so it overlaps the kernel of the other slot.
 static int stage_pageable(thr_detector *d, Slot &s, const void **src, size_t bytes, size_t cap_hint) {
+    NvtxRange r("thr: pageable input -> page-locked staging");
     if (s.h_in_cap < bytes) {
         if (s.h_in) cudaFreeHost(s.h_in);
         s.h_in = nullptr;
@@ -677,8 +687,13 @@ static int detect_host(thr_detector *d, const uint8_t *raw, const float *iq, con
          b0 = cursor ? cursor->fetch_add(chunk) : b0 + chunk, ++c) {
         Slot &s = d->slot[c & 1];
         const int nb = (int)((n_blocks - b0) < chunk ? (n_blocks - b0) : chunk);
-        int rc = slot_flush(d, s);                 // chunk c-2 done: its records go to the caller, staging is free
+        int rc;
+        {
+            NvtxRange r("thr: records of chunk c-2 -> caller");
+            rc = slot_flush(d, s);                 // chunk c-2 done: its records go to the caller, staging is free
+        }
         if (rc != THR_OK) return rc;
+        NvtxRange r_chunk("thr: chunk (stage, H2D, launch, D2H queued)");
         const void *src = raw ? (const void *)(raw + (size_t)b0 * 2 * N) : (const void *)(iq + (size_t)b0 * 2 * N);
         const size_t bytes = raw ? (size_t)nb * 2 * N : (size_t)nb * N * 8;
         if (pageable) {
@@ -704,6 +719,7 @@ static int detect_host(thr_detector *d, const uint8_t *raw, const float *iq, con
 
 int thr_detect_batch(thr_detector *d, const uint8_t *raw, const int64_t *block_idx, int64_t n_blocks,
                      thr_record *out) {
+    NvtxRange r("thr_detect_batch");
     if (!raw) return d ? fail(d, THR_ERR_INVALID, "raw is NULL") : THR_ERR_INVALID;
     return detect_host(d, raw, nullptr, block_idx, n_blocks, out);
 }
@@ -991,6 +1007,7 @@ int thr_detect_card(thr_detector *d, const char *text, size_t len, int32_t final
                     int64_t *consumed) {
     if (!d || !text || !timestamps || !block_idx || !out || !n_blocks || !consumed)
         return d ? fail(d, THR_ERR_INVALID, "null argument") : THR_ERR_INVALID;
+    NvtxRange r_call("thr_detect_card");
     CU(d, cudaSetDevice(d->device));
     const int N = d->cfg.block_len, NT = d->cfg.n_templates;
     const int64_t want = ((2 * (int64_t)N + 2) / 3) * 4;
@@ -1013,8 +1030,11 @@ int thr_detect_card(thr_detector *d, const char *text, size_t len, int32_t final
     for (int c = 0; b0 < max_blocks; ++c) {
         const int64_t ask = (max_blocks - b0) < chunk ? (max_blocks - b0) : chunk;
         int64_t got = 0, used = 0, bad_line = -1;
-        rc = card_scan_lines(text + pos, len - (size_t)pos, N, final_chunk, ask, timestamps + b0, block_idx + b0, off.data(),
-                             &got, &used, &bad_line, &lines);
+        {
+            NvtxRange r("thr: scan .card line headers");
+            rc = card_scan_lines(text + pos, len - (size_t)pos, N, final_chunk, ask, timestamps + b0, block_idx + b0, off.data(),
+                                 &got, &used, &bad_line, &lines);
+        }
         if (rc != THR_OK)
             return fail(d, rc, ".card data line %lld is malformed (expected '<time> <index> <%lld base64 chars>')",
                         (long long)bad_line, (long long)want);
@@ -1106,6 +1126,7 @@ int thr_detect_stream_device(thr_detector *d, const uint8_t *d_stream, int64_t n
 int thr_detect_stream(thr_detector *d, const uint8_t *stream, int64_t n_stream_bytes, int64_t first_block,
                       thr_record *out, int64_t *n_blocks_out) {
     if (!d || !stream || !out || !n_blocks_out) return d ? fail(d, THR_ERR_INVALID, "null argument") : THR_ERR_INVALID;
+    NvtxRange r_call("thr_detect_stream");
     CU(d, cudaSetDevice(d->device));
     const int64_t N = d->cfg.block_len, H = d->cfg.history_len, stride = 2 * (N - H);
     const int NT = d->cfg.n_templates;
@@ -1433,6 +1454,158 @@ void thr_group_host_free(thr_group *g, void *p, size_t bytes_per_device) {
     const size_t part = (bytes_per_device + page - 1) / page * page;
     cudaHostUnregister(p);
     munmap(p, part * g->w.size());
+}
+
+// ---- .toad text (thrifty/toads_data.py:47-61) ------------------------------------------------------------------
+// One line per detected block: "{rxid} {t:.6f} {block} {soa:.8f} {sample} {offset} {energy} {noise} {bin} {coffset}
+// {cenergy} {cnoise}".  The fields without a format spec are what Python's str() prints for the values the Python layer
+// holds (thrifty_b200/detect.py records_to_results): float32 record fields widened to Python floats print as the shortest
+// string that round-trips the DOUBLE, the carrier energy / noise stay numpy.float32 (as in the reference) and print as the
+// shortest string that round-trips the FLOAT.  Same digits as CPython / numpy (all are shortest-round-trip), same layout
+// rule: fixed notation for 1e-4 <= |x| < 1e16 (numpy float32: < 1e6) with ".0" appended to integers, else d.ddde+XX.
+}  // extern "C"
+namespace {
+
+template <class F>
+char *py_float_str(char *out, F v) {
+    if (v != v) { std::memcpy(out, "nan", 3); return out + 3; }
+    if (std::isinf(v)) {
+        if (v < 0) *out++ = '-';
+        std::memcpy(out, "inf", 3);
+        return out + 3;
+    }
+    char sci[48];
+    const auto r = std::to_chars(sci, sci + sizeof sci, v, std::chars_format::scientific);   // shortest: d[.ddd]e[+-]XX
+    char *p = sci;
+    if (*p == '-') *out++ = *p++;
+    char digits[32];
+    int nd = 0;
+    digits[nd++] = *p++;
+    if (*p == '.') {
+        ++p;
+        while (*p != 'e') digits[nd++] = *p++;
+    }
+    ++p;                                           // 'e'
+    int e = 0;
+    std::from_chars(*p == '+' ? p + 1 : p, r.ptr, e);
+    if (nd == 1 && digits[0] == '0') { std::memcpy(out, "0.0", 3); return out + 3; }
+    const int decpt = e + 1;                       // position of the decimal point relative to the digit string
+    // exponent notation: CPython's repr of a float switches at 1e16, numpy's str of a float32 scalar at 1e6
+    // (CPython decides on the decimal exponent of the shortest digits, numpy on the value itself)
+    const double av = std::fabs((double)v);
+    const bool sci_notation = sizeof(F) == 4 ? (av >= 1e6 || av < 1e-4) : (decpt > 16 || decpt <= -4);
+    if (sci_notation) {
+        *out++ = digits[0];
+        if (nd > 1) {
+            *out++ = '.';
+            std::memcpy(out, digits + 1, (size_t)nd - 1);
+            out += nd - 1;
+        }
+        *out++ = 'e';
+        *out++ = e < 0 ? '-' : '+';
+        const int ae = e < 0 ? -e : e;
+        if (ae < 10) *out++ = '0';
+        out = std::to_chars(out, out + 8, ae).ptr;
+        return out;
+    }
+    if (decpt <= 0) {                              // 0.000ddd
+        *out++ = '0';
+        *out++ = '.';
+        for (int i = 0; i < -decpt; ++i) *out++ = '0';
+        std::memcpy(out, digits, (size_t)nd);
+        return out + nd;
+    }
+    if (decpt >= nd) {                             // ddd000.0
+        std::memcpy(out, digits, (size_t)nd);
+        out += nd;
+        for (int i = nd; i < decpt; ++i) *out++ = '0';
+        *out++ = '.';
+        *out++ = '0';
+        return out;
+    }
+    std::memcpy(out, digits, (size_t)decpt);       // dd.ddd
+    out += decpt;
+    *out++ = '.';
+    std::memcpy(out, digits + decpt, (size_t)(nd - decpt));
+    return out + (nd - decpt);
+}
+
+constexpr size_t TOAD_LINE_MAX = 1024;             // 10 fields of <= 26 characters + "%.6f" / "%.8f" of any double (<= 320 each)
+
+char *toad_line(char *o, const thr_record &r, double ts, int32_t rxid, int32_t txid) {
+    o = std::to_chars(o, o + 12, rxid).ptr;
+    *o++ = ' ';
+    if (txid != INT32_MIN) {                       // .toads: transmitter id after the receiver id (toads_data.py:57-60)
+        o = std::to_chars(o, o + 12, txid).ptr;
+        *o++ = ' ';
+    }
+    o = std::to_chars(o, o + 330, ts, std::chars_format::fixed, 6).ptr;          // "%.6f" (exact, like printf)
+    *o++ = ' ';
+    o = std::to_chars(o, o + 24, (long long)r.block_idx).ptr;
+    *o++ = ' ';
+    o = std::to_chars(o, o + 330, r.soa, std::chars_format::fixed, 8).ptr;       // "%.8f"
+    *o++ = ' ';
+    o = std::to_chars(o, o + 12, r.corr_sample).ptr;
+    *o++ = ' ';
+    o = py_float_str(o, (double)r.corr_offset);
+    *o++ = ' ';
+    o = py_float_str(o, (double)r.corr_energy);
+    *o++ = ' ';
+    o = py_float_str(o, (double)r.corr_noise);
+    *o++ = ' ';
+    o = std::to_chars(o, o + 12, r.carrier_bin).ptr;
+    *o++ = ' ';
+    o = py_float_str(o, (double)r.carrier_offset);
+    *o++ = ' ';
+    o = py_float_str(o, r.carrier_energy);         // numpy.float32 in the Python layer
+    *o++ = ' ';
+    o = py_float_str(o, r.carrier_noise);
+    *o++ = '\n';
+    return o;
+}
+
+}  // namespace
+extern "C" {
+
+// Formats the detected records (flags & THR_FLAG_CORR_DETECTED) of recs[0 .. n) (stride = records per block, template 0)
+// as .toad lines into buf; *used = bytes written.  txids: NULL for a .toad, else one transmitter id per record (.toads).
+// THR_ERR_NOMEM (and *used = bytes needed at most) if cap < n_detected * 1024.  Several threads for large n.
+int thr_format_toad(const thr_record *recs, const double *timestamps, int64_t n, int64_t stride, int32_t rxid,
+                    const int32_t *txids, char *buf, size_t cap, size_t *used) {
+    if (!recs || !timestamps || !used || n < 0 || stride < 1) return THR_ERR_INVALID;
+    int64_t n_det = 0;
+    for (int64_t i = 0; i < n; ++i) n_det += (recs[i * stride].flags & THR_FLAG_CORR_DETECTED) ? 1 : 0;
+    *used = (size_t)n_det * TOAD_LINE_MAX;
+    if (!buf || cap < *used) return THR_ERR_NOMEM;
+    int parts = (int)(n / 512);                    // ~0.5 ms of formatting per part
+    parts = parts < 1 ? 1 : (parts > 8 ? 8 : parts);
+    std::vector<char *> begin((size_t)parts), end((size_t)parts);
+    std::vector<std::thread> th;
+    int64_t det_before = 0;
+    for (int p = 0; p < parts; ++p) {
+        const int64_t lo = n * p / parts, hi = n * (p + 1) / parts;
+        char *o0 = buf + (size_t)det_before * TOAD_LINE_MAX;
+        for (int64_t i = lo; i < hi; ++i) det_before += (recs[i * stride].flags & THR_FLAG_CORR_DETECTED) ? 1 : 0;
+        begin[(size_t)p] = o0;
+        auto work = [=, &end] {
+            char *o = o0;
+            for (int64_t i = lo; i < hi; ++i) {
+                const thr_record &r = recs[i * stride];
+                if (r.flags & THR_FLAG_CORR_DETECTED) o = toad_line(o, r, timestamps[i], rxid, txids ? txids[i] : INT32_MIN);
+            }
+            end[(size_t)p] = o;
+        };
+        if (p + 1 < parts) th.emplace_back(work); else work();
+    }
+    for (auto &t : th) t.join();
+    char *o = buf;
+    for (int p = 0; p < parts; ++p) {              // close the gaps between the parts
+        const size_t len = (size_t)(end[(size_t)p] - begin[(size_t)p]);
+        if (begin[(size_t)p] != o) std::memmove(o, begin[(size_t)p], len);
+        o += len;
+    }
+    *used = (size_t)(o - buf);
+    return THR_OK;
 }
 
 void *thr_host_alloc(size_t bytes) {

@@ -36,6 +36,18 @@ DetectorSettings = namedtuple("DetectorSettings", [
     "template", "corr_thresh"])
 
 
+def _pread_full(fd, view, offset):
+    """pread until `view` is full or the file ends; returns the number of bytes read (the GIL is released in pread)."""
+    import os
+    got = 0
+    while got < len(view):
+        n = os.preadv(fd, [view[got:]], offset + got)
+        if n <= 0:
+            break
+        got += n
+    return got
+
+
 def record_to_result(rec, timestamp, rxid):
     """thr_record -> (detected, DetectionResult) with the reference's field types."""
     carrier_found = bool(rec["flags"] & FLAG_CARRIER)
@@ -188,62 +200,158 @@ class Detector(object):
         return records_to_results(recs[:, 0], [it[0] for it in items], self.rxid)
 
     # ---- whole `.card` streams: scan on the host, base64 decode + detect on the GPU
-    def detect_card_stream(self, stream, chunk_bytes=64 << 20, min_lines=None):
-        """Yield (detected, DetectionResult) for every data line of a binary `.card` stream.
+    def iter_card_records(self, stream, chunk_bytes=32 << 20, min_lines=None, read_threads=8):
+        """Yield (timestamps f8[B], block_idx i8[B], records [B, T]) per chunk of a binary `.card` stream.
 
-        Same results as iterating Detector(settings, card_reader(stream)) (block_data.py:101-131),
-        but the text goes to the GPU as is (thr_detect_card): no host-side base64 or rawconv.
-        Reads are accumulated until `min_lines` lines' worth of text (default: min(batch, 8)) or the
-        end of the stream is buffered, so a pipe that hands out 64 KB at a time does not cost one
-        launch per read; lower it (or --batch) for latency on live inputs."""
+        The text goes to the GPU as is (thr_detect_card: host jump-scan of the line headers, base64 decode and detect on
+        the device).  A reader thread fills one of two page-locked buffers while the GPU works on the other; a regular
+        file is read with `read_threads` parallel preads (one thread copies ~6 GB/s out of the page cache, eight ~21 on the
+        test hosts, the GPU path takes ~45; mapping the file instead costs a page fault per 4 KB and is 2x slower), a pipe
+        with whatever each read returns -- accumulated until `min_lines` lines' worth of text
+        (default min(batch, 8)) or the end of the stream is buffered, so a pipe that hands out 64 KB at a time does not
+        cost one launch per read; lower it (or --batch) for latency on live inputs.  Chunks are cut at line ends."""
+        import os
+        import queue
+        import stat
+        import threading
+        from concurrent.futures import ThreadPoolExecutor
         from thrifty_b200._native import PinnedBuffer
         line_len = ((2 * self.settings.block_len + 2) // 3) * 4 + 64
         chunk_bytes = max(int(chunk_bytes), 4 * line_len)
         if min_lines is None:
             min_lines = max(1, min(self.batch, 8))
         want = min(chunk_bytes, min_lines * line_len)
-        buf = PinnedBuffer(chunk_bytes + 1)      # page-locked: the text is DMA'd straight from here; one spare byte
-        view = buf.array                         # keeps the C number parser inside the allocation
-        view[chunk_bytes] = 0
-        fill = 0
-        read_into = getattr(stream, "readinto1", None) or getattr(stream, "readinto", None)
+        fd, regular = None, False
         try:
-            eof = False
-            while not eof or fill:
-                while not eof and fill < want:
-                    if read_into is not None:
-                        got = read_into(memoryview(view)[fill:chunk_bytes]) or 0
-                    else:
-                        data = stream.read(chunk_bytes - fill)
-                        if isinstance(data, str):
-                            data = data.encode("ascii")
-                        got = len(data)
-                        view[fill:fill + got] = np.frombuffer(data, dtype=np.uint8)
-                    eof = got == 0
-                    fill += got
-                if fill == 0:
+            fd = stream.fileno()
+            regular = stat.S_ISREG(os.fstat(fd).st_mode)
+        except (AttributeError, OSError, ValueError):
+            pass
+        read_into = getattr(stream, "readinto1", None) or getattr(stream, "readinto", None)
+        # two page-locked buffers (one spare byte keeps the C number parser inside the allocation), allocated by the
+        # reader thread when it first needs them: pinning 32 MB takes ~15 ms, which then overlaps the first chunk's GPU work
+        bufs = []
+        free_q, ready_q = queue.Queue(), queue.Queue()
+        stop = threading.Event()
+
+        def next_buffer():
+            try:
+                return free_q.get_nowait()
+            except queue.Empty:
+                if len(bufs) < 2:
+                    bufs.append(PinnedBuffer(chunk_bytes + 1))
+                    return bufs[-1]
+                return free_q.get()
+
+        def fill_regular(view, start, pool, pos):
+            """Parallel pread of [pos, pos + room) into view[start:]; returns the number of bytes read."""
+            room = chunk_bytes - start
+            part = max(1 << 20, -(-room // read_threads))
+            jobs = []
+            for off in range(0, room, part):
+                n = min(part, room - off)
+                jobs.append(pool.submit(_pread_full, fd, memoryview(view)[start + off:start + off + n], pos + off))
+            got = 0
+            for n_req, fut in zip([min(part, room - off) for off in range(0, room, part)], jobs):
+                n = fut.result()
+                got += n
+                if n < n_req:
                     break
-                view[fill] = 0
-                ts, idx, recs, consumed = self.native.detect_card_ptr(buf.ptr, fill, final=eof)
-                for pair in records_to_results(recs[:, 0], ts, self.rxid):
-                    yield pair
-                rest = fill - consumed
-                if rest:
-                    view[:rest] = view[consumed:fill].copy()
-                if eof and consumed == 0:
-                    break                        # nothing but an unparsable remainder is left
-                if not eof and consumed == 0 and fill >= chunk_bytes:
-                    raise ValueError(".card line longer than the %d-byte chunk buffer" % chunk_bytes)
-                if not eof and consumed == 0:
-                    want = min(chunk_bytes, fill + line_len)     # an incomplete line: read on
-                else:
-                    want = min(chunk_bytes, max(rest + 1, min_lines * line_len))
-                fill = rest
+            return got
+
+        def reader():
+            carry = b""
+            pos = 0
+            pool = ThreadPoolExecutor(read_threads) if regular else None
+            try:
+                if regular:
+                    pos = stream.tell()
+                eof = False
+                while not eof and not stop.is_set():
+                    buf = next_buffer()
+                    if buf is None:
+                        break
+                    view = buf.array
+                    fill = len(carry)
+                    if fill:
+                        view[:fill] = np.frombuffer(carry, dtype=np.uint8)
+                    if regular:
+                        got = fill_regular(view, fill, pool, pos)
+                        pos += got
+                        eof = got < chunk_bytes - fill
+                        fill += got
+                    else:
+                        target = max(want, fill + 1)
+                        while not eof and fill < target:
+                            if read_into is not None:
+                                got = read_into(memoryview(view)[fill:chunk_bytes]) or 0
+                            else:
+                                data = stream.read(chunk_bytes - fill)
+                                if isinstance(data, str):
+                                    data = data.encode("ascii")
+                                got = len(data)
+                                view[fill:fill + got] = np.frombuffer(data, dtype=np.uint8)
+                            eof = got == 0
+                            fill += got
+                    cut = fill
+                    if not eof:                  # cut behind the last complete line
+                        lo = max(0, fill - 2 * line_len)
+                        nl = np.flatnonzero(view[lo:fill] == 10)
+                        if len(nl) == 0 and lo > 0:
+                            nl, lo = np.flatnonzero(view[:fill] == 10), 0
+                        if len(nl) == 0:
+                            if fill >= chunk_bytes:
+                                raise ValueError(".card line longer than the %d-byte chunk buffer" % chunk_bytes)
+                            cut = 0              # not one complete line yet: read on
+                        else:
+                            cut = lo + int(nl[-1]) + 1
+                    carry = view[cut:fill].tobytes()
+                    view[cut] = 0
+                    ready_q.put((buf, cut, eof))
+            except BaseException as exc:         # noqa: BLE001  (handed to the consumer)
+                ready_q.put(exc)
+            finally:
+                if pool is not None:
+                    pool.shutdown()
+
+        thread = threading.Thread(target=reader, daemon=True)
+        thread.start()
+        try:
+            while True:
+                item = ready_q.get()
+                if isinstance(item, BaseException):
+                    raise item
+                buf, cut, eof = item
+                if cut:
+                    done = 0
+                    while done < cut:            # (a short max_blocks estimate only costs another call)
+                        ts, idx, recs, consumed = self.native.detect_card_ptr(buf.ptr + done, cut - done, final=True)
+                        if len(idx):
+                            yield ts, idx, recs
+                        if consumed == 0:
+                            break
+                        done += consumed
+                free_q.put(buf)
+                if eof:
+                    break
         finally:
-            buf.close()
+            stop.set()
+            free_q.put(None)
+            thread.join(timeout=5)
+            for b in bufs:
+                b.close()
+
+    def detect_card_stream(self, stream, chunk_bytes=32 << 20, min_lines=None):
+        """Yield (detected, DetectionResult) for every data line of a binary `.card` stream.
+
+        Same results as iterating Detector(settings, card_reader(stream)) (block_data.py:101-131), through
+        iter_card_records (no host-side base64 or rawconv)."""
+        for ts, _, recs in self.iter_card_records(stream, chunk_bytes, min_lines):
+            for pair in records_to_results(recs[:, 0], ts, self.rxid):
+                yield pair
 
     # ---- raw sample streams (`thrifty detect --raw`): no host-side re-blocking
-    def detect_raw_stream(self, stream, chunk_blocks=4096):
+    def detect_raw_stream(self, stream, chunk_blocks=4096, card_out=None):
         """Yield (detected, DetectionResult) for every block of a raw uint8 I/Q stream
         (block_data.py:70-98 semantics: block b = H samples of history + N-H new samples; the history
         that precedes the stream is complex zeros; a trailing partial block is dropped).  The
@@ -251,7 +359,11 @@ class Detector(object):
         copied.  The first ceil(H / (N-H)) blocks reach back before the start of the stream: their
         zero history has no uint8 representation, so they go through the complex64 entry point.
         Whatever a read returns is processed (at most `chunk_blocks` blocks per launch): on a live
-        pipe the latency is one block, not one batch."""
+        pipe the latency is one block, not one batch.
+        `card_out`: text stream; every carrier-positive block is also written to it as a `.card` line
+        ("<sec>.<usec> <block> <base64 of the 2N raw bytes>", fastcard/fastcard_cli.c:171-193 /
+        fastdet/fastdet.cpp:210-219), so the capture can be re-processed later -- the fastcard half of
+        the raw-stream front end."""
         import time
         from thrifty_b200.block_data import raw_to_complex
         n, h = self.settings.block_len, self.settings.history_len
@@ -273,7 +385,12 @@ class Detector(object):
                 assert pos == 0
                 real = raw_to_complex(buf[:2 * (blk + 1) * new_s])
                 block = np.concatenate([np.zeros(n - len(real), dtype=np.complex64), real])
-                yield self.detect(time.time(), blk, block)[:2]
+                now = time.time()
+                pair = self.detect(now, blk, block)[:2]
+                if card_out is not None and pair[1].corr_info is not None:      # carrier found
+                    from thrifty_b200.block_data import card_line, complex_to_raw
+                    card_out.write(card_line(now, blk, complex_to_raw(block)))
+                yield pair
                 blk += 1
                 n_avail -= 1
             while n_avail > 0:
@@ -282,6 +399,10 @@ class Detector(object):
                 sub = buf[2 * (first - pos):2 * ((blk + nb) * new_s - pos)]
                 recs = self.native.detect_stream(sub, blk)
                 now = time.time()
+                if card_out is not None:
+                    from thrifty_b200.block_data import card_line
+                    for k in np.nonzero(recs[:nb, 0]["flags"] & FLAG_CARRIER)[0]:
+                        card_out.write(card_line(now, blk + int(k), sub[2 * new_s * k:2 * new_s * k + 2 * n]))
                 for pair in records_to_results(recs[:nb, 0], now, self.rxid):
                     yield pair
                 blk += nb
@@ -406,6 +527,9 @@ def detector_cli(detector_class, parser=None, extra_args=None, argv=None):
     parser.add_argument("--host-decode", dest="host_decode", action="store_true",
                         help="decode the .card base64 payloads on the host (reference behaviour) "
                              "instead of on the GPU")
+    parser.add_argument("--card-out", dest="card_out", type=argparse.FileType("w"), default=None,
+                        help="with --raw: also write every carrier-positive block as a .card line to this file "
+                             "(what fastcard does while capturing)")
     group = parser.add_mutually_exclusive_group()
     group.add_argument("-o", "--output", dest="output", type=argparse.FileType("w"),
                        help="Output file (.toad) ('-' for stdout)")
@@ -460,13 +584,59 @@ def detector_cli(detector_class, parser=None, extra_args=None, argv=None):
         _multi_template_cli(settings, [np.load(t) for t in templates], blocks, config, args, output_file, info_out)
         return
     detections = detector_class(settings, blocks, rxid=config.rxid, **kwargs)
+    if detector_class is Detector and not args.raw and not args.host_decode and args.quiet:
+        # fastest path: nothing is printed per block, so no result objects are built either -- records go straight to
+        # .toad text (thr_format_toad: the same characters DetectionResult.serialize() produces)
+        from thrifty_b200._native import format_toad
+        import queue
+        import threading
+        sink = None
+        if output_file is not None:
+            output_file.flush()
+            sink = getattr(output_file, "buffer", None)
+        todo = queue.Queue(maxsize=8)
+        failed = []
+
+        def writer():                            # formats and writes chunk c while the GPU works on chunk c+1
+            try:
+                while True:
+                    item = todo.get()
+                    if item is None:
+                        return
+                    text = format_toad(item[0], item[1], config.rxid)
+                    if sink is not None:
+                        sink.write(text)
+                    else:
+                        output_file.write(text.decode("ascii"))
+            except BaseException as exc:         # noqa: BLE001
+                failed.append(exc)
+
+        wthread = threading.Thread(target=writer, daemon=True) if output_file is not None else None
+        if wthread is not None:
+            wthread.start()
+        try:
+            for ts, _, recs in detections.iter_card_records(args.input):
+                if wthread is not None and not failed:
+                    todo.put((recs, ts))
+        finally:
+            if wthread is not None:
+                todo.put(None)
+                wthread.join()
+        if failed:
+            raise failed[0]
+        if output_file is not None:
+            if sink is not None:
+                sink.flush()
+            output_file.flush()
+        detections.close()
+        return
     if detector_class is Detector and not args.raw and not args.host_decode:
         # fast path: the `.card` text is decoded on the GPU (same records, same order)
         detections = detections.detect_card_stream(args.input)
     elif detector_class is Detector and args.raw and not args.host_decode \
             and (2 * (config.block_size - config.block_history)) % 16 == 0:
         # fast path: overlapping windows are read in place from the contiguous stream
-        detections = detections.detect_raw_stream(args.input, chunk_blocks=max(args.batch, 1))
+        detections = detections.detect_raw_stream(args.input, chunk_blocks=max(args.batch, 1), card_out=args.card_out)
     summary_liner = SummaryLineFormatter(config.sample_rate, config.block_size, add_dt=True)
     for detected, result in detections:
         if detected and output_file is not None:
@@ -475,6 +645,8 @@ def detector_cli(detector_class, parser=None, extra_args=None, argv=None):
             print(summary_liner(detected, result), file=info_out)
     if output_file is not None:
         output_file.flush()
+    if args.card_out is not None:
+        args.card_out.flush()
 
 
 def parse_devices(text):
