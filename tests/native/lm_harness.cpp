@@ -23,12 +23,16 @@ extern "C" int lm_fit_host(const double *y, double W, double N, double *amplitud
 // the short cut (quick_fit): returns 1 if its result may stand in for lmdif's
 extern "C" int lm_quick_host(const double *y, double W, double N, double *amplitude, double *offset, double *slack) {
     const double piW = 3.141592653589793 * W;
-    auto derivs = [&](double d, double *g, double *gd) {
-        for (int i = 0; i < thr::lm::M; ++i) thr::lm::kernel_deriv((double)(i - 3) - d, piW, N, W, g[i], gd[i]);
+    auto derivs_d = [&](double d, double *D, double *Dz) {
+        for (int i = 0; i < thr::lm::M; ++i) thr::lm::kernel_deriv<double>((double)(i - 3) - d, piW, N, W, D[i], Dz[i]);
+    };
+    auto derivs_f = [&](float d, float *D, float *Dz) {
+        for (int i = 0; i < thr::lm::M; ++i)
+            thr::lm::kernel_deriv<float>((float)(i - 3) - d, (float)piW, (float)N, (float)W, D[i], Dz[i]);
     };
     thr::lm::Rows rows;
     for (int i = 0; i < thr::lm::M; ++i) rows.y[i] = y[i];
-    const thr::lm::Quick q = thr::lm::quick_fit(thr::lm::SerialExec(), derivs, rows, y[3], 0.0, N / W);
+    const thr::lm::Quick q = thr::lm::quick_fit(thr::lm::SerialExec(), derivs_f, derivs_d, rows, N / W);
     *amplitude = q.amplitude;
     *offset = q.offset;
     *slack = q.slack;

@@ -404,6 +404,68 @@ __device__ __forceinline__ RedOut block_reduce(float s0, float s1, unsigned long
 // lane runs the (scalar, warp-uniform) iteration; the 7 rows of the problem live in shared memory (lm::Rows), lane
 // r < 7 does the element-wise work of row r, lanes 8..14 evaluate the sines of the look-ahead offset.
 // y: magnitude of point (lane & 7).  Returns the offset.
+// lm::gn_fit for one warp: lane r (mod 8) < 7 owns point r, all four groups of 8 lanes compute the same thing.
+template <class T>
+struct GnWarp {
+    T A, d;
+    double slack;
+    unsigned pattern;
+    bool ok;
+};
+template <class T>
+__device__ __forceinline__ T xor_sum8(T v) {
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <class T>
+__device__ __forceinline__ GnWarp<T> gn_fit_warp(T y, int lane, T piW, T N, T W, T a0, T d0, T step_tol, int settle,
+                                                  unsigned pattern_in, int max_iter) {
+    const bool active = (lane & 7) < 7;
+    const T xi = (T)(min(lane & 7, 6) - 3);
+    T A = a0, d = d0;
+    GnWarp<T> q;
+    q.ok = false;
+    q.slack = 1.0;
+    q.pattern = pattern_in;
+    T cost_prev = (T)3e38;
+    T saa = 0, sdd = 0, sad = 0, cost = 0;
+    bool converged = false;
+#pragma unroll 1
+    for (int it = 0; it < max_iter; ++it) {
+        T D, Dz;
+        lm::kernel_deriv<T>(xi - d, piW, N, W, D, Dz);
+        const T g = active ? fabs(D) : (T)0, jd = active ? A * (D < (T)0 ? Dz : -Dz) : (T)0, r = active ? A * g - y : (T)0;
+        saa = xor_sum8(g * g);
+        sad = xor_sum8(g * jd);
+        sdd = xor_sum8(jd * jd);
+        const T sar = xor_sum8(g * r), sdr = xor_sum8(jd * r);
+        cost = xor_sum8(r * r);
+        const unsigned pattern = __ballot_sync(0xffffffffu, active && D < (T)0) & 0x7fu;
+        if (it == settle) q.pattern = pattern;
+        const T slop = sizeof(T) == 4 ? (T)1.00002 : (T)1.00000000001;
+        if (!(cost <= cost_prev * slop) || (it > settle - (settle == 0) && pattern != q.pattern)) break;
+        cost_prev = cost;
+        const T det = saa * sdd - sad * sad;
+        if (!(det > (T)0)) break;
+        const T dA = -(sdd * sar - sad * sdr) / det, dd = -(saa * sdr - sad * sar) / det;
+        A += dA;
+        d += dd;
+        if (it >= settle && fabs(dd) < step_tol && fabs(dA) <= step_tol * fabs(A)) {
+            converged = true;
+            break;
+        }
+    }
+    q.A = A;
+    q.d = d;
+    if (converged) {
+        const double det = (double)saa * (double)sdd - (double)sad * (double)sad;
+        q.slack = sqrt(2.0 * lm::TOL * (double)cost * ((double)saa / det));
+        q.ok = true;
+    }
+    return q;
+}
+
 struct WarpExec {                // lm::fit on one warp: lane r < 7 owns row r of the shared lm::Rows
     int lane;
     template <class F>
@@ -424,19 +486,23 @@ __device__ __forceinline__ float dirichlet_fit(float y, int lane, const DetectPa
         }
         __syncwarp();
     };
+#ifndef THR_EXP_NOQUICK
+    // short cut (dirichlet_lm.cuh, lm::quick_fit): Gauss-Newton to the least-squares minimum (float steps first, double
+    // to finish), accepted where lmdif provably stops within 3e-5 bins of it (every block of a well-conditioned geometry
+    // such as the example configuration).  Same iteration as lm::gn_fit, laid out for a warp: one lane per point, the
+    // six sums of the normal equations by xor-shuffles, nothing in shared memory.
+    if (N / W <= lm::QUICK_MAX_LOBE) {
+        const GnWarp<float> p1 = gn_fit_warp<float>(y, lane, (float)piW, (float)N, (float)W, __shfl_sync(0xffffffffu, y, 3), 0.f,
+                                                    lm::QUICK_STEP_F32, 1, 0u, lm::QUICK_MAXIT);
+        if (p1.ok) {
+            const GnWarp<double> p2 = gn_fit_warp<double>((double)y, lane, piW, N, W, (double)p1.A, (double)p1.d, lm::QUICK_STEP,
+                                                          0, p1.pattern, 4);
+            if (p2.ok && p2.slack < lm::QUICK_SLACK && fabs(p2.d) < 1.0) return (float)p2.d;
+        }
+    }
+#endif
     if (lane < 8) w.y[lane] = (double)y;
     __syncwarp();
-#ifndef THR_EXP_NOQUICK
-    // short cut (dirichlet_lm.cuh): Gauss-Newton to the least-squares minimum, accepted where lmdif provably stops
-    // within 3e-5 bins of it (every block of a well-conditioned geometry such as the example configuration)
-    auto derivs = [&](double d, double *g, double *gd) {
-        if (lane < 8) lm::kernel_deriv(xi - d, piW, N, W, g[lane], gd[lane]);
-        __syncwarp();
-    };
-    const lm::Quick quick = lm::quick_fit(WarpExec{lane}, derivs, w, w.y[3], 0.0, N / W);
-    if (quick.ok) return (float)quick.offset;
-    __syncwarp();
-#endif
     const lm::Result res = lm::fit(WarpExec{lane}, weights, w, w.y[3], 0.0);
     __syncwarp();                                  // the rows may be overwritten by the next fit
     return (float)res.offset;
@@ -845,7 +911,11 @@ detect_kernel(const __grid_constant__ DetectParams p) {
     };
     if (use_raw && tid == 0) {
         if (has_block(0)) issue_tile(0, 0);
+#ifdef THR_EXP_NOREFETCH
+        if (FASTDET && has_block(1)) issue_tile(1, 1);
+#else
         if (FASTDET ? has_block(1) : has_block(0)) issue_tile(FASTDET ? 1 : 0, 1);
+#endif
     }
     uint32_t par0 = 0, par1 = 0;    // phase parity of the two tile barriers
 
@@ -919,7 +989,11 @@ detect_kernel(const __grid_constant__ DetectParams p) {
         }
         bar_sync(BAR_MAIN, T);
         // after the pass-1 barrier nobody reads this raw stage any more: fetch its next block
+#ifdef THR_EXP_NOREFETCH
+        if (use_raw && tid == 0 && has_block(next) && stage == 0) issue_tile(next, stage);
+#else
         if (use_raw && tid == 0 && has_block(next)) issue_tile(next, stage);
+#endif
         if constexpr (C::ZOOM_OK) {
             if (!stageB && zoom) {
                 // pruned pass 2: outputs k2 = 0..3 of the R2-point DFT over n2 = Q m + r (Q = R2/4):
@@ -1495,10 +1569,12 @@ detect_kernel(const __grid_constant__ DetectParams p) {
             } else {
                 bar_sync(BAR_MAIN, T);
             }
+#ifndef THR_EXP_NOREFETCH                               // (timing experiment: stage B on whatever stage 1 holds)
             if (use_raw) {                              // the re-fetched raw tile of block i (stage 1)
                 mbar_wait(&mbar[1], par1);
                 par1 ^= 1;
             }
+#endif
             const FitSlot &fs = fitslot[i % NSLOT];
             const int kpeak = fs.kpeak;
             const bool carrier = fs.carrier != 0;

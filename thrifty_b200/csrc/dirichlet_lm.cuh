@@ -461,33 +461,124 @@ THR_HD Result fit(Exec &&ex, Weights &&weights, Rows &w, double a0, double d0) {
 // of the least-squares minimum along the offset: beyond that distance one more step still lowers the cost by more
 // than ftol C.  (Measured on 2 100 fits, well- and ill-conditioned: |offset_lmdif - offset_min| <= 0.18 slack.)
 // Where the slack is far below the parity bar of 1e-4 bins the minimum itself is therefore the answer, and a plain
-// Gauss-Newton iteration on the normal equations finds it in a third of the instructions.  quick_fit() does that and
+// Gauss-Newton iteration on the normal equations finds it in a fraction of the instructions.  quick_fit() does that and
 // reports whether its result may stand in for lmdif's: converged, every step lowered the cost (no damping: nothing
-// path dependent happened), |offset| < 1 and slack < QUICK_SLACK.  Otherwise the caller runs fit().
-//
-// derivs(d, g, gd) must fill rows 0..6 with the model weight and its derivative with respect to the offset at d, and
-// synchronise.
+// path dependent happened), |offset| < 1 and slack < QUICK_SLACK.  Otherwise the caller runs fit() -- after restoring
+// rows.y, which the short cut's workspace overlays.
 constexpr double QUICK_SLACK = 3e-5;
 constexpr int QUICK_MAXIT = 10;
-constexpr double QUICK_STEP = 1e-5;
+constexpr double QUICK_STEP = 1e-4;       // double phase: a step below this ends the iteration (what is left after a step
+                                           // is <= 0.1 of it here; the float phase usually leaves one such step of ~1e-5)
 constexpr double QUICK_MAX_LOBE = 24.0;    // short cut only for N / W <= 24 bins (beyond, the 7 points sit on the flat top
                                            // of the main lobe and lmdif can stop on xtol far outside the ftol slack)
 // D(z) = sin(pi W z / N) / (W sin(pi z / N)) and dD/dz at z = x - offset (carrier_sync.py:121-132); z == 0: (1, 0)
-THR_HD void kernel_deriv(double z, double piW, double N, double W, double &D, double &Dz) {
-    const double t1 = (piW * z) / N, t2 = (3.141592653589793 * z) / N;
-    double s1, c1, s2, c2;
+template <class T>
+THR_HD void kernel_deriv(T z, T piW, T N, T W, T &D, T &Dz) {
+    const T pi = (T)3.141592653589793;
+    const T t1 = (piW * z) / N, t2 = (pi * z) / N;
+    T s1, c1, s2, c2;
 #if defined(__CUDA_ARCH__)
-    sincos(t1, &s1, &c1);           // one range reduction per angle
-    sincos(t2, &s2, &c2);
+    if constexpr (sizeof(T) == 4) {
+        sincosf(t1, &s1, &c1);
+        sincosf(t2, &s2, &c2);
+    } else {
+        sincos(t1, &s1, &c1);       // one range reduction per angle
+        sincos(t2, &s2, &c2);
+    }
 #else
-    s1 = sin(t1), c1 = cos(t1), s2 = sin(t2), c2 = cos(t2);
+    s1 = (T)sin((double)t1), c1 = (T)cos((double)t1), s2 = (T)sin((double)t2), c2 = (T)cos((double)t2);
 #endif
     D = s1 / s2 / W;
-    Dz = ((piW / N) * c1 * s2 - (3.141592653589793 / N) * s1 * c2) / (s2 * s2) / W;
+    Dz = ((piW / N) * c1 * s2 - (pi / N) * s1 * c2) / (s2 * s2) / W;
     if (D != D) {
-        D = 1.0;
-        Dz = 0.0;
+        D = (T)1;
+        Dz = (T)0;
     }
+}
+
+// Gauss-Newton on the normal equations of the 7-point problem, in float or double.  Row workspace (shared memory on the
+// device: the double-precision lm::Rows is large enough for either instantiation and is reused).
+template <class T>
+struct GnRows {
+    T y[8], D[8], Dz[8], g[8], r[8], jd[8], neg[8];
+};
+static_assert(sizeof(GnRows<double>) <= sizeof(Rows), "the Gauss-Newton rows live in the lmdif workspace");
+
+template <class T>
+struct GnResult {
+    T amplitude, offset;
+    double slack;           // sqrt(2 ftol C cov_dd) at the last evaluated iterate
+    unsigned pattern;       // bit r: D < 0 at point r (sign pattern the iteration settled in)
+    bool ok;                // converged, every step lowered the cost, the sign pattern never changed after `settle`
+};
+
+// derivs(d, D, Dz) must fill rows 0..6 with the kernel and its z-derivative at the offset d, and synchronise.
+// The model |D| has a kink wherever D changes sign (the nulls of the kernel, at z = m N / W), and with a point next to a
+// null there is a local minimum on either side of it -- which one an iteration ends in depends on its path.  lmdif starts
+// at (y[3], 0) and its first step is the Gauss-Newton step; so the sign pattern of D over the 7 points is recorded after
+// the first step from that start (settle = 1) and must not change afterwards -- neither in this run nor in a later one
+// that continues from its result (settle = 0, pattern_in = the recorded pattern).  Otherwise the result is not vouched for.
+template <class T, class Exec, class Derivs>
+THR_HD GnResult<T> gn_fit(Exec &&ex, Derivs &&derivs, GnRows<T> &w, T a0, T d0, T step_tol, int settle, unsigned pattern_in,
+                          int max_iter) {
+    T A = a0, d = d0;
+    GnResult<T> q;
+    q.ok = false;
+    q.slack = 1.0;
+    q.pattern = pattern_in;
+    T cost_prev = (T)3e38;
+    bool converged = false;
+    T saa = 0, sdd = 0, sad = 0, cost = 0;
+    THR_ROLLED
+    for (int it = 0; it < max_iter; ++it) {
+        derivs(d, w.D, w.Dz);
+        ex.each(0, [&](int r) {
+            const T D = w.D[r];
+            const T g = D < (T)0 ? -D : D, gd = D < (T)0 ? w.Dz[r] : -w.Dz[r];   // d|D|/d offset = -sign(D) dD/dz
+            w.g[r] = g;
+            w.r[r] = A * g - w.y[r];                            // residual
+            w.jd[r] = A * gd;                                   // d residual / d offset (d residual / d A = g)
+            w.neg[r] = D < (T)0 ? (T)1 : (T)0;
+        });
+        ex.sync();
+        T sar = 0, sdr = 0;
+        saa = sdd = sad = cost = 0;
+        unsigned pattern = 0;
+        for (int i = 0; i < M; ++i) {
+            const T g = w.g[i], jd = w.jd[i], r = w.r[i];
+            saa += g * g;
+            sad += g * jd;
+            sdd += jd * jd;
+            sar += g * r;
+            sdr += jd * r;
+            cost += r * r;
+            pattern |= (w.neg[i] != (T)0 ? 1u : 0u) << i;
+        }
+        ex.sync();
+        if (it == settle) q.pattern = pattern;
+        // (a cost that only moves in its last bits -- the iteration has arrived, in this precision -- is not an increase)
+        const T slop = sizeof(T) == 4 ? (T)1.00002 : (T)1.00000000001;
+        if (!(cost <= cost_prev * slop) || (it > settle - (settle == 0) && pattern != q.pattern)) break;   // leave it to lmdif
+        cost_prev = cost;
+        const T det = saa * sdd - sad * sad;
+        if (!(det > (T)0)) break;
+        const T dA = -(sdd * sar - sad * sdr) / det, dd = -(saa * sdr - sad * sar) / det;
+        A += dA;
+        d += dd;
+        const T adA = dA < (T)0 ? -dA : dA, add = dd < (T)0 ? -dd : dd, aA = A < (T)0 ? -A : A;
+        if (it >= settle && add < step_tol && adA <= step_tol * aA) {     // what is left after this step is a small
+            converged = true;                                             // fraction of it
+            break;
+        }
+    }
+    q.amplitude = A;
+    q.offset = d;
+    if (converged) {
+        const double det = (double)saa * (double)sdd - (double)sad * (double)sad;
+        q.slack = sqrt(2.0 * TOL * (double)cost * ((double)saa / det));
+        q.ok = true;
+    }
+    return q;
 }
 
 struct Quick {
@@ -495,64 +586,40 @@ struct Quick {
     bool ok;
 };
 
-// derivs(d, D, Dz) must fill rows 0..6 with the kernel and its z-derivative at the offset d, and synchronise.
-// Starts from the same point as lmdif, whose first step is the same Gauss-Newton step; the model |D| has a kink
-// wherever D changes sign (the nulls of the kernel, at z = m N / W), and with a point next to a null there is a
-// local minimum on either side of it -- which one an iteration ends in depends on its path.  So if the sign pattern
-// of D over the 7 points changes after the first step, the short cut does not vouch for its result.
-template <class Exec, class Derivs>
-THR_HD Quick quick_fit(Exec &&ex, Derivs &&derivs, Rows &w, double a0, double d0, double lobe /* = N / W */) {
-    double A = a0, d = d0;
+// The short cut in two phases: float Gauss-Newton from lmdif's starting point down to the float noise floor (cheap: the
+// FP32 pipe, ~6-digit sines), then the same iteration in double from there -- one or two steps -- to the minimum itself.
+// derivs_f / derivs_d: the kernel evaluations in float / double (see gn_fit).
+constexpr float QUICK_STEP_F32 = 3e-5f;
+template <class Exec, class DerivsF, class DerivsD>
+THR_HD Quick quick_fit(Exec &&ex, DerivsF &&derivs_f, DerivsD &&derivs_d, Rows &rows, double lobe /* = N / W */) {
     Quick q;
     q.ok = false;
     q.slack = 1.0;
-    double cost_prev = 1e300;
-    bool converged = false;
-    double saa = 0.0, sdd = 0.0, sad = 0.0, cost = 0.0, flips = 0.0;
-    THR_ROLLED
-    for (int it = 0; it < QUICK_MAXIT; ++it) {
-        derivs(d, w.gt, w.gth);                                 // gt = D, gth = dD/dz
-        ex.each(0, [&](int r) {
-            const double D = w.gt[r], neg = D < 0.0 ? 1.0 : 0.0;
-            const double g = fabs(D), gd = D < 0.0 ? w.gth[r] : -w.gth[r];     // d|D|/d offset = -sign(D) dD/dz
-            w.gx[r] = g;
-            w.fvec[r] = A * g - w.y[r];                         // residual
-            w.a[1][r] = A * gd;                                 // d residual / d offset (d residual / d A = g)
-            if (it == 1) w.wa4[r] = neg;                        // sign pattern after the first step
-            w.gh[r] = (it > 1 && neg != w.wa4[r]) ? 1.0 : 0.0;
-        });
-        ex.sync();
-        double sar = 0.0, sdr = 0.0;
-        saa = sdd = sad = cost = flips = 0.0;
-        for (int i = 0; i < M; ++i) {
-            const double g = w.gx[i], jd = w.a[1][i], r = w.fvec[i];
-            saa += g * g;
-            sad += g * jd;
-            sdd += jd * jd;
-            sar += g * r;
-            sdr += jd * r;
-            cost += r * r;
-            flips += w.gh[i];
-        }
-        ex.sync();
-        if (!(cost <= cost_prev) || flips != 0.0) break;        // leave it to lmdif
-        cost_prev = cost;
-        const double det = saa * sdd - sad * sad;
-        if (!(det > 0.0)) break;
-        const double dA = -(sdd * sar - sad * sdr) / det, dd = -(saa * sdr - sad * sar) / det;
-        A += dA;
-        d += dd;
-        if (it >= 1 && fabs(dd) < QUICK_STEP && fabs(dA) <= QUICK_STEP * fabs(A)) {   // what is left after this step is
-            converged = true;                                                         // a small fraction of it
-            break;
-        }
-    }
-    q.amplitude = A;
-    q.offset = d;
-    if (converged) {
-        const double det = saa * sdd - sad * sad;
-        q.slack = sqrt(2.0 * TOL * cost * (saa / det));
-        q.ok = q.slack < QUICK_SLACK && fabs(d) < 1.0 && lobe <= QUICK_MAX_LOBE;
+    q.amplitude = rows.y[3];
+    q.offset = 0.0;
+    if (!(lobe <= QUICK_MAX_LOBE)) return q;
+    const double y0 = rows.y[0], y1 = rows.y[1], y2 = rows.y[2], y3 = rows.y[3], y4 = rows.y[4], y5 = rows.y[5], y6 = rows.y[6];
+    ex.sync();
+    GnRows<float> &wf = *reinterpret_cast<GnRows<float> *>(&rows);
+    ex.each(0, [&](int r) {
+        const double yr = r == 0 ? y0 : r == 1 ? y1 : r == 2 ? y2 : r == 3 ? y3 : r == 4 ? y4 : r == 5 ? y5 : y6;
+        wf.y[r] = (float)yr;
+    });
+    ex.sync();
+    const GnResult<float> p1 = gn_fit<float>(ex, derivs_f, wf, (float)y3, 0.0f, QUICK_STEP_F32, 1, 0u, QUICK_MAXIT);
+    ex.sync();
+    GnRows<double> &wd = *reinterpret_cast<GnRows<double> *>(&rows);
+    ex.each(0, [&](int r) {
+        wd.y[r] = r == 0 ? y0 : r == 1 ? y1 : r == 2 ? y2 : r == 3 ? y3 : r == 4 ? y4 : r == 5 ? y5 : y6;
+    });
+    ex.sync();
+    if (p1.ok) {
+        const GnResult<double> p2 = gn_fit<double>(ex, derivs_d, wd, (double)p1.amplitude, (double)p1.offset, QUICK_STEP, 0,
+                                                   p1.pattern, 4);
+        q.amplitude = p2.amplitude;
+        q.offset = p2.offset;
+        q.slack = p2.slack;
+        q.ok = p2.ok && p2.slack < QUICK_SLACK && fabs(p2.offset) < 1.0;
     }
     return q;
 }
