@@ -146,3 +146,23 @@ def test_short_cut_refuses_points_next_to_a_null(quick):
         if ok:
             ref = leastsq(lambda p: p[0] * np.abs(kern(XD - p[1], w, n)) - y, (y[3], 0.0), full_output=1)
             assert abs(d - ref[0][1]) < 2e-5, (y, d, ref[0])
+
+
+def test_short_cut_refuses_a_start_on_a_null(quick):
+    """Carrier as long as the block (or half / a third of it): at lmdif's starting guess the off-peak points sit ON nulls of
+    the kernel, where the slope of |D| is one-sided.  The short cut must hand such blocks over (the reference's own
+    freq_shift vectors, tests/test_carrier_sync.py:12-39, are of this kind) -- and wherever it does answer, agree."""
+    rng = np.random.default_rng(0)
+    n = 4096
+    for ratio, may_answer in [(1, False), (1.5, False), (2, False), (3, False), (1.0001, False), (2.999, False), (4, True), (6, True)]:
+        n_ok = 0
+        for _ in range(200):
+            w = int(round(n / ratio))
+            y = 100 * np.abs(kern(XD - rng.uniform(-0.6, 0.6), w, n)) + rng.normal(0, 100 * rng.choice([1e-6, 1e-3, 1e-2]), 7)
+            y = np.abs(y).astype(np.float32).astype(np.float64)
+            ok, d, _ = quick(y, w, n)
+            if ok:
+                n_ok += 1
+                ref = leastsq(lambda p: p[0] * np.abs(kern(XD - p[1], w, n)) - y, (y[3], 0.0), full_output=1)
+                assert abs(d - ref[0][1]) < 2e-5, (ratio, y, d, ref[0])
+        assert (n_ok > 100) == may_answer, (ratio, n_ok)

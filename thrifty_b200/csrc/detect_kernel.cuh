@@ -442,6 +442,8 @@ __device__ __forceinline__ GnWarp<T> gn_fit_warp(T y, int lane, T piW, T N, T W,
         const T sar = xor_sum8(g * r), sdr = xor_sum8(jd * r);
         cost = xor_sum8(r * r);
         const unsigned pattern = __ballot_sync(0xffffffffu, active && D < (T)0) & 0x7fu;
+        // a point on a null of the kernel at lmdif's starting guess: not vouched for (see lm::gn_fit)
+        if (it == 0 && settle == 1 && __any_sync(0xffffffffu, active && (lane & 7) != 3 && g < (T)lm::START_NULL)) break;
         if (it == settle) q.pattern = pattern;
         const T slop = sizeof(T) == 4 ? (T)1.00002 : (T)1.00000000001;
         if (!(cost <= cost_prev * slop) || (it > settle - (settle == 0) && pattern != q.pattern)) break;
@@ -494,6 +496,9 @@ __device__ __forceinline__ float dirichlet_fit(float y, int lane, const DetectPa
     if (N / W <= lm::QUICK_MAX_LOBE) {
         const GnWarp<float> p1 = gn_fit_warp<float>(y, lane, (float)piW, (float)N, (float)W, __shfl_sync(0xffffffffu, y, 3), 0.f,
                                                     lm::QUICK_STEP_F32, 1, 0u, lm::QUICK_MAXIT);
+#ifdef THR_EXP_F32ONLY          // timing experiment: what does the double-precision finish cost?
+        if (p1.ok) return p1.d;
+#endif
         if (p1.ok) {
             const GnWarp<double> p2 = gn_fit_warp<double>((double)y, lane, piW, N, W, (double)p1.A, (double)p1.d, lm::QUICK_STEP,
                                                           0, p1.pattern, 4);

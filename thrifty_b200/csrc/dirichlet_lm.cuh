@@ -469,6 +469,7 @@ constexpr double QUICK_SLACK = 3e-5;
 constexpr int QUICK_MAXIT = 10;
 constexpr double QUICK_STEP = 1e-4;       // double phase: a step below this ends the iteration (what is left after a step
                                            // is <= 0.1 of it here; the float phase usually leaves one such step of ~1e-5)
+constexpr double START_NULL = 1e-3;        // |D| below this at an off-peak point of the starting guess: on a null
 constexpr double QUICK_MAX_LOBE = 24.0;    // short cut only for N / W <= 24 bins (beyond, the 7 points sit on the flat top
                                            // of the main lobe and lmdif can stop on xtol far outside the ftol slack)
 // D(z) = sin(pi W z / N) / (W sin(pi z / N)) and dD/dz at z = x - offset (carrier_sync.py:121-132); z == 0: (1, 0)
@@ -555,6 +556,14 @@ THR_HD GnResult<T> gn_fit(Exec &&ex, Derivs &&derivs, GnRows<T> &w, T a0, T d0, 
             pattern |= (w.neg[i] != (T)0 ? 1u : 0u) << i;
         }
         ex.sync();
+        if (it == 0 && settle == 1) {
+            // lmdif starts exactly here too, but differentiates one-sidedly; with a point ON a null of the kernel at the
+            // start (carrier as long as the block, or half / a third of it) the analytic slope of |D| there is a coin
+            // toss and the first steps part ways
+            bool on_null = false;
+            for (int i = 0; i < M; ++i) on_null = on_null || (i != 3 && w.g[i] < (T)START_NULL);
+            if (on_null) break;
+        }
         if (it == settle) q.pattern = pattern;
         // (a cost that only moves in its last bits -- the iteration has arrived, in this precision -- is not an increase)
         const T slop = sizeof(T) == 4 ? (T)1.00002 : (T)1.00000000001;
