@@ -512,6 +512,30 @@ def test_raw_stream_card_export(tmp_path):
             assert abs(r1.soa - r0.soa) < 1e-3 and r1.corr_info.sample == r0.corr_info.sample
 
 
+def test_pipelined_chunks_do_not_share_scratch():
+    """A host-buffer call is cut into chunks that run on two streams and overlap on the device; kernels with per-CTA
+    global scratch (multi-template X' save area, block_len 32768) must not share it between the two chunks in flight
+    (found in round 2: records of a 4-template detector changed from run to run once a call spanned two chunks)."""
+    from thrifty_b200._native import NativeDetector
+    tpls = np.stack([synth.gold_template(11, i) for i in range(3)])
+    n, h = 16384, tpls.shape[1] + 6
+    raw, _ = synth.make_blocks(64, n, h, tpls[1], 0.8, seed=99)
+    raw = raw[np.arange(1400) % 64]
+    det = NativeDetector(n, h, tpls, tpls.shape[1], (7, 110), (0., 15., 0.), (0., 15., 0.), max_batch=1024)
+    want = np.concatenate([det.detect_raw(raw[a:a + 200], np.arange(a, a + 200)) for a in range(0, 1400, 200)])   # one chunk each
+    for _ in range(5):
+        assert det.detect_raw(raw, np.arange(1400)).tobytes() == want.tobytes()
+    det.close()
+    tpl = np.load(os.path.join(parity.GOLDEN, "template_example.npy"))
+    raw, _ = synth.make_blocks(32, 32768, 4920, tpl, 0.8, seed=98)
+    raw = raw[np.arange(700) % 32]
+    det = NativeDetector(32768, 4920, tpl, len(tpl), (7, 110), (0., 15., 0.), (0., 15., 0.), max_batch=512)
+    want = np.concatenate([det.detect_raw(raw[a:a + 100], np.arange(a, a + 100)) for a in range(0, 700, 100)])
+    for _ in range(3):
+        assert det.detect_raw(raw, np.arange(700)).tobytes() == want.tobytes()
+    det.close()
+
+
 def test_smoke_entry():
     sys.path.insert(0, ROOT)
     import __graft_entry__

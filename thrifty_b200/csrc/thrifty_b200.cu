@@ -170,6 +170,23 @@ int launch(thr_detector *d, cudaStream_t st, const uint8_t *d_raw, const float *
            bool allow_overlap = false, int64_t raw_stride = 0) {
     if (n_blocks <= 0) return THR_OK;
     DetectParams p = d->base;
+    const int grid = n_blocks < d->grid ? n_blocks : d->grid;
+    // Kernels with per-CTA global scratch (global-memory FFT buffer, the 2 x 16384 kernel's parking area, the
+    // multi-template X' save area) index it by blockIdx.x, and two launches can be on the device at once: the two
+    // pipelined slots of a host-buffer call run on two streams, and with programmatic dependent launch the next batch's
+    // CTA k starts while this batch's CTA k may still run.  Two scratch sets: one per slot, or alternating per launch --
+    // the latter only for full grids, where launch k+2 cannot start before launch k has left the SMs.
+    bool pdl = allow_overlap && (d->cfg.flags & THR_CFG_OVERLAP_LAUNCHES);
+    int set = (st == d->slot[1].stream) ? 1 : 0;
+    if (pdl && (p.scratch || p.xsave)) {
+        if (grid == d->grid) set = (int)(d->launches & 1);
+        else pdl = false;
+    }
+    if (set) {
+        const size_t stride = (size_t)d->grid * d->cfg.block_len;
+        if (p.scratch) p.scratch += stride;
+        if (p.xsave) p.xsave += stride;
+    }
     p.raw = d_raw;
     p.raw_stride = raw_stride ? raw_stride : 2 * (int64_t)d->cfg.block_len;
     p.iq = reinterpret_cast<const float2 *>(d_iq);
@@ -179,7 +196,6 @@ int launch(thr_detector *d, cudaStream_t st, const uint8_t *d_raw, const float *
     p.dbg_shifted_fft = dbg_sfft;
     p.dbg_corr = dbg_corr;
     p.dbg_fft_mag = dbg_mag;
-    const int grid = n_blocks < d->grid ? n_blocks : d->grid;
     const Variant *var = &d->var;
     if (d->has_generic && (dbg_sfft || dbg_corr || dbg_mag)) {    // intermediates: generic kernel (one block)
         var = &d->var_generic;
@@ -193,7 +209,7 @@ int launch(thr_detector *d, cudaStream_t st, const uint8_t *d_raw, const float *
     lc.dynamicSmemBytes = var->smem;
     lc.stream = st;
     cudaLaunchAttribute attr[1];
-    if (allow_overlap && (d->cfg.flags & THR_CFG_OVERLAP_LAUNCHES) && !d->var.gmem && d->cfg.n_templates == 1) {
+    if (pdl) {
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         lc.attrs = attr;
@@ -438,8 +454,10 @@ int thr_create(const thr_config *cfg, thr_detector **out) {
         CUC(cudaMalloc(&d->d_tpl_energy, NT * sizeof(float)));
         CUC(cudaMemcpy(d->d_tpl_energy, energy.data(), NT * sizeof(float), cudaMemcpyHostToDevice));
     }
-    if (var.gmem || use_2x) CUC(cudaMalloc(&d->d_scratch, (size_t)d->grid * N * sizeof(float2)));
-    if (NT > 1) CUC(cudaMalloc(&d->d_xsave, (size_t)d->grid * N * sizeof(float2)));
+    // per-CTA scratch areas, one set per pipelined slot: the kernels of two consecutive chunks of a host-buffer call run
+    // on two streams and overlap on the device, and both index their scratch by blockIdx.x
+    if (var.gmem || use_2x) CUC(cudaMalloc(&d->d_scratch, 2 * (size_t)d->grid * N * sizeof(float2)));
+    if (NT > 1) CUC(cudaMalloc(&d->d_xsave, 2 * (size_t)d->grid * N * sizeof(float2)));
     for (auto &s : d->slot) {
         CUC(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         CUC(cudaMalloc(&s.d_in, (size_t)cfg->max_batch * 2 * N));
@@ -682,11 +700,23 @@ static int detect_host(thr_detector *d, const uint8_t *raw, const float *iq, con
     }
     const bool pageable = is_pageable(raw ? (const void *)raw : (const void *)iq);
     if (int rc0 = slots_reset(d)) return rc0;
+    // A call ends with the link idle while the last chunk's kernel and record copy drain; so the tail of a call is cut
+    // into ever smaller chunks (half of what is left, down to two blocks per CTA): the last kernel is short.
+    auto chunk_at = [&](int64_t b0) -> int64_t {
+        if (cursor) return chunk;
+        const int64_t left = n_blocks - b0;
+        if (left > chunk) return chunk;
+        const int64_t small = 2 * (int64_t)d->grid;
+        if (left <= small) return left;
+        const int64_t half = ((left / 2 + d->grid - 1) / d->grid) * d->grid;
+        return half < small ? small : half;
+    };
     int c = 0;
+    int64_t this_chunk = chunk_at(0);
     for (int64_t b0 = cursor ? cursor->fetch_add(chunk) : 0; b0 < n_blocks;
-         b0 = cursor ? cursor->fetch_add(chunk) : b0 + chunk, ++c) {
+         b0 = cursor ? cursor->fetch_add(chunk) : b0 + this_chunk, this_chunk = chunk_at(b0), ++c) {
         Slot &s = d->slot[c & 1];
-        const int nb = (int)((n_blocks - b0) < chunk ? (n_blocks - b0) : chunk);
+        const int nb = (int)((n_blocks - b0) < this_chunk ? (n_blocks - b0) : this_chunk);
         int rc;
         {
             NvtxRange r("thr: records of chunk c-2 -> caller");
@@ -788,7 +818,7 @@ static int stage_setup(thr_detector *d, int st) {
         if (occ < 1) return fail(d, THR_ERR_CUDA, "kernel %s does not fit on an SM (smem %zu)", v.name, v.smem);
         int grid = d->sm_count * occ;
         if (v.gmem) {                                            // global-scratch kernel (block_len 32768)
-            if (!d->d_scratch) CU(d, cudaMalloc(&d->d_scratch, (size_t)d->grid * N * sizeof(float2)));
+            if (!d->d_scratch) CU(d, cudaMalloc(&d->d_scratch, 2 * (size_t)d->grid * N * sizeof(float2)));
             d->base.scratch = d->d_scratch;
             if (grid > d->grid) grid = d->grid;                  // the scratch is sized for the main kernel's grid
         }

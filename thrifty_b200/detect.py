@@ -338,8 +338,9 @@ class Detector(object):
             stop.set()
             free_q.put(None)
             thread.join(timeout=5)
-            for b in bufs:
-                b.close()
+            if not thread.is_alive():            # (a reader stuck in a blocking read keeps its buffers: never free
+                for b in bufs:                   # page-locked memory a thread may still write to)
+                    b.close()
 
     def detect_card_stream(self, stream, chunk_bytes=32 << 20, min_lines=None):
         """Yield (detected, DetectionResult) for every data line of a binary `.card` stream.
