@@ -63,7 +63,9 @@ def spread(cfg, raw_block, trials=64, seed=1):
     return base, float(np.abs(vals - base).max()), float(vals.std())
 
 
-CASES = [(200, 99, False, 53, 11), (40, 3, True, 25, 20)]     # (n_cfg, seed, big, cfg, block): r02 stress runs
+# (n_cfg, seed, big, cfg, block): every block the round-2 stress runs (1 000 + 100 configurations) left above the bar
+CASES = [(200, 99, False, 53, 11), (40, 3, True, 25, 20), (200, 7, False, 190, 40), (200, 123, False, 165, 24),
+         (200, 2026, False, 35, 58), (200, 2026, False, 107, 21), (60, 11, True, 27, 1), (60, 11, True, 34, 5)]
 
 if __name__ == "__main__":
     cases = CASES
