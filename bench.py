@@ -480,19 +480,18 @@ def run_ours(args):
     if world > 1:
         _, probe_u = make_unique_blocks(256, 0.7, synth.SEED0 + 424242)           # same probe on every rank
         probe = probe_u[np.arange(PROBE_BLOCKS) % len(probe_u)]
-        per = (PROBE_BLOCKS + world - 1) // world
-        lo, hi = min(per * rank, PROBE_BLOCKS), min(per * (rank + 1), PROBE_BLOCKS)
+        from thrifty_b200 import stripe                 # stripe bounds + record gather: the code tests/test_stripe_gloo.py
+        lo, hi = stripe.stripe_bounds(PROBE_BLOCKS, world, rank)                    # covers with gloo on CPU ranks
         part = torch.from_numpy(np.ascontiguousarray(probe[lo:hi])).to(dev)
         pidx = torch.arange(lo, hi, dtype=torch.int64, device=dev)
-        mine = torch.zeros(per * 64, dtype=torch.uint8, device=dev)
+        mine = torch.zeros(max(hi - lo, 1) * 64, dtype=torch.uint8, device=dev)
         if hi > lo:
             det.detect_device(part.data_ptr(), pidx.data_ptr(), hi - lo, mine.data_ptr())
-        allrec = torch.zeros(world * per * 64, dtype=torch.uint8, device=dev)
-        dist.all_gather_into_tensor(allrec, mine)
         torch.cuda.synchronize()
+        local = np.frombuffer(mine.cpu().numpy().tobytes(), dtype=RECORD_DTYPE)[:hi - lo].reshape(hi - lo, 1)
+        got = stripe.gather_records(local, PROBE_BLOCKS)[:, 0]                      # NCCL all-gather of the 64-byte records
         if rank == 0:
             whole = det.detect_raw(probe, np.arange(PROBE_BLOCKS))[:, 0]
-            got = np.frombuffer(allrec.cpu().numpy().tobytes(), dtype=RECORD_DTYPE)[:PROBE_BLOCKS]
             stripe_parity = bool(got.tobytes() == whole.tobytes())
             # the consumer of the gathered records: `identify` on the device (txid by carrier-bin window, duplicate
             # filter over adjacent blocks) must give the same survivors from the gathered records as from one GPU's
@@ -503,7 +502,7 @@ def run_ours(args):
             identify_leg = {"detections": int(((got["flags"] & 2) != 0).sum()), "kept": int(len(sel_g)),
                             "transmitters": int(len(set(tx_g.tolist()))),
                             "equal_single_gpu": bool(np.array_equal(sel_g, sel_1) and np.array_equal(tx_g, tx_1))}
-        del part, pidx, mine, allrec
+        del part, pidx, mine
 
     # ---- e2e: HOST buffers through the product API, copies inside the timed region.
     # 1 GPU: thr_detect_batch with pinned buffers.  N GPUs: rank 0 drives all N through the multi-GPU handle
