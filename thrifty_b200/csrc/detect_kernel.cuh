@@ -44,6 +44,11 @@
 #ifndef THR_FIT_DEPTH_BIG
 #define THR_FIT_DEPTH_BIG 4     // blocks of look-ahead of stage A over stage B where shared memory allows a 5-slot ring (T >= 256)
 #endif
+#ifndef THR_ROLL_ITEMS
+#define THR_ROLL_ITEMS 1        // kernels with several CTAs per SM (N <= 8192) keep the loops over a thread's pass-2 / pass-3
+                                // items rolled: those kernels are bound by instruction fetch (four unsynchronised CTAs walk
+                                // the same straight-line code), and 2-4 copies of a radix-8/16 transform are the bulk of it
+#endif
 #ifndef THR_TW3
 #define THR_TW3 1           // (+2 %) inter-pass twiddles W_M^{n3 k2} of FFT#2 / IFFT applied on the pass-3 side from a
                             // per-item register chain instead of the shared-memory table on the pass-2 side
@@ -636,6 +641,9 @@ detect_kernel(const __grid_constant__ DetectParams p) {
     constexpr bool TW3 = (THR_TW3 != 0) && (!MULTI || THR_TW3_MULTI != 0) && !FASTDET && C::R3 == 16 && C::R2 > 1;
     constexpr int N = C::N, M = C::M, R2 = C::R2, R3 = C::R3, S = C::S;
     constexpr int I1 = C::I1, I2 = C::I2, I3 = C::I3;
+    constexpr bool ROLL = (THR_ROLL_ITEMS != 0) && !C::ONE_CTA;
+    constexpr int UNROLL_I2 = ROLL ? 1 : I2;                   // #pragma unroll factors of the item loops
+    constexpr int UNROLL_I3 = (ROLL && !FASTDET) ? 1 : I3;     // (FASTDET keeps its pass-3 outputs in registers per item)
     constexpr int LOG2M = ilog2(M), LOG2R3 = ilog2(R3), LOG2R2 = ilog2(R2), LOG2S = ilog2(S);
     constexpr uint32_t RAW_BYTES = 2u * N;
     constexpr int NTHREADS = T + 32;     // participants of the worker<->service barriers
@@ -1005,7 +1013,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 //   c_r[k] = sum_m a[Q m + r] W_4^{mk}    (radix-4, no multiplications)
                 //   B[k]   = sum_r W_R2^{rk} c_r[k]       (2 packed FMAs per term; W_R2 = W_32^(32/R2))
                 constexpr int Q = R2 / 4, E = 32 / R2;
-#pragma unroll
+#pragma unroll UNROLL_I2
                 for (int it = 0; it < I2; ++it) {
                     const int w = tid + T * it;
                     const int k1 = w >> LOG2R3, n3 = w & (R3 - 1);
@@ -1046,7 +1054,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
         }
         // pass 2: radix-R2 over n2 (stride R3) inside each k1 slab, twiddle W_M^{n3 k2}
         if (R2 > 1) {
-#pragma unroll
+#pragma unroll UNROLL_I2
             for (int it = 0; it < I2; ++it) {
                 const int w = tid + T * it;
                 const int k1 = w >> LOG2R3, n3 = w & (R3 - 1);
@@ -1082,7 +1090,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
     };
     int corr_blk = 0;                // block being correlated (offset of the optional per-block correlation output)
     auto corr_stage = [&](int q, int tpl, auto &&get_tv, auto &&get_x) {
-#pragma unroll
+#pragma unroll UNROLL_I3
         for (int it = 0; it < I3; ++it) {
             const int g = C::p3_item(tid, it);
             const uint32_t ab = a3_base(g);
@@ -1112,7 +1120,7 @@ detect_kernel(const __grid_constant__ DetectParams p) {
         else bar_sync(BAR_MAIN, T);
         // inverse pass 2': conj twiddle on load, radix-R2 over k2
         if (R2 > 1) {
-#pragma unroll
+#pragma unroll UNROLL_I2
             for (int it = 0; it < I2; ++it) {
                 const int w = tid + T * it;
                 const int k1 = w >> LOG2R3, n3 = w & (R3 - 1);
@@ -1381,8 +1389,12 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 }
             }
             float tenergy = 0.f;
-            if (shiftA) fwd_pass12(ia, 0, ia + 1, true, false, phA, zrho, tenergy);     // two specialised copies: a run-time
-            else fwd_pass12(ia, 0, ia + 1, false, false, phA, zrho, tenergy);           // flag inside pass 1 costs registers
+            if constexpr (ROLL) {
+                fwd_pass12(ia, 0, ia + 1, shiftA, false, phA, zrho, tenergy);               // one copy: code size first
+            } else {
+                if (shiftA) fwd_pass12(ia, 0, ia + 1, true, false, phA, zrho, tenergy);     // two specialised copies: a run-time
+                else fwd_pass12(ia, 0, ia + 1, false, false, phA, zrho, tenergy);           // flag inside pass 1 costs registers
+            }
 
             FitSlot &fs = fitslot[q];                   // ring slot of block ia
             // carrier decision in float32 (carrier_detect.py:99-115); returns the peak bin or -1
