@@ -19,6 +19,7 @@ for the `cpu_baseline` leg and the `--impl reference` arm.
 """
 
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -533,6 +534,34 @@ def run_ours(args):
         e2e_det = int(((e2e_recs["flags"] & 2) != 0).sum())
         e2e_api = "thr_detect_batch (pinned host buffers)"
         for b in hbuf + hidx + hout:
+            b.close()
+        # the same number of blocks as ONE contiguous raw stream (the reference's block_reader input, block_data.py:70-98):
+        # the windows overlap by `history`, so only N - H new samples per block cross PCIe (thr_detect_stream)
+        new = 2 * (n - HISTORY)
+        sbytes = 2 * HISTORY + batch * new
+        spin = [PinnedBuffer(sbytes) for _ in range(2)]
+        sout = [PinnedBuffer(batch * 64) for _ in range(2)]
+        for b in range(2):
+            src = uniq[(np.arange(batch) + b * 7) % len(uniq)]
+            spin[b].array[:2 * HISTORY] = src[0][:2 * HISTORY]
+            spin[b].array[2 * HISTORY:] = src[:, 2 * HISTORY:].reshape(-1)
+        got = ctypes.c_int64(0)
+        for b in range(2):   # warm-up
+            det._check(lib.thr_detect_stream(det.handle, spin[b].ptr, sbytes, b * batch, sout[b].ptr, ctypes.byref(got)))
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            b = i & 1
+            det._check(lib.thr_detect_stream(det.handle, spin[b].ptr, sbytes, b * batch, sout[b].ptr, ctypes.byref(got)))
+        torch.cuda.synchronize()
+        s_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+        s_recs = sout[(e2e_steps - 1) & 1].array.view(RECORD_DTYPE)
+        e2e_extra["raw_stream"] = {
+            "value": int(got.value) * n / (s_ms * 1e-3) / 1e6, "unit": "Msamples/s", "api": "thr_detect_stream (pinned host stream)",
+            "blocks_per_step": int(got.value), "ms_per_step": s_ms, "h2d_bytes_per_step": sbytes,
+            "h2d_gbs": sbytes / (s_ms * 1e-3) / 1e9, "carrier_detected_last_batch": int(((s_recs["flags"] & 1) != 0).sum()),
+            "what": "the same blocks as one contiguous uint8 I/Q stream whose windows overlap by `history` (what "
+                    "`detect --raw` reads): N - H new samples per block cross PCIe instead of N"}
+        for b in spin + sout:
             b.close()
     elif rank == 0:
         grp = NativeGroup(list(range(world)), n, HISTORY, tpl, len(tpl), WINDOW, THRESH, THRESH, max_batch=batch)
