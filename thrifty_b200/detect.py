@@ -200,7 +200,7 @@ class Detector(object):
         return records_to_results(recs[:, 0], [it[0] for it in items], self.rxid)
 
     # ---- whole `.card` streams: scan on the host, base64 decode + detect on the GPU
-    def iter_card_records(self, stream, chunk_bytes=32 << 20, min_lines=None, read_threads=8):
+    def iter_card_records(self, stream, chunk_bytes=None, min_lines=None, read_threads=8):
         """Yield (timestamps f8[B], block_idx i8[B], records [B, T]) per chunk of a binary `.card` stream.
 
         The text goes to the GPU as is (thr_detect_card: host jump-scan of the line headers, base64 decode and detect on
@@ -217,6 +217,8 @@ class Detector(object):
         from concurrent.futures import ThreadPoolExecutor
         from thrifty_b200._native import PinnedBuffer
         line_len = ((2 * self.settings.block_len + 2) // 3) * 4 + 64
+        if chunk_bytes is None:                  # size of each staging buffer; THRIFTY_B200_CARD_CHUNK_MB overrides
+            chunk_bytes = int(float(os.environ.get("THRIFTY_B200_CARD_CHUNK_MB", "16")) * (1 << 20))
         chunk_bytes = max(int(chunk_bytes), 4 * line_len)
         if min_lines is None:
             min_lines = max(1, min(self.batch, 8))
@@ -229,7 +231,8 @@ class Detector(object):
             pass
         read_into = getattr(stream, "readinto1", None) or getattr(stream, "readinto", None)
         # two page-locked buffers (one spare byte keeps the C number parser inside the allocation), allocated by the
-        # reader thread when it first needs them: pinning 32 MB takes ~15 ms, which then overlaps the first chunk's GPU work
+        # reader thread when it first needs them: pinning costs 0.6-1 ms per MiB (the fixed cost of a short run), and while the
+        # reader bounds the rate 16 MiB chunks (~380 lines of 16384 samples) keep the GPU side above it
         bufs = []
         free_q, ready_q = queue.Queue(), queue.Queue()
         stop = threading.Event()
@@ -342,7 +345,7 @@ class Detector(object):
                 for b in bufs:                   # page-locked memory a thread may still write to)
                     b.close()
 
-    def detect_card_stream(self, stream, chunk_bytes=32 << 20, min_lines=None):
+    def detect_card_stream(self, stream, chunk_bytes=None, min_lines=None):
         """Yield (detected, DetectionResult) for every data line of a binary `.card` stream.
 
         Same results as iterating Detector(settings, card_reader(stream)) (block_data.py:101-131), through
