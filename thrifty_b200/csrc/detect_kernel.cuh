@@ -30,7 +30,8 @@
 #define THR_WL23 1          // warp-local hand-over between passes 2 and 3 (no CTA barrier)
 #endif
 #ifndef THR_TW3_MULTI
-#define THR_TW3_MULTI 0     // the same in the multi-template kernels: measured -6 % (176 bytes of spills with the template loop)
+#define THR_TW3_MULTI 0     // the same in the multi-template kernels: measured -6.5 % (the inverse-side chain is paid once per
+                            // template, the table look-up it replaces in the forward pass 2 only once per block)
 #endif
 #ifndef THR_SERVICE_T256
 #define THR_SERVICE_T256 1      // (+12 % at N = 8192) service warpgroup also for the 2-CTAs-per-SM kernel
@@ -1711,7 +1712,11 @@ detect_kernel(const __grid_constant__ DetectParams p) {
                 } else {
 #pragma unroll
                     for (int k3 = 0; k3 < R3; ++k3)
+#ifdef THR_EXP_NOXLOAD          // timing experiment only (wrong results): what re-reading X' from L2 costs
+                        x[k3] = make_float2((float)tid, (float)(k3 + tpl));
+#else
                         x[k3] = p.xsave[(size_t)blockIdx.x * N + (size_t)(it * R3 + k3) * T + tid];
+#endif
                 }
                 });
                 // next template reuses the FFT buffer: all pass-1' loads are done (reduction barriers)

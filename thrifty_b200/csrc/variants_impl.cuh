@@ -59,7 +59,7 @@ bool THR_PICK(int n, Variant *out) {
         case 8192:  *out = make_variant<13, 256, false>("detect_kernel<N=8192,T=256,smem" THR_SUFFIX); return true;
         case 32768: *out = make_variant<15, 512, true>("detect_kernel<N=32768,T=512,gmem" THR_SUFFIX); return true;
 #endif
-#if !(THR_MULTI && defined(THR_ONLY_N16384))
+#if !(THR_MULTI && defined(THR_ONLY_N16384) && !defined(THR_KEEP_MULTI))   // (experiment builds drop the multi-template kernel unless asked)
 #ifdef THR_N16384_T256      // experiment: 8 fat worker warps (2 items per thread and pass, 232 registers)
         case 16384: *out = make_variant<14, 256, false>("detect_kernel<N=16384,T=256,smem" THR_SUFFIX); return true;
 #else
