@@ -330,15 +330,18 @@ def cli_e2e(tpl, raw_unique, n_blocks, device):
                     break
         argv_q = [quarter] + argv[1:]
         dt_q, dt_q_all = timed(argv_q, warm=1)
-        steady = (n_blocks - lines_q) / (dt - dt_q) if dt > dt_q else None
+        # host-side noise is one-sided (stalls of 0.1-0.5 s on shared hosts): the difference quotient uses the best runs
+        best, best_q = min(dt_all), min(dt_q_all)
+        steady = (n_blocks - lines_q) / (best - best_q) if best > best_q else None
         return {"value": n_blocks / dt, "unit": "blocks/s", "msamples_per_s": n_blocks * BLOCK_LEN / dt / 1e6,
                 "blocks": n_blocks, "seconds": dt, "card_bytes": os.path.getsize(card), "toad_lines": n_lines,
                 "seconds_all_runs": dt_all, "quarter_file_seconds": dt_q, "quarter_file_seconds_all_runs": dt_q_all,
                 "steady_blocks_per_s": steady,
-                "fixed_cost_seconds": (dt_q - lines_q / steady) if steady else None,
+                "fixed_cost_seconds": (best_q - lines_q / steady) if steady else None,
+                "best_seconds": best, "best_blocks_per_s": n_blocks / best,
                 "what": "thrifty_b200.detect.detector_cli(Detector) in-process on a synthetic .card in /dev/shm: file read + "
                         "GPU base64 decode + detect + .toad text; interpreter start-up and imports excluded; "
-                        "seconds = median of 5 runs after 2 warm-up runs; steady_blocks_per_s = extra blocks / extra seconds between the quarter file and the whole file"}
+                        "seconds = median of 5 runs after 2 warm-up runs; steady_blocks_per_s = extra blocks / extra seconds between the best quarter-file run and the best whole-file run"}
     except Exception as e:      # noqa: BLE001  (the bench line must still come out)
         return {"error": "%s: %s" % (type(e).__name__, e)}
     finally:
