@@ -340,8 +340,8 @@ def cli_e2e(tpl, raw_unique, n_blocks, device):
                 "fixed_cost_seconds": (best_q - lines_q / steady) if steady else None,
                 "best_seconds": best, "best_blocks_per_s": n_blocks / best,
                 "what": "thrifty_b200.detect.detector_cli(Detector) in-process on a synthetic .card in /dev/shm: file read + "
-                        "GPU base64 decode + detect + .toad text; interpreter start-up and imports excluded; "
-                        "seconds = median of 5 runs after 2 warm-up runs; steady_blocks_per_s = extra blocks / extra seconds between the best quarter-file run and the best whole-file run"}
+                        "GPU base64 decode + detect + .toad text; interpreter start-up, imports, CUDA context and the two page-locked staging buffers (pinned once per process) "
+                        "excluded; seconds = median of 5 runs after 2 warm-up runs; steady_blocks_per_s = extra blocks / extra seconds between the best quarter-file run and the best whole-file run"}
     except Exception as e:      # noqa: BLE001  (the bench line must still come out)
         return {"error": "%s: %s" % (type(e).__name__, e)}
     finally:

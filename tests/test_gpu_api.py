@@ -152,6 +152,14 @@ def test_card_ingest_gpu_decode():
     results = list(d.detect_card_stream(io.BytesIO(text.getvalue().encode()), chunk_bytes=50000))
     assert len(results) == len(raw)
     parity.compare_records(_rows_as_records(_results_to_rows(results)), ref, what="card stream")
+    # the two page-locked staging buffers are pinned once per process: a second stream of the same chunk size gets the
+    # same memory back (and the same results)
+    from thrifty_b200 import _native
+    cached = {b.ptr for b in _native._staging_pool.get(50000 + 1, [])}
+    assert cached
+    again = list(d.detect_card_stream(io.BytesIO(text.getvalue().encode()), chunk_bytes=50000))
+    assert {b.ptr for b in _native._staging_pool.get(50000 + 1, [])} == cached
+    assert [(ok, r.serialize() if ok else r.block) for ok, r in again] == [(ok, r.serialize() if ok else r.block) for ok, r in results]
     d.close()
 
 

@@ -7,8 +7,10 @@ device is usable, constructing a detector raises.  Build the library with
 
 from __future__ import annotations
 
+import atexit
 import ctypes
 import os
+import threading
 from ctypes import (POINTER, Structure, byref, c_char, c_char_p, c_double, c_float, c_int,
                     c_int32, c_int64, c_size_t, c_uint32, c_void_p)
 
@@ -220,6 +222,52 @@ class PinnedBuffer(object):
             self.close()
         except Exception:
             pass
+
+
+# Page-locked staging buffers of the stream readers, kept for the life of the process: pinning costs 0.6-1 ms per MiB and
+# cudaFreeHost / cudaMallocHost now and then stall for 0.2-0.7 s (measured: tools/cli_stalls.py), so a process that
+# reads many `.card` streams pins its two buffers once.  At most _STAGING_KEEP buffers per size stay cached.
+_STAGING_KEEP = 4
+_staging_pool = {}
+_staging_lock = threading.Lock()
+
+
+def acquire_staging(nbytes):
+    """A PinnedBuffer of exactly `nbytes` from the per-process cache, or a new one."""
+    with _staging_lock:
+        cached = _staging_pool.get(nbytes)
+        if cached:
+            return cached.pop()
+    return PinnedBuffer(nbytes)
+
+
+def release_staging(buf):
+    """Hand a buffer from acquire_staging back (it stays page-locked for the next reader)."""
+    if buf is None or not buf.ptr:
+        return
+    if getattr(buf, "nbytes", None) is None:     # (a test double)
+        buf.close()
+        return
+    with _staging_lock:
+        cached = _staging_pool.setdefault(buf.nbytes, [])
+        if len(cached) < _STAGING_KEEP:
+            cached.append(buf)
+            return
+    buf.close()
+
+
+def _forget_staging():
+    # interpreter exit: the driver unmaps everything with the process; an explicit cudaFreeHost per buffer only adds
+    # wall clock to the end of a command-line run
+    with _staging_lock:
+        for cached in _staging_pool.values():
+            for buf in cached:
+                buf.array = None
+                buf.ptr = None
+        _staging_pool.clear()
+
+
+atexit.register(_forget_staging)
 
 
 def _make_config(self, block_len, history_len, templates, carrier_len, carrier_window, carrier_thresh, corr_thresh,

@@ -20,6 +20,7 @@ from __future__ import print_function
 
 import argparse
 import gc
+import os
 import sys
 from collections import namedtuple
 
@@ -215,7 +216,7 @@ class Detector(object):
         import stat
         import threading
         from concurrent.futures import ThreadPoolExecutor
-        from thrifty_b200._native import PinnedBuffer
+        from thrifty_b200._native import acquire_staging, release_staging
         line_len = ((2 * self.settings.block_len + 2) // 3) * 4 + 64
         if chunk_bytes is None:                  # size of each staging buffer; THRIFTY_B200_CARD_CHUNK_MB overrides
             chunk_bytes = int(float(os.environ.get("THRIFTY_B200_CARD_CHUNK_MB", "16")) * (1 << 20))
@@ -230,8 +231,8 @@ class Detector(object):
         except (AttributeError, OSError, ValueError):
             pass
         read_into = getattr(stream, "readinto1", None) or getattr(stream, "readinto", None)
-        # two page-locked buffers (one spare byte keeps the C number parser inside the allocation), allocated by the
-        # reader thread when it first needs them: pinning costs 0.6-1 ms per MiB (the fixed cost of a short run), and while the
+        # two page-locked buffers (one spare byte keeps the C number parser inside the allocation), taken from the
+        # per-process cache or allocated by the reader thread when it first needs them: pinning costs 0.6-1 ms per MiB (the fixed cost of a short run), and while the
         # reader bounds the rate 16 MiB chunks (~380 lines of 16384 samples) keep the GPU side above it
         bufs = []
         free_q, ready_q = queue.Queue(), queue.Queue()
@@ -242,7 +243,7 @@ class Detector(object):
                 return free_q.get_nowait()
             except queue.Empty:
                 if len(bufs) < 2:
-                    bufs.append(PinnedBuffer(chunk_bytes + 1))
+                    bufs.append(acquire_staging(chunk_bytes + 1))
                     return bufs[-1]
                 return free_q.get()
 
@@ -341,9 +342,9 @@ class Detector(object):
             stop.set()
             free_q.put(None)
             thread.join(timeout=5)
-            if not thread.is_alive():            # (a reader stuck in a blocking read keeps its buffers: never free
+            if not thread.is_alive():            # (a reader stuck in a blocking read keeps its buffers: never recycle
                 for b in bufs:                   # page-locked memory a thread may still write to)
-                    b.close()
+                    release_staging(b)           # stays pinned for the next stream of this process
 
     def detect_card_stream(self, stream, chunk_bytes=None, min_lines=None):
         """Yield (detected, DetectionResult) for every data line of a binary `.card` stream.
@@ -587,7 +588,10 @@ def detector_cli(detector_class, parser=None, extra_args=None, argv=None):
     if detector_class is Detector and len(templates) > 1:
         _multi_template_cli(settings, [np.load(t) for t in templates], blocks, config, args, output_file, info_out)
         return
+    import time as _time
+    marks = [("start", _time.perf_counter())]            # THRIFTY_B200_CLI_TIMING=1: phase times of the quiet path on stderr
     detections = detector_class(settings, blocks, rxid=config.rxid, **kwargs)
+    marks.append(("detector created", _time.perf_counter()))
     if detector_class is Detector and not args.raw and not args.host_decode and args.quiet:
         # fastest path: nothing is printed per block, so no result objects are built either -- records go straight to
         # .toad text (thr_format_toad: the same characters DetectionResult.serialize() produces)
@@ -619,13 +623,19 @@ def detector_cli(detector_class, parser=None, extra_args=None, argv=None):
         if wthread is not None:
             wthread.start()
         try:
+            gaps = []
             for ts, _, recs in detections.iter_card_records(args.input):
+                gaps.append(_time.perf_counter())
                 if wthread is not None and not failed:
                     todo.put((recs, ts))
+            marks.append(("%d chunks (first after %.1f ms, longest gap %.1f ms)"
+                          % (len(gaps), (gaps[0] - marks[-1][1]) * 1e3 if gaps else 0.0,
+                             max(np.diff(gaps)) * 1e3 if len(gaps) > 1 else 0.0), _time.perf_counter()))
         finally:
             if wthread is not None:
                 todo.put(None)
                 wthread.join()
+        marks.append(("writer joined", _time.perf_counter()))
         if failed:
             raise failed[0]
         if output_file is not None:
@@ -633,6 +643,10 @@ def detector_cli(detector_class, parser=None, extra_args=None, argv=None):
                 sink.flush()
             output_file.flush()
         detections.close()
+        marks.append(("closed", _time.perf_counter()))
+        if os.environ.get("THRIFTY_B200_CLI_TIMING"):
+            print("detect --quiet: " + ", ".join("%s +%.1f ms" % (name, (t - marks[i][1]) * 1e3)
+                                                 for i, (name, t) in enumerate(marks[1:])), file=sys.stderr)
         return
     if detector_class is Detector and not args.raw and not args.host_decode:
         # fast path: the `.card` text is decoded on the GPU (same records, same order)
