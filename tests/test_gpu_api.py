@@ -565,6 +565,42 @@ def test_n32768_two_half_kernel_shifted_band():
     det.close()
 
 
+@pytest.mark.parametrize("window,cthresh,bins", [
+    ((7, 300), (0., 15., 0.), (9.0, 298.0)),             # wide window: FFT#1 in full
+    ((-400, -5), (0., 15., 0.), (-398.0, -7.0)),         # negative frequencies: bins of the upper half spectrum
+    ((5, -5), (2.0, 12., 0.), (-16000.0, 16000.0)),      # every bin but the DC leak of rawconv (a peak there is noise on
+                                                         # both sides: the fit is ill-conditioned), constant term
+    ((7, 110), (0., 12., 2.5), (9.0, 108.0)),            # narrow window, but a stddev term needs every magnitude
+    ((16000, 16800), (0., 15., 1.0), (16010.0, 16790.0)),  # window across the seam between the two half spectra
+])
+def test_n32768_two_half_kernel_full_fft1(window, cthresh, bins):
+    """2 x 16384 kernel with FFT#1 computed in full (carrier window wider than the 128-bin zoom band, or a carrier stddev
+    threshold term): oracle parity, agreement with the generic kernel, and several blocks per CTA."""
+    from thrifty_b200._native import NativeDetector
+    tpl = np.load(os.path.join(os.path.dirname(__file__), "golden", "template_example.npy"))
+    n, h = 32768, 4920
+    raw, _ = synth.make_blocks(40, n, h, tpl, 0.7, seed=9003, bin_range=bins)
+    idx = 3 + 2 * np.arange(40, dtype=np.int64)
+    st = orc.DetectorSettings(n, h, len(tpl), cthresh, window, tpl, (0., 15., 0.))
+    ref = orc.detect_blocks(st, raw, idx)
+    two = NativeDetector(n, h, tpl, len(tpl), window, cthresh, (0., 15., 0.), max_batch=700)
+    gen = NativeDetector(n, h, tpl, len(tpl), window, cthresh, (0., 15., 0.), max_batch=64, generic_kernel=True)
+    assert "detect2x" in two.info()["kernel"] and "gmem" in gen.info()["kernel"]
+    got2 = two.detect_raw(raw, idx)[:, 0]
+    gotg = gen.detect_raw(raw, idx)[:, 0]
+    stats = parity.compare_records(got2, ref, what="n32768/2x full FFT#1")
+    parity.compare_records(gotg, ref, what="n32768/generic")
+    assert stats["carrier"] > 10
+    for f in ("flags", "carrier_bin", "corr_sample"):
+        assert np.array_equal(got2[f], gotg[f]), f
+    gotb = two.detect_raw(raw[np.arange(700) % 40])[:, 0]          # 4-5 blocks per CTA through the pipeline
+    for f in ("flags", "carrier_bin", "corr_sample", "corr_energy", "corr_offset", "carrier_offset", "carrier_energy"):
+        assert np.array_equal(gotb[f][:40], gotb[f][40 * 16:40 * 17], equal_nan=True), f
+        assert np.array_equal(gotb[f][:40], got2[f], equal_nan=True), f
+    two.close()
+    gen.close()
+
+
 @pytest.mark.parametrize("kthresh", [(0., 15., 0.), (0.5, 10., 3.)])
 def test_n32768_two_half_kernel_vs_generic_and_oracle(kthresh):
     """block_len 32768 runs as two interleaved 16384-point transforms (detect_kernel_2x.cuh) when FFT#1 can

@@ -15,10 +15,11 @@
 // leaves the SM.  |c|^2 of every lag is also written there so that the neighbours of the peak (which
 // belong to the other half-transform) can be fetched without keeping 64 more registers alive.
 //
-// Scope: the pruned ("zoom") FFT#1 configurations only -- carrier window (+-3 bins) at most 128 bins wide (moved to
-// bin 0 by an integer pre-shift if necessary), no carrier stddev threshold term, one template (true for
-// example/detector.cfg).  Every other configuration at
-// this block length runs the generic global-scratch variant of detect_kernel.
+// Scope: one template (true for example/detector.cfg).  FFT#1 is pruned ("zoom") when the carrier window (+-3 bins) is at
+// most 128 bins wide (moved to bin 0 by an integer pre-shift if necessary) and there is no carrier stddev threshold term;
+// otherwise both half transforms of FFT#1 are computed in full and joined the same way as FFT#2, with |X|^2 of all 32768
+// bins parked in the scratch area for the arg-max key and the 7 fit magnitudes.  Several templates at this block length
+// run the generic global-scratch variant of detect_kernel.
 //
 // Same semantics, mailboxes, service-warp pipeline and record format as detect_kernel (see there for the
 // reference citations of each stage).
@@ -54,6 +55,7 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
     constexpr uint32_t RAW_BYTES = 2u * NB;
     constexpr int NTHREADS = T + 32;
     constexpr uint32_t A1_STEP = (uint32_t)(M / 16) * 136u, A2_STEP = 136u;
+    constexpr int S = 32 * R2;                       // bin stride of the pass-3 outputs
 
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x;
@@ -329,6 +331,101 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
                 par ^= 1;
             }
             float tenergy = 0.f;
+            FitSlot &fs = fitslot[q];
+            if (!p.zoom) {
+                // ---- full FFT #1 (wide carrier window or a stddev threshold term): both halves are transformed
+                // completely, E is parked like E' of stage B, the radix-2 join happens on this thread's pass-3 outputs of
+                // O; |X|^2 of all NB bins goes to the (idle) |c|^2 area of the scratch so that the arg-max key and the
+                // 7 fit magnitudes can be fetched without keeping 64 powers per thread in registers
+                float *pws = cps;
+                float bestv = 0.f, msum = 0.f;
+#pragma unroll 1
+                for (int h = 0; h < 2; ++h) {
+                    pass1(std::false_type{}, std::false_type{}, ia, h, make_float2(1.f, 0.f), nullptr, tenergy);
+                    bar_sync(BAR_MAIN, T);
+                    // the raw stage is not read again in stage A: fetch the next block's tile into it
+                    if (h == 1 && use_raw && tid == 0 && has_block(ia + 1)) issue_tile(ia + 1);
+                    pass2();
+                    __syncwarp();
+#pragma unroll 1
+                    for (int it = 0; it < 2; ++it) {
+                        const int g = H::p3_item(tid, it);
+                        const uint32_t ab = (uint32_t)g * 136u;
+                        float2 x[R3];
+#pragma unroll
+                        for (int n3 = 0; n3 < R3; ++n3) x[brev(n3, LOG2R3)] = ld8(ab + (uint32_t)n3 * 8u);
+                        fft_dit<R3, false>(x);
+                        float2 *park = &scrE[(size_t)(it * R3) * T + tid];
+                        if (h == 0) {                                                    // E: parked
+#pragma unroll
+                            for (int k3 = 0; k3 < R3; ++k3) __stcg(&park[(size_t)k3 * T], x[k3]);
+                        } else {                                                         // O: join with E
+                            const int kb = (g >> LOG2R2) + 32 * (g & (R2 - 1));          // bin k = kb + S k3 < F
+                            const float2 wb = cispi(-2.0f * (float)kb / (float)NB);      // W_NB^kb
+                            const uint32_t relb = (uint32_t)(kb - p.win_start) & (uint32_t)(NB - 1);
+#pragma unroll
+                            for (int k3 = 0; k3 < R3; ++k3) {
+                                const float2 ev = __ldcg(&park[(size_t)k3 * T]);
+                                const float2 w = (k3 == 0) ? wb : mul_tw<false>(wb, cos32(k3), sin32(k3));
+                                const float2 t = cmul(x[k3], w);
+                                const float2 lo = f2add(ev, t), hi = f2sub(ev, t);       // X[k], X[k + F]
+                                const float plo = lo.x * lo.x + lo.y * lo.y, phi = hi.x * hi.x + hi.y * hi.y;
+                                const int k = kb + S * k3;
+                                __stcg(&pws[k], plo);
+                                __stcg(&pws[k + F], phi);
+                                if (p.c_std != 0.f) msum += sqrtf(plo) + sqrtf(phi);
+                                const uint32_t rlo = (relb + (uint32_t)(S * k3)) & (uint32_t)(NB - 1);
+                                const uint32_t rhi = (rlo + (uint32_t)F) & (uint32_t)(NB - 1);
+                                if (rlo < (uint32_t)p.win_len) bestv = fmaxf(bestv, plo);
+                                if (rhi < (uint32_t)p.win_len) bestv = fmaxf(bestv, phi);
+                            }
+                        }
+                    }
+                    if (h == 0) bar_sync(BAR_MAIN, T);      // every warp is done reading the buffer
+                }
+                // first maximum in window order (np.argmax over the wrapped window, carrier_detect.py:138-149); the
+                // thread that holds the maximum re-reads its own powers from the scratch
+                const ArgOut ra = main_argmax<T, true>(__float_as_uint(bestv), tenergy, msum, red, tid, [&](uint32_t gb) {
+                    uint32_t key = 0xffffffffu;
+#pragma unroll 1
+                    for (int it = 0; it < 2; ++it) {
+                        const int g = H::p3_item(tid, it);
+                        const int kb = (g >> LOG2R2) + 32 * (g & (R2 - 1));
+                        const uint32_t relb = (uint32_t)(kb - p.win_start) & (uint32_t)(NB - 1);
+#pragma unroll 1
+                        for (int k3 = 0; k3 < R3; ++k3) {
+                            const int k = kb + S * k3;
+                            const uint32_t rlo = (relb + (uint32_t)(S * k3)) & (uint32_t)(NB - 1);
+                            const uint32_t rhi = (rlo + (uint32_t)F) & (uint32_t)(NB - 1);
+                            if (rlo < (uint32_t)p.win_len && __float_as_uint(__ldcg(&pws[k])) == gb) key = min(key, rlo);
+                            if (rhi < (uint32_t)p.win_len && __float_as_uint(__ldcg(&pws[k + F])) == gb) key = min(key, rhi);
+                        }
+                    }
+                    return key;
+                });
+                // carrier decision in float32 (carrier_detect.py:99-115); Parseval: sum |X|^2 = NB sum |x|^2
+                const float s0 = ra.s0 * (float)NB;
+                const float peak_mag = sqrtf(__uint_as_float(ra.vbits));
+                const int kpeak = (p.win_start + (int)ra.key) & (NB - 1);
+                const float noise_c = sqrtf((s0 - 2.f * (peak_mag * peak_mag)) / (float)(NB - 1));
+                float var_c = 0.f;
+                if (p.c_std != 0.f) {
+                    const float mean = ra.s1 / (float)NB;
+                    var_c = fmaxf(s0 / (float)NB - mean * mean, 0.f);
+                }
+                const bool carrier = peak_mag > sqrtf(p.c_const + p.c_snr * (noise_c * noise_c) + p.c_std * var_c);
+                if (tid == 0) {
+                    fs.kpeak = kpeak;
+                    fs.carrier = carrier ? 1 : 0;
+                    fs.peak_mag = peak_mag;
+                    fs.noise_c = noise_c;
+                    fs.sig_energy1 = s0 / (float)NB;
+                    fs.delta = 0.f;
+                }
+                // (every power was written before the two barriers of the arg-max: visible to these threads)
+                if (carrier && tid < 7) fs.mags[tid] = sqrtf(__ldcg(&pws[(kpeak - 3 + tid) & (NB - 1)]));
+                bar_arrive(BAR_FITREQ + q, NTHREADS);
+            } else {
             const bool shiftA = (p.zoom_base != 0);
 #pragma unroll 1
             for (int h = 0; h < 2; ++h) {
@@ -368,7 +465,6 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
                 zpow[tid] = xk.x * xk.x + xk.y * xk.y;
             }
             bar_sync(BAR_MAIN, T);
-            FitSlot &fs = fitslot[q];
             uint32_t vb = 0u;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -404,6 +500,7 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
             }
             if (carrier && tid < 7) fs.mags[tid] = sqrtf(zpow[p.zoom_w0 + (int)key - 3 + tid]);
             bar_arrive(BAR_FITREQ + q, NTHREADS);
+            }   // zoom
         }
 
         // ================================================================= B(i): mix, FFT #2, correlation

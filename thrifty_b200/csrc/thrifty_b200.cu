@@ -298,8 +298,9 @@ int thr_create(const thr_config *cfg, thr_detector **out) {
         return fail(nullptr, THR_ERR_INVALID, "Frequency window out of range: %d - %d", cfg->window_start,
                     cfg->window_stop);
 
-    // block_len 32768 with a pruned-FFT#1 configuration: two interleaved 16384-point transforms in shared memory
-    // (detect_kernel_2x.cuh) instead of the generic global-scratch variant, which stays for debug launches
+    // block_len 32768 with one template: two interleaved 16384-point transforms in shared memory
+    // (detect_kernel_2x.cuh; FFT#1 pruned or in full) instead of the generic global-scratch variant, which stays for
+    // several templates and for debug launches
     // pruned FFT#1: the carrier window and its +-3 fit neighbours span at most 128 consecutive bins (mod N), no stddev
     // term.  The band starts at bin 0 when the window lies in [3,124] (no pre-shift), else 3 bins below the window.
     const int wlen_cfg = (we - ws + 1) > N ? N : (we - ws + 1);
@@ -307,7 +308,7 @@ int thr_create(const thr_config *cfg, thr_detector **out) {
     const int zoom_base = (ws >= 3 && we + 3 < 128) ? 0 : ((ws % N) - 3 + N) % N;
     Variant var_generic = var;
     bool use_2x = false;
-    if (zoom_cfg && NT == 1 && N == 32768 && !(cfg->flags & THR_CFG_GENERIC_KERNEL)) {
+    if (!fastdet && NT == 1 && N == 32768 && !(cfg->flags & THR_CFG_GENERIC_KERNEL)) {
         Variant v2;
         if (thr::pick_variant_2x(N, &v2)) {
             var = v2;

@@ -31,6 +31,7 @@ cases = [
     (4096, t9, None, (7, 110), 12, {}),                                # 4 CTAs/SM variant
     (4096, t9, None, (1, 2047), 8, dict(fastdet=True)),                # fastdet gather fall-back
     (32768, example, 4920, (7, 110), 7, {}),                           # 2 x 16384 kernel
+    (32768, example, 4920, (7, 300), 7, {}),                           # ... with FFT#1 in full (powers parked in the scratch)
     (32768, example, 4920, (7, 110), 4, dict(generic_kernel=True)),    # global-scratch variant
 ]
 only = [int(a) for a in sys.argv[1:]]                                 # optional: block lengths to run

@@ -22,13 +22,13 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
 def run(block_len, templates, history, batch, p_signal, steps=64, warmup=4, window=(7, 110), unique=256,
-        label="", fastdet=False, bin_range=(8.0, 109.0)):
+        label="", fastdet=False, bin_range=(8.0, 109.0), generic=False):
     lib = load_library()
     tpl0 = templates[0] if templates.ndim == 2 else templates
     raw, _ = synth.make_blocks(unique, block_len, history, tpl0, p_signal, seed=424242, bin_range=bin_range)
     n_tpl = templates.shape[0] if templates.ndim == 2 else 1
     det = NativeDetector(block_len, history, templates, len(tpl0), window, (0., 15., 0.), (0., 15., 0.),
-                         max_batch=batch, overlap_launches=True, fastdet=fastdet)
+                         max_batch=batch, overlap_launches=True, fastdet=fastdet, generic_kernel=generic)
     # pool > L2 (126 MB): at least 160 MiB of raw blocks, a multiple of the batch
     pool_blocks = max(2 * batch, ((160 << 20) // (2 * block_len) + batch - 1) // batch * batch)
     host = np.ascontiguousarray(raw[np.arange(pool_blocks) % unique])
@@ -185,6 +185,9 @@ def main():
     run(16384, example, 4920, 4096, 1.0, window=(-110, -7), bin_range=(-108.0, -9.0),
         label="N=16384 window -110..-7 (pruned FFT#1, pre-shifted band)")
     run(32768, example, 4920, 2048, 1.0, steps=16, label="cfg3 N=32768 (2 x 16384 kernel)")
+    run(32768, example, 4920, 2048, 1.0, window=(7, 300), label="N=32768 full FFT#1 (window 7-300, 2 x 16384 kernel)")
+    run(32768, example, 4920, 2048, 1.0, window=(7, 300), steps=8, generic=True,
+        label="N=32768 full FFT#1 on the generic global-scratch kernel (what several templates at this length still use)")
     # signal mixes at N=16384
     run(16384, example, 4920, 4096, 0.5, label="N=16384 50% burst blocks")
     run(16384, example, 4920, 4096, 0.0, label="N=16384 noise only")
