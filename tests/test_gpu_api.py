@@ -456,6 +456,47 @@ def test_multi_template_vs_independent_oracles():
     det.close()
 
 
+@pytest.mark.parametrize("window", [(7, 110), (7, 300)])
+def test_multi_template_n32768_two_half_kernel(window):
+    """Three Gold-11 templates jointly at block_len 32768: the 2 x 16384 kernel (E' and O' parked for the template loop)
+    == three independent oracle detectors == the generic global-scratch kernel; several blocks per CTA."""
+    from thrifty_b200._native import NativeDetector
+    n = 32768
+    tpls = np.stack([synth.gold_template(11, i) for i in range(3)])
+    hist = tpls.shape[1] + 6
+    rng = np.random.default_rng(12)
+    raws = []
+    for b in range(30):
+        t = int(rng.integers(0, 3))
+        r, _ = synth.make_blocks(1, n, hist, tpls[t], 0.8, seed=7100 + b, bin_range=(9.0, window[1] - 2.0))
+        raws.append(r[0])
+    raws = np.stack(raws)
+    idx = 7 + 3 * np.arange(len(raws), dtype=np.int64)
+    two = NativeDetector(n, hist, tpls, tpls.shape[1], window, (0., 15., 0.), (0., 15., 0.), max_batch=600)
+    gen = NativeDetector(n, hist, tpls, tpls.shape[1], window, (0., 15., 0.), (0., 15., 0.), max_batch=64, generic_kernel=True)
+    assert "detect2x" in two.info()["kernel"] and "gmem" in gen.info()["kernel"]
+    got2 = two.detect_raw(raws, idx)
+    gotg = gen.detect_raw(raws, idx)
+    assert got2.shape == (len(raws), 3)
+    n_det = 0
+    for t in range(3):
+        st = orc.DetectorSettings(n, hist, tpls.shape[1], (0., 15., 0.), window, tpls[t], (0., 15., 0.))
+        ref = orc.detect_blocks(st, raws, idx)
+        stats = parity.compare_records(got2[:, t], ref, what="n32768/2x template %d" % t)
+        parity.compare_records(gotg[:, t], ref, what="n32768/generic template %d" % t)
+        assert np.all(got2[:, t]["template_idx"] == t)
+        n_det += stats["detected"]
+        for f in ("flags", "carrier_bin", "corr_sample"):
+            assert np.array_equal(got2[:, t][f], gotg[:, t][f]), f
+    assert n_det > 10
+    big = two.detect_raw(raws[np.arange(600) % 30])                    # 4 blocks per CTA through the pipeline
+    for f in ("flags", "carrier_bin", "corr_sample", "corr_energy", "corr_offset", "carrier_offset"):
+        assert np.array_equal(big[f][:30], big[f][30 * 19:30 * 20], equal_nan=True), f
+        assert np.array_equal(big[f][:30], got2[f], equal_nan=True), f
+    two.close()
+    gen.close()
+
+
 def test_multi_template_n16384_gold11x4_vs_reference_golden():
     """BASELINE config 5 at its stated size: four Gold-11 templates (L=4914), block_len 16384, history 4920, 320 blocks
     (> 2 per persistent CTA) through MultiTemplateDetector == four independent runs of the reference's own Detector

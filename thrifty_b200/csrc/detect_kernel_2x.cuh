@@ -15,11 +15,12 @@
 // leaves the SM.  |c|^2 of every lag is also written there so that the neighbours of the peak (which
 // belong to the other half-transform) can be fetched without keeping 64 more registers alive.
 //
-// Scope: one template (true for example/detector.cfg).  FFT#1 is pruned ("zoom") when the carrier window (+-3 bins) is at
-// most 128 bins wide (moved to bin 0 by an integer pre-shift if necessary) and there is no carrier stddev threshold term;
-// otherwise both half transforms of FFT#1 are computed in full and joined the same way as FFT#2, with |X|^2 of all 32768
-// bins parked in the scratch area for the arg-max key and the 7 fit magnitudes.  Several templates at this block length
-// run the generic global-scratch variant of detect_kernel.
+// Scope: every configuration of the Python path's semantics at this block length.  FFT#1 is pruned ("zoom") when the
+// carrier window (+-3 bins) is at most 128 bins wide (moved to bin 0 by an integer pre-shift if necessary) and there is no
+// carrier stddev threshold term; otherwise both half transforms of FFT#1 are computed in full and joined the same way as
+// FFT#2, with |X|^2 of all 32768 bins parked in the scratch area for the arg-max key and the 7 fit magnitudes.  With
+// several templates O' and the odd-lag spectrum get parking areas of their own (DetectParams::xsave), so that E' and O'
+// survive the template loop.  The generic global-scratch variant of detect_kernel remains for debug launches.
 //
 // Same semantics, mailboxes, service-warp pipeline and record format as detect_kernel (see there for the
 // reference citations of each stage).
@@ -39,8 +40,9 @@ struct Cfg2x {
     static constexpr int R2 = 32, R3 = 16, S = 32 * R2;
     static constexpr int LAUNCH_THREADS = T + 128;
     static constexpr size_t BUF_BYTES = (size_t)(F / 16) * 136;
+    static constexpr int MAX_TPL = 32;               // templates per detector (tail mailbox size, as Cfg::MAX_TPL)
     static constexpr size_t smem_bytes() {
-        return BUF_BYTES + (size_t)(2 * NB) + (size_t)M * 8 + 2 * 320 + 2 * 32 + 2 * 32 + 256
+        return BUF_BYTES + (size_t)(2 * NB) + (size_t)M * 8 + 2 * 320 + 2 * 32 + 2 * MAX_TPL * 32 + 256
                + 2 * 128 * 8 + 512 + 256 + 64 + sizeof(lm::Rows);
     }
     using Half = Cfg<14, 512, false>;                // geometry of one half (pass-3 item order)
@@ -72,8 +74,8 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
     off += 2 * sizeof(FitSlot);
     TailHdr *tailhdr = reinterpret_cast<TailHdr *>(smem + off);          // [2]
     off += 2 * sizeof(TailHdr);
-    TailSlot *tailslot = reinterpret_cast<TailSlot *>(smem + off);       // [2]
-    off += 2 * sizeof(TailSlot);
+    TailSlot *tailslot = reinterpret_cast<TailSlot *>(smem + off);       // [2][MAX_TPL]
+    off += 2 * (size_t)C::MAX_TPL * sizeof(TailSlot);
     uint32_t *red = reinterpret_cast<uint32_t *>(smem + off);
     off += 256;
     float2 *zc = reinterpret_cast<float2 *>(smem + off);                 // [2][128] pruned spectra of E, O
@@ -91,6 +93,11 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
     auto has_block = [&](int i) -> bool { return (int)blockIdx.x + i * (int)gridDim.x < p.n_blocks; };
     float2 *scrE = p.scratch + (size_t)blockIdx.x * NB;                  // F float2: parked half spectrum
     float *cps = reinterpret_cast<float *>(scrE + F);                    // [2][F] floats: |c|^2 per lag parity
+    // several templates: O' (pass-3 outputs of the odd half) and the odd-lag spectrum B get their own parking areas, so
+    // that E' and O' survive the template loop; with one template B simply overwrites E'
+    const int n_tpl = p.n_templates > 1 ? p.n_templates : 1;
+    float2 *scrO = p.xsave ? p.xsave + (size_t)blockIdx.x * NB : nullptr;
+    float2 *scrB = (n_tpl > 1) ? scrO + F : scrE;
 
     asm volatile("griddepcontrol.launch_dependents;");
     if (tid == 0) {
@@ -119,14 +126,15 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
     auto do_tail = [&](int i, int q) {
         const TailHdr &h = tailhdr[q];
         const int blk = (int)blockIdx.x + i * (int)gridDim.x;
-        if (lane == 0) {
+        if (lane < n_tpl) {
+            const int tpl = lane;
             const int64_t bidx = p.block_idx ? p.block_idx[blk] : (int64_t)blk;
             thr_record rec;
             rec.block_idx = bidx;
             rec.carrier_bin = h.kpeak;
             rec.carrier_energy = h.peak_mag;
             rec.carrier_noise = h.noise_c;
-            rec.template_idx = 0;
+            rec.template_idx = tpl;
             rec.reserved = 0.f;
             rec.signal_energy = h.sig_energy1;
             if (!h.carrier) {
@@ -138,9 +146,9 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
                 rec.corr_noise = __int_as_float(0x7fc00000);
                 rec.flags = 0u;
             } else {
-                const TailSlot &ts = tailslot[q];
+                const TailSlot &ts = tailslot[q * C::MAX_TPL + tpl];
                 const float peak_mag_k = sqrtf(ts.peak_cp);
-                const float noise_pw = (h.sig_energy1 * p.tpl_energy[0] - ts.peak_cp) / (float)NB;
+                const float noise_pw = (h.sig_energy1 * p.tpl_energy[tpl] - ts.peak_cp) / (float)NB;
                 const float noise_k = sqrtf(noise_pw);                 // NaN if negative
                 float var_k = 0.f;
                 if (need_std_k) {
@@ -163,7 +171,7 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
                 rec.corr_noise = noise_k;
                 rec.flags = THR_FLAG_CARRIER_DETECTED | (detected ? THR_FLAG_CORR_DETECTED : 0u);
             }
-            p.out[blk] = rec;
+            p.out[(size_t)blk * n_tpl + tpl] = rec;
         }
     };
 
@@ -530,7 +538,6 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
             const float turns0 = -((float)e0 / (float)F) - delta * ((float)tid / (float)F)
                                  + 0.5f * (float)(kpeak & 1) + 0.5f * delta;
             const float turns_h = -((float)kpeak + delta) / (float)NB;
-            const float2 *tlo = p.tpl_spec, *thi = p.tpl_spec + F;
             float unused_energy = 0.f;
 
             // ---- half 0: E' = FFT_F(x'[2m]) -> parked
@@ -555,6 +562,10 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
             bar_sync(BAR_MAIN, T);
             pass2();
             __syncwarp();
+            // ---- per template: join, x conj(T)/N, the two inverse half-transforms, |c|^2 arg-max
+#pragma unroll 1
+            for (int tpl = 0; tpl < n_tpl; ++tpl) {
+            const float2 *tlo = p.tpl_spec + (size_t)tpl * NB, *thi = tlo + F;
 #pragma unroll
             for (int it = 0; it < 2; ++it) {
                 const int g = H::p3_item(tid, it);
@@ -565,9 +576,18 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
                 // into a per-thread local-memory table (reloads would miss the small L1)
                 asm volatile("" : "+f"(wb.x), "+f"(wb.y));
                 float2 x[R3];
+                if (tpl == 0) {          // pass 3 of O'; kept for the other templates
 #pragma unroll
-                for (int n3 = 0; n3 < R3; ++n3) x[brev(n3, LOG2R3)] = ld8(ab + (uint32_t)n3 * 8u);
-                fft_dit<R3, false>(x);
+                    for (int n3 = 0; n3 < R3; ++n3) x[brev(n3, LOG2R3)] = ld8(ab + (uint32_t)n3 * 8u);
+                    fft_dit<R3, false>(x);
+                    if (n_tpl > 1) {
+#pragma unroll
+                        for (int k3 = 0; k3 < R3; ++k3) __stcg(&scrO[(size_t)(it * R3 + k3) * T + tid], x[k3]);
+                    }
+                } else {
+#pragma unroll
+                    for (int k3 = 0; k3 < R3; ++k3) x[k3] = __ldcg(&scrO[(size_t)(it * R3 + k3) * T + tid]);
+                }
                 float2 y[R3];
 #pragma unroll
                 for (int k3 = 0; k3 < R3; ++k3) {
@@ -579,7 +599,7 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
                     const float2 ylo = cmul(f2add(ev, t), __ldg(&tlo[sidx]));
                     const float2 yhi = cmul(f2sub(ev, t), __ldg(&thi[sidx]));
                     y[brev(k3, LOG2R3)] = f2add(ylo, yhi);
-                    __stcg(&scrE[sidx], cmulc(f2sub(ylo, yhi), w));
+                    __stcg(&scrB[sidx], cmulc(f2sub(ylo, yhi), w));
                 }
                 fft_dit<R3, true>(y);
 #pragma unroll
@@ -599,7 +619,7 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
                         float2 y[R3];
 #pragma unroll
                         for (int k3 = 0; k3 < R3; ++k3)
-                            y[brev(k3, LOG2R3)] = __ldcg(&scrE[(size_t)(it * R3 + k3) * T + tid]);
+                            y[brev(k3, LOG2R3)] = __ldcg(&scrB[(size_t)(it * R3 + k3) * T + tid]);
                         fft_dit<R3, true>(y);
 #pragma unroll
                         for (int n3 = 0; n3 < R3; ++n3) st8(ab + (uint32_t)n3 * 8u, y[n3]);
@@ -652,7 +672,7 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
                             }
                         }
                     }
-                    if (p.dbg_corr) {
+                    if (p.dbg_corr && tpl == 0) {
 #pragma unroll
                         for (int n1 = 0; n1 < 32; ++n1) {
                             const int lagd = 2 * (n1 * M + tid) + e;
@@ -679,7 +699,7 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
                 }
             }
             if (tid == 0) {
-                TailSlot &ts = tailslot[q];
+                TailSlot &ts = tailslot[q * C::MAX_TPL + tpl];
                 const int s = (int)best_lag;
                 ts.peak_cp = __uint_as_float(best_bits);
                 ts.s = s;
@@ -691,6 +711,7 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
                 ts.pa = __ldcg(&cps[(size_t)(sm1 & 1) * F + (sm1 >> 1)]);
                 ts.pc = __ldcg(&cps[(size_t)(sp1 & 1) * F + (sp1 >> 1)]);
             }
+            }   // templates (the next one reuses the FFT buffer: all pass-1' loads are done, arg-max barriers)
             bar_arrive(BAR_TAILREQ + q, NTHREADS);
         }
     }

@@ -298,9 +298,8 @@ int thr_create(const thr_config *cfg, thr_detector **out) {
         return fail(nullptr, THR_ERR_INVALID, "Frequency window out of range: %d - %d", cfg->window_start,
                     cfg->window_stop);
 
-    // block_len 32768 with one template: two interleaved 16384-point transforms in shared memory
-    // (detect_kernel_2x.cuh; FFT#1 pruned or in full) instead of the generic global-scratch variant, which stays for
-    // several templates and for debug launches
+    // block_len 32768: two interleaved 16384-point transforms in shared memory (detect_kernel_2x.cuh; FFT#1 pruned or in
+    // full, one or several templates) instead of the generic global-scratch variant, which stays for debug launches
     // pruned FFT#1: the carrier window and its +-3 fit neighbours span at most 128 consecutive bins (mod N), no stddev
     // term.  The band starts at bin 0 when the window lies in [3,124] (no pre-shift), else 3 bins below the window.
     const int wlen_cfg = (we - ws + 1) > N ? N : (we - ws + 1);
@@ -308,7 +307,7 @@ int thr_create(const thr_config *cfg, thr_detector **out) {
     const int zoom_base = (ws >= 3 && we + 3 < 128) ? 0 : ((ws % N) - 3 + N) % N;
     Variant var_generic = var;
     bool use_2x = false;
-    if (!fastdet && NT == 1 && N == 32768 && !(cfg->flags & THR_CFG_GENERIC_KERNEL)) {
+    if (!fastdet && N == 32768 && !(cfg->flags & THR_CFG_GENERIC_KERNEL)) {
         Variant v2;
         if (thr::pick_variant_2x(N, &v2)) {
             var = v2;
@@ -411,13 +410,13 @@ int thr_create(const thr_config *cfg, thr_detector **out) {
                     }
             if (use_2x) {                        // the generic kernel's own order for debug launches
                 const int Tg = var_generic.threads, R2g = var_generic.r2, R3g = var_generic.r3, I3g = var_generic.i3;
-                perm_generic.resize(N);
+                perm_generic.resize((size_t)NT * N);
                 for (int i = 0; i < I3g; ++i)
                     for (int k3 = 0; k3 < R3g; ++k3)
                         for (int tid = 0; tid < Tg; ++tid) {
                             const int g = var_generic.p3_item(tid, i);
                             const int k = (g / R2g) + 32 * (g % R2g) + 32 * R2g * k3;
-                            perm_generic[(size_t)(i * R3g + k3) * Tg + tid] =
+                            perm_generic[(size_t)t * N + (size_t)(i * R3g + k3) * Tg + tid] =
                                 make_float2((float)(a[k].real() / N), (float)(-a[k].imag() / N));
                         }
             }

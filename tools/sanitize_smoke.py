@@ -32,6 +32,7 @@ cases = [
     (4096, t9, None, (1, 2047), 8, dict(fastdet=True)),                # fastdet gather fall-back
     (32768, example, 4920, (7, 110), 7, {}),                           # 2 x 16384 kernel
     (32768, example, 4920, (7, 300), 7, {}),                           # ... with FFT#1 in full (powers parked in the scratch)
+    (32768, t11, None, (7, 110), 6, {}),                               # ... two templates (E', O' and B parked per template)
     (32768, example, 4920, (7, 110), 4, dict(generic_kernel=True)),    # global-scratch variant
 ]
 only = [int(a) for a in sys.argv[1:]]                                 # optional: block lengths to run

@@ -186,8 +186,12 @@ def main():
         label="N=16384 window -110..-7 (pruned FFT#1, pre-shifted band)")
     run(32768, example, 4920, 2048, 1.0, steps=16, label="cfg3 N=32768 (2 x 16384 kernel)")
     run(32768, example, 4920, 2048, 1.0, window=(7, 300), label="N=32768 full FFT#1 (window 7-300, 2 x 16384 kernel)")
+    g11 = np.stack([synth.gold_template(11, i) for i in range(4)])
+    run(32768, g11, g11.shape[1] + 6, 2048, 1.0, steps=8, label="N=32768, 4 Gold-11 templates (2 x 16384 kernel)")
+    run(32768, g11, g11.shape[1] + 6, 2048, 1.0, steps=4, generic=True,
+        label="N=32768, 4 Gold-11 templates on the generic global-scratch kernel (debug launches only)")
     run(32768, example, 4920, 2048, 1.0, window=(7, 300), steps=8, generic=True,
-        label="N=32768 full FFT#1 on the generic global-scratch kernel (what several templates at this length still use)")
+        label="N=32768 full FFT#1 on the generic global-scratch kernel (debug launches only)")
     # signal mixes at N=16384
     run(16384, example, 4920, 4096, 0.5, label="N=16384 50% burst blocks")
     run(16384, example, 4920, 4096, 0.0, label="N=16384 noise only")
