@@ -4,7 +4,7 @@
 
 namespace thr {
 
-bool pick_variant_2x(int n, Variant *out) {
+bool pick_variant_2x(int n, bool multi, Variant *out) {
     if (n != Cfg2x::NB) return false;
     using H = Cfg2x::Half;
     Variant v;
@@ -19,8 +19,9 @@ bool pick_variant_2x(int n, Variant *out) {
     v.launch_threads = Cfg2x::LAUNCH_THREADS;
     v.worker_regs = 112;               // detect_kernel_2x.cuh: setmaxnreg.inc 112 / dec 32
     v.smem = Cfg2x::smem_bytes();
-    v.fn = (const void *)&detect2x_kernel;
-    v.name = "detect2x_kernel<N=32768 as 2x16384,T=512,smem+L2 park>";
+    v.fn = multi ? (const void *)&detect2x_kernel<true> : (const void *)&detect2x_kernel<false>;
+    v.name = multi ? "detect2x_kernel<N=32768 as 2x16384,T=512,smem+L2 park,multi>"
+                   : "detect2x_kernel<N=32768 as 2x16384,T=512,smem+L2 park>";
     *out = v;
     return true;
 }

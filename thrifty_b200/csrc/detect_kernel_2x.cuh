@@ -48,6 +48,8 @@ struct Cfg2x {
     using Half = Cfg<14, 512, false>;                // geometry of one half (pass-3 item order)
 };
 
+// MULTI = false: exactly one template (no template loop, B parked over E'), as detect_kernel's MULTI
+template <bool MULTI>
 __global__ void __launch_bounds__(Cfg2x::LAUNCH_THREADS, 1)
 detect2x_kernel(const __grid_constant__ DetectParams p) {
     using C = Cfg2x;
@@ -74,8 +76,9 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
     off += 2 * sizeof(FitSlot);
     TailHdr *tailhdr = reinterpret_cast<TailHdr *>(smem + off);          // [2]
     off += 2 * sizeof(TailHdr);
-    TailSlot *tailslot = reinterpret_cast<TailSlot *>(smem + off);       // [2][MAX_TPL]
-    off += 2 * (size_t)C::MAX_TPL * sizeof(TailSlot);
+    constexpr int TPL_SLOTS = MULTI ? C::MAX_TPL : 1;                    // tail mailbox entries per block
+    TailSlot *tailslot = reinterpret_cast<TailSlot *>(smem + off);       // [2][TPL_SLOTS]
+    off += 2 * (size_t)TPL_SLOTS * sizeof(TailSlot);
     uint32_t *red = reinterpret_cast<uint32_t *>(smem + off);
     off += 256;
     float2 *zc = reinterpret_cast<float2 *>(smem + off);                 // [2][128] pruned spectra of E, O
@@ -95,9 +98,9 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
     float *cps = reinterpret_cast<float *>(scrE + F);                    // [2][F] floats: |c|^2 per lag parity
     // several templates: O' (pass-3 outputs of the odd half) and the odd-lag spectrum B get their own parking areas, so
     // that E' and O' survive the template loop; with one template B simply overwrites E'
-    const int n_tpl = p.n_templates > 1 ? p.n_templates : 1;
-    float2 *scrO = p.xsave ? p.xsave + (size_t)blockIdx.x * NB : nullptr;
-    float2 *scrB = (n_tpl > 1) ? scrO + F : scrE;
+    const int n_tpl = MULTI ? p.n_templates : 1;
+    float2 *scrO = MULTI ? p.xsave + (size_t)blockIdx.x * NB : nullptr;
+    float2 *scrB = MULTI ? scrO + F : scrE;
 
     asm volatile("griddepcontrol.launch_dependents;");
     if (tid == 0) {
@@ -146,7 +149,7 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
                 rec.corr_noise = __int_as_float(0x7fc00000);
                 rec.flags = 0u;
             } else {
-                const TailSlot &ts = tailslot[q * C::MAX_TPL + tpl];
+                const TailSlot &ts = tailslot[q * TPL_SLOTS + tpl];
                 const float peak_mag_k = sqrtf(ts.peak_cp);
                 const float noise_pw = (h.sig_energy1 * p.tpl_energy[tpl] - ts.peak_cp) / (float)NB;
                 const float noise_k = sqrtf(noise_pw);                 // NaN if negative
@@ -576,11 +579,11 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
                 // into a per-thread local-memory table (reloads would miss the small L1)
                 asm volatile("" : "+f"(wb.x), "+f"(wb.y));
                 float2 x[R3];
-                if (tpl == 0) {          // pass 3 of O'; kept for the other templates
+                if (!MULTI || tpl == 0) {    // pass 3 of O'; kept for the other templates
 #pragma unroll
                     for (int n3 = 0; n3 < R3; ++n3) x[brev(n3, LOG2R3)] = ld8(ab + (uint32_t)n3 * 8u);
                     fft_dit<R3, false>(x);
-                    if (n_tpl > 1) {
+                    if constexpr (MULTI) {
 #pragma unroll
                         for (int k3 = 0; k3 < R3; ++k3) __stcg(&scrO[(size_t)(it * R3 + k3) * T + tid], x[k3]);
                     }
@@ -699,7 +702,7 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
                 }
             }
             if (tid == 0) {
-                TailSlot &ts = tailslot[q * C::MAX_TPL + tpl];
+                TailSlot &ts = tailslot[q * TPL_SLOTS + tpl];
                 const int s = (int)best_lag;
                 ts.peak_cp = __uint_as_float(best_bits);
                 ts.s = s;

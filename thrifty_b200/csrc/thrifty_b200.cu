@@ -309,7 +309,7 @@ int thr_create(const thr_config *cfg, thr_detector **out) {
     bool use_2x = false;
     if (!fastdet && N == 32768 && !(cfg->flags & THR_CFG_GENERIC_KERNEL)) {
         Variant v2;
-        if (thr::pick_variant_2x(N, &v2)) {
+        if (thr::pick_variant_2x(N, NT > 1, &v2)) {
             var = v2;
             use_2x = true;
         }

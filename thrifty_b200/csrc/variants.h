@@ -26,6 +26,6 @@ bool pick_variant_multi(int block_len, Variant *out);    // n_templates >= 1
 bool pick_variant_fastdet(int block_len, Variant *out);  // fastdet semantics (one template)
 bool pick_variant_stage(int block_len, int stages, Variant *out);   // stage-boundary kernels (one template): stages = 1
                                                                     // (thr_sync_batch) or 2 (thr_soa_batch)
-bool pick_variant_2x(int block_len, Variant *out);       // 32768 = 2 x 16384 (pruned-FFT#1 configurations, one template)
+bool pick_variant_2x(int block_len, bool multi, Variant *out);   // 32768 = 2 x 16384 (one / several templates)
 
 }  // namespace thr
