@@ -226,8 +226,10 @@ class PinnedBuffer(object):
 
 # Page-locked staging buffers of the stream readers, kept for the life of the process: pinning costs 0.6-1 ms per MiB and
 # cudaFreeHost / cudaMallocHost now and then stall for 0.2-0.7 s (measured: tools/cli_stalls.py), so a process that
-# reads many `.card` streams pins its two buffers once.  At most _STAGING_KEEP buffers per size stay cached.
+# reads many `.card` streams pins its two buffers once.  At most _STAGING_KEEP buffers per size and _STAGING_MAX_BYTES in
+# total stay cached (page-locked memory is not swappable).
 _STAGING_KEEP = 4
+_STAGING_MAX_BYTES = 256 << 20
 _staging_pool = {}
 _staging_lock = threading.Lock()
 
@@ -250,7 +252,8 @@ def release_staging(buf):
         return
     with _staging_lock:
         cached = _staging_pool.setdefault(buf.nbytes, [])
-        if len(cached) < _STAGING_KEEP:
+        total = sum(size * len(bufs) for size, bufs in _staging_pool.items())
+        if len(cached) < _STAGING_KEEP and total + buf.nbytes <= _STAGING_MAX_BYTES:
             cached.append(buf)
             return
     buf.close()
