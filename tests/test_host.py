@@ -479,3 +479,34 @@ def test_native_toad_text_equals_python_serialize():
         r.txid = int(t)
     assert _native.format_toad(recs, ts, 7, txids=tx) == "".join(r.serialize() + "\n" for r in results).encode()
     assert _native.format_toad(recs[:0], ts[:0], 7) == b""
+
+
+def test_staging_cache_reuses_buffers_and_is_bounded(monkeypatch):
+    """The stream readers' page-locked staging buffers are handed back to a per-process cache (pinning is slow and
+    cudaFreeHost occasionally stalls): same size -> same buffer again; at most _STAGING_KEEP per size and
+    _STAGING_MAX_BYTES in total stay cached, the rest is freed."""
+    import thrifty_b200._native as nat
+
+    class Fake(object):
+        def __init__(self, nbytes):
+            self.nbytes, self.ptr, self.array, self.closed = nbytes, 1, None, False
+
+        def close(self):
+            self.closed, self.ptr = True, None
+
+    monkeypatch.setattr(nat, "PinnedBuffer", Fake)
+    monkeypatch.setattr(nat, "_staging_pool", {})
+    a = nat.acquire_staging(100)
+    nat.release_staging(a)
+    assert nat.acquire_staging(100) is a and not a.closed
+    assert nat.acquire_staging(101) is not a
+    bufs = [nat.acquire_staging(64) for _ in range(nat._STAGING_KEEP + 2)]
+    for b in bufs:
+        nat.release_staging(b)
+    assert sum(b.closed for b in bufs) == 2 and len(nat._staging_pool[64]) == nat._STAGING_KEEP
+    monkeypatch.setattr(nat, "_STAGING_MAX_BYTES", 64 * nat._STAGING_KEEP + 150)
+    big = [nat.acquire_staging(100) for _ in range(2)]
+    for b in big:
+        nat.release_staging(b)
+    assert [b.closed for b in big] == [False, True]             # the second one would exceed the byte bound
+    nat.release_staging(None)                                   # harmless
