@@ -30,6 +30,10 @@
 
 #include "detect_kernel.cuh"
 
+#ifndef THR_2X_SMEM_B
+#define THR_2X_SMEM_B 1     // stage B reads the raw block from the shared-memory stage too (a second TMA fetch of the tile, an
+#endif                      // L2 hit hidden behind the end of stage A) instead of 64 ld.global.nc.u16 per thread and block
+
 namespace thr {
 
 struct Cfg2x {
@@ -215,6 +219,14 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
     };
     if (use_raw && tid == 0 && has_block(0)) issue_tile(0);
     uint32_t par = 0;
+    // The one raw stage serves both stages of the pipeline (THR_2X_SMEM_B): once pass 1 of A(ia) has consumed tile ia, the
+    // stage is refilled with tile ia-1 for B(ia-1) if that block has a carrier (decided one iteration ago, written by this
+    // very thread), else with tile ia+1 for A(ia+1); B refills it with tile ia+1 after its own pass 1.  Every refill comes
+    // behind a BAR_MAIN that follows all threads' wait for the previous fill (mbarrier phase safety).
+    auto refill_after_a = [&](int ia) {              // thread 0, after the pass-1 barrier of A(ia), second half
+        if (THR_2X_SMEM_B && ia >= 1 && fitslot[(ia - 1) & 1].carrier) issue_tile(ia - 1);
+        else if (has_block(ia + 1)) issue_tile(ia + 1);
+    };
 
     // forward pass 1 of half h of block i: samples x[2m + h], m = n1*M + j (from the shared-memory raw
     // stage in stage A, re-read from global/L2 in stage B) -> radix-32 over n1 -> twiddle W_F^{j k1}
@@ -226,6 +238,10 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
         float2 x[32];
         if (use_raw) {
             if constexpr (!stageb) {
+                const uint16_t *rawt = reinterpret_cast<const uint16_t *>(raw_s);
+#pragma unroll
+                for (int n1 = 0; n1 < 32; ++n1) x[brev(n1, 5)] = rawconv(rawt[2 * (n1 * M + tid) + h]);
+            } else if (THR_2X_SMEM_B) {
                 const uint16_t *rawt = reinterpret_cast<const uint16_t *>(raw_s);
 #pragma unroll
                 for (int n1 = 0; n1 < 32; ++n1) x[brev(n1, 5)] = rawconv(rawt[2 * (n1 * M + tid) + h]);
@@ -355,7 +371,7 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
                     pass1(std::false_type{}, std::false_type{}, ia, h, make_float2(1.f, 0.f), nullptr, tenergy);
                     bar_sync(BAR_MAIN, T);
                     // the raw stage is not read again in stage A: fetch the next block's tile into it
-                    if (h == 1 && use_raw && tid == 0 && has_block(ia + 1)) issue_tile(ia + 1);
+                    if (h == 1 && use_raw && tid == 0) refill_after_a(ia);
                     pass2();
                     __syncwarp();
 #pragma unroll 1
@@ -451,7 +467,7 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
                 }
                 bar_sync(BAR_MAIN, T);
                 // the raw stage is not read again in stage A: fetch the next block's tile into it
-                if (h == 1 && use_raw && tid == 0 && has_block(ia + 1)) issue_tile(ia + 1);
+                if (h == 1 && use_raw && tid == 0) refill_after_a(ia);
                 pass2_pruned();
                 __syncwarp();
                 {   // pruned pass 3: warp w owns slabs k1 = 2w, 2w+1: 8 bins x 4 lanes (4 terms each)
@@ -544,6 +560,12 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
                                  + 0.5f * (float)(kpeak & 1) + 0.5f * delta;
             const float turns_h = -((float)kpeak + delta) / (float)NB;
             float unused_energy = 0.f;
+            if (THR_2X_SMEM_B && use_raw) {
+                // tile i again (an L2 hit), requested behind pass 1 of A(i+1); the last block of a CTA has no A(i+1)
+                if (!has_block(i + 1) && tid == 0) issue_tile(i);
+                mbar_wait(&mbar[0], par);
+                par ^= 1;
+            }
 
             // ---- half 0: E' = FFT_F(x'[2m]) -> parked
             pass1(std::true_type{}, std::true_type{}, i, 0, cispi(2.f * turns0), fs.rho, unused_energy);
@@ -565,6 +587,7 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
             // ---- half 1: O' = FFT_F(x'[2m+1]); join, x conj(T)/N, split into A (inverted now) and B (parked)
             pass1(std::true_type{}, std::true_type{}, i, 1, cispi(2.f * (turns0 + turns_h)), fs.rho, unused_energy);
             bar_sync(BAR_MAIN, T);
+            if (THR_2X_SMEM_B && use_raw && tid == 0 && has_block(i + 2)) issue_tile(i + 2);      // for A(i+2)
             pass2();
             __syncwarp();
             // ---- per template: join, x conj(T)/N, the two inverse half-transforms, |c|^2 arg-max
