@@ -229,9 +229,9 @@ detect2x_kernel(const __grid_constant__ DetectParams p) {
     };
 
     // forward pass 1 of half h of block i: samples x[2m + h], m = n1*M + j (from the shared-memory raw
-    // stage in stage A, re-read from global/L2 in stage B) -> radix-32 over n1 -> twiddle W_F^{j k1}
+    // stage in both stages; complex64 input: from global memory) -> radix-32 over n1 -> twiddle W_F^{j k1}
     //   SHIFT : multiply by the phasor rho[n1] * ph0 (mix of stage B, or the integer pre-shift of the zoom band)
-    //   STAGEB: FFT#2 (raw block re-read from global/L2, no energy sum); otherwise FFT#1 from the shared raw stage
+    //   STAGEB: FFT#2 (the tile was fetched a second time, see refill_after_a; no energy sum); otherwise FFT#1
     auto pass1 = [&](auto shift_c, auto stageb_c, int i, int h, float2 ph0, const float2 *rho, float &energy) {
         constexpr bool shift = decltype(shift_c)::value, stageb = decltype(stageb_c)::value;
         const int blk = (int)blockIdx.x + i * (int)gridDim.x;
