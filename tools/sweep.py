@@ -73,7 +73,6 @@ def run(block_len, templates, history, batch, p_signal, steps=64, warmup=4, wind
 def run_card(n_blocks=2048, reps=3):
     """`.card` text -> records: host scan + GPU base64 decode + detect (thr_detect_card) vs the
     host-side decode a Python card_reader does (base64.b64decode + detect_raw)."""
-    import base64
     import io
     import time
     from thrifty_b200 import block_data
