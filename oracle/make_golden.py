@@ -12,7 +12,7 @@ synthetic block configurations it
 It also copies the canonical template ``example/template.npy`` into
 ``tests/golden/template_example.npy`` (a data fixture, 39 KB).
 
-    python oracle/make_golden.py
+    python oracle/make_golden.py [name ...]      # all configurations, or only the named ones
 """
 
 import os
@@ -65,6 +65,11 @@ def configs():
     yield dict(name="n32768_example", block_len=32768, history_len=4920, template=tpl,
                template_id="example", window=(7, 110), n_blocks=16, p_signal=0.7,
                bin_range=(8.0, 109.0), cthresh=(0., 15., 0.), kthresh=(0., 15., 0.))
+    # carrier window wider than the 128-bin zoom band + constant / stddev threshold terms: FFT#1 in full at the block
+    # length that is transformed as two halves (detect_kernel_2x.cuh)
+    yield dict(name="n32768_example_wide_std", block_len=32768, history_len=4920, template=tpl,
+               template_id="example", window=(7, 300), n_blocks=16, p_signal=0.7,
+               bin_range=(9.0, 298.0), cthresh=(1., 12., 2.), kthresh=(0.5, 10., 3.))
 
 
 def run_reference(cfg, raw):
@@ -115,7 +120,10 @@ def main():
     os.makedirs(GOLDEN, exist_ok=True)
     tpl = np.load(os.path.join(REF, "example", "template.npy"))
     np.save(os.path.join(GOLDEN, "template_example.npy"), tpl)
+    only = sys.argv[1:]
     for cfg in configs():
+        if only and cfg["name"] not in only:
+            continue
         raw, truths = synth.make_blocks(cfg["n_blocks"], cfg["block_len"], cfg["history_len"],
                                         cfg.get("gen_template", cfg["template"]),
                                         cfg["p_signal"], seed=synth.SEED0,
@@ -149,6 +157,8 @@ def main():
         print("%-28s blocks=%d signal=%d carrier=%d detected=%d  oracle==reference OK"
               % (cfg["name"], cfg["n_blocks"], nsig, ncar, ndet))
 
+    if only:
+        return
     # one block with full intermediate arrays (yield_data=True) at N=4096
     cfg = [c for c in configs() if c["name"] == "n4096_gold9"][0]
     raw, truths = synth.make_blocks(8, cfg["block_len"], cfg["history_len"], cfg["template"],

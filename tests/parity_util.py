@@ -47,7 +47,7 @@ def load_golden(name):
 
 
 GOLDEN_NAMES = ["n16384_example", "n8192_gold10", "n4096_gold9", "n4096_gold9_wrapwin_std",
-                "n4096_gold9_tone", "n32768_example"]
+                "n4096_gold9_tone", "n32768_example", "n32768_example_wide_std"]
 
 
 def compare_records(got, ref, what=""):
