@@ -125,7 +125,8 @@ typedef struct thr_info {
     char    kernel[64];
 } thr_info;
 
-/* ---- lifecycle (cf. fastcard_new / fastcard_free) ----
+/* ---- lifecycle (cf. fastcard_new / fastcard_free, fastcard/fastcard.h:46-53; CorrDetector's constructor,
+ * fastdet/corr_detector.h:24-45; thrifty/detect.py:40-58 Detector.__init__) ----
  * thr_create fails with THR_ERR_NO_DEVICE unless the device is sm_100 (the library carries sm_100a code only; there is
  * no CPU fallback).  Testing aid: the environment variable THRIFTY_B200_MAX_GRID=<n> caps the persistent grid at n CTAs
  * so that small inputs exercise the multi-block pipeline of a CTA (compute-sanitizer runs).
@@ -185,7 +186,8 @@ int thr_detect_stream_device(thr_detector *det, const uint8_t *d_stream, int64_t
                              const int64_t *d_block_idx, int32_t n_blocks, thr_record *d_out);
 
 /* ---- detection, device-resident buffers (async on the handle's stream) ----
- * n_blocks <= max_batch.  Pointers are device pointers. */
+ * The same call as thr_detect_batch (thrifty/detect.py:60-78 per block) for callers that keep the samples on the GPU;
+ * no counterpart in the reference.  n_blocks <= max_batch.  Pointers are device pointers. */
 int thr_detect_batch_device(thr_detector *det, const uint8_t *d_raw, const int64_t *d_block_idx,
                             int32_t n_blocks, thr_record *d_out);
 int thr_detect_batch_device_c64(thr_detector *det, const float *d_iq, const int64_t *d_block_idx,
@@ -276,13 +278,13 @@ const char *thr_identify_last_error(void);
 int thr_format_toad(const thr_record *recs, const double *timestamps, int64_t n, int64_t stride, int32_t rxid,
                     const int32_t *txids, char *buf, size_t cap, size_t *used);
 
-/* ---- stream / timing plumbing ---- */
+/* ---- stream / timing plumbing (no counterpart in the reference) ---- */
 int thr_set_stream(thr_detector *det, void *cuda_stream);   /* NULL -> handle's own stream */
 int thr_synchronize(thr_detector *det);
 int thr_timer_start(thr_detector *det);                     /* CUDA event on the handle's stream */
 int thr_timer_stop(thr_detector *det, float *elapsed_ms);   /* records, synchronises, returns ms  */
 
-/* ---- memory helpers (so callers need no CUDA binding of their own) ---- */
+/* ---- memory helpers (so callers need no CUDA binding of their own; no counterpart in the reference) ---- */
 void *thr_host_alloc(size_t bytes);                         /* pinned host memory */
 void  thr_host_free(void *p);
 void *thr_device_alloc(int device, size_t bytes);
