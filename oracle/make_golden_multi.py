@@ -7,7 +7,7 @@ container only: imports /root/reference) does exactly that, checks the oracle re
 reference's outputs as tests/golden/detect_n16384_gold11x4.npz.  Inputs are regenerated from seeds by
 tests/parity_util.make_multi_blocks (CRC32 stored).
 
-    python oracle/make_golden_multi.py
+    python oracle/make_golden_multi.py [name ...]      # all of CONFIGS, or only the named ones
 """
 import os
 import sys
@@ -29,14 +29,18 @@ from oracle.make_golden import compare  # noqa: E402
 from thrifty_b200 import synth  # noqa: E402
 import parity_util  # noqa: E402
 
-NAME = "n16384_gold11x4"
-N, BITS, IDX = 16384, 11, (0, 1, 2, 3)
-N_BLOCKS = 320          # > 2 x 148: every persistent CTA of a B200 walks more than one block
-WINDOW, CTH, KTH = (7, 110), (0., 15., 0.), (0., 15., 0.)
-P_SIGNAL, SEED = 0.8, synth.SEED0 + 555
+# name -> (block_len, Gold bits, template indices, blocks, window, carrier / correlation thresholds, p_signal, seed)
+CONFIGS = {
+    # BASELINE config 5; > 2 x 148 blocks: every persistent CTA of a B200 walks more than one block
+    "n16384_gold11x4": (16384, 11, (0, 1, 2, 3), 320, (7, 110), (0., 15., 0.), (0., 15., 0.), 0.8, synth.SEED0 + 555),
+    # block_len 32768 (transformed as two halves, detect_kernel_2x.cuh) with a window too wide for the pruned FFT#1
+    "n32768_gold11x3": (32768, 11, (0, 1, 2), 48, (7, 300), (0., 15., 0.), (0., 15., 0.), 0.8, synth.SEED0 + 556),
+}
 
 
-def main():
+def main(name):
+    NAME = name
+    N, BITS, IDX, N_BLOCKS, WINDOW, CTH, KTH, P_SIGNAL, SEED = CONFIGS[name]
     tpls = np.stack([synth.gold_template(BITS, i) for i in IDX])
     hist = tpls.shape[1] + 6                 # 4914 + 6 = 4920, as example/detector.cfg
     assert tpls.shape[1] == 4914
@@ -66,4 +70,5 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    for cfg_name in (sys.argv[1:] or list(CONFIGS)):
+        main(cfg_name)

@@ -521,6 +521,23 @@ def test_multi_template_n16384_gold11x4_vs_reference_golden():
     det.close()
 
 
+def test_multi_template_n32768_gold11x3_vs_reference_golden():
+    """Three Gold-11 templates at block_len 32768 with a carrier window too wide for the pruned FFT#1 (2 x 16384 kernel,
+    FFT#1 in full, template loop over the parked half spectra) == three independent runs of the reference's own Detector
+    (tests/golden/detect_n32768_gold11x3.npz, oracle/make_golden_multi.py)."""
+    from thrifty_b200._native import NativeDetector
+    cfg, tpls, raw, block_idx, ref, which = parity.load_multi_golden("n32768_gold11x3")
+    det = NativeDetector(cfg["block_len"], cfg["history_len"], tpls, tpls.shape[1], cfg["window"], cfg["cthresh"],
+                         cfg["kthresh"], max_batch=64)
+    assert "detect2x" in det.info()["kernel"] and "multi" in det.info()["kernel"]
+    recs = det.detect_raw(raw, block_idx)
+    for t in range(len(tpls)):
+        assert np.all(recs[:, t]["template_idx"] == t)
+        stats = parity.compare_records(recs[:, t], ref[t], what="n32768 gold11x3 template %d" % t)
+        assert stats["carrier"] == int(ref[t]["carrier_detected"].sum()) and stats["detected"] > 30
+    det.close()
+
+
 def test_raw_stream_card_export(tmp_path):
     """`detect --raw --card-out`: every carrier-positive block of the stream is re-exported as a .card line
     (fastcard/fastcard_cli.c:171-193); detecting that .card gives the same records as the stream did."""

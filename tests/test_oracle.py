@@ -158,12 +158,16 @@ def test_oracle_matches_reference_golden(name):
             np.testing.assert_array_equal(got[f], ref[f][:limit])
 
 
-def test_oracle_matches_reference_multi_template_golden():
-    """BASELINE config 5 (4 Gold-11 templates at N=16384): golden = four independent reference Detectors."""
-    cfg, tpls, raw, block_idx, ref, _ = parity.load_multi_golden()
-    assert ref.shape == (4, cfg["n_blocks"]) and cfg["n_blocks"] > 2 * 148
-    limit = 10
-    for t in (0, 3):
+@pytest.mark.parametrize("name", ["n16384_gold11x4", "n32768_gold11x3"])
+def test_oracle_matches_reference_multi_template_golden(name):
+    """BASELINE config 5 (4 Gold-11 templates at N=16384) and 3 templates at N=32768 with a wide carrier window: golden =
+    one independent reference Detector per template."""
+    cfg, tpls, raw, block_idx, ref, _ = parity.load_multi_golden(name)
+    assert ref.shape == (len(tpls), cfg["n_blocks"])
+    if name == "n16384_gold11x4":
+        assert len(tpls) == 4 and cfg["n_blocks"] > 2 * 148
+    limit = 10 if cfg["block_len"] <= 16384 else 6
+    for t in (0, len(tpls) - 1):
         st = orc.DetectorSettings(cfg["block_len"], cfg["history_len"], tpls.shape[1], cfg["cthresh"], cfg["window"],
                                   tpls[t], cfg["kthresh"])
         got = orc.detect_blocks(st, raw[:limit], block_idx[:limit])
